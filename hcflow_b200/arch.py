@@ -1,0 +1,167 @@
+"""Drop-in network classes: HCFlowNet_SR and HCFlowNet_Rescaling.
+
+Same constructor ``(opt, step=None)``, same keyword ``forward`` and same return values as
+the reference's codes/models/modules/HCFlowNet_SR_arch.py:12-75 and
+HCFlowNet_Rescaling_arch.py:14-54, and the same state_dict layout (modules.py), so the
+reference's model wrappers (HCFlow_SR_model.py:195,208,305,311) and checkpoints work
+unchanged.  The arithmetic runs in the CUDA engine; the modules refuse to run on a CPU.
+
+Extensions (keyword-only, all optional, ignored by the reference's callers):
+  gt=            alias of hr= (the task statement's spelling)
+  eps=           list of unit-normal noise tensors [B,Cz,H,W], deepest level first, used
+                 instead of the torch.normal draws of Basic.py:96-100 (parity / reproducibility)
+  dequant_noise= the U[0,1) tensor used instead of torch.rand of HCFlowNet_SR_arch.py:52
+After a call ``net.last`` holds the un-clamped tensors (hr_raw / z_raw / logdet / ...).
+"""
+import math
+
+import torch
+from torch import nn
+
+from . import modules as M
+from .options import opt_get
+
+
+class _HCFlowBase(nn.Module):
+    SR = True
+
+    def __init__(self, opt, step=None):
+        super().__init__()
+        self.opt = opt
+        hr_size = opt_get(opt, ["datasets", "train", "GT_size"], 160)
+        hr_channel = opt_get(opt, ["network_G", "in_nc"], 3)
+        self.flow = M.FlowNet((hr_size, hr_size, hr_channel), opt, SR=self.SR)
+        self.precision = "fp32"
+        self.use_graph = True
+        self._engines = {}
+        self.last = {}
+
+    # ---- engine management -------------------------------------------------------------
+    def set_precision(self, precision):
+        """"fp32" (CUDA-core exact), "tf32" (tcgen05, 1 pass) or "tf32x3" (tcgen05, 3-pass split)."""
+        assert precision in ("fp32", "tf32", "tf32x3")
+        if precision != self.precision:
+            self.precision = precision
+            self._engines.clear()
+
+    def engine(self, direction, B, h, w, device):
+        from .engine import Engine
+        key = (direction, B, h, w, str(device), self.precision, self.use_graph)
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = Engine(self, direction, B, h, w, device, precision=self.precision, use_graph=self.use_graph)
+            self._engines[key] = eng
+        return eng
+
+    def _check(self, t, name, c=3):
+        if t is None:
+            raise ValueError("{} is required".format(name))
+        if t.dim() != 4 or t.shape[1] != c:
+            raise ValueError("{} must be [B,{},H,W], got {}".format(name, c, tuple(t.shape)))
+        if not t.is_cuda:
+            raise RuntimeError("hcflow_b200 runs on CUDA tensors only (no CPU fallback); got {} on {}".format(
+                name, t.device))
+        return t.detach().to(torch.float32).contiguous()
+
+    def _draw_eps(self, eng, eps_std, eps, device):
+        B = eng.B
+        std = 0.0 if eps_std is None else float(eps_std)
+        for i, (c, H, W) in enumerate(eng.plan.noise_shapes):
+            dst = eng.ext["eps{}".format(i)]
+            if eps is not None:
+                e = eps[i].to(device=device, dtype=torch.float32)
+                assert tuple(e.shape) == (B, c, H, W), (tuple(e.shape), (B, c, H, W))
+                dst.copy_(e * std)
+            else:
+                # the reference's own draw, in its order (Basic.py:96-100)
+                zeros = torch.zeros(B, c, H, W, device=device)
+                dst.copy_(torch.normal(mean=zeros, std=torch.ones_like(zeros) * std))
+
+    def _reverse(self, lr, eps_std, eps):
+        lr = self._check(lr, "lr")
+        B, _, h, w = lr.shape
+        eng = self.engine("reverse", B, h, w, lr.device)
+        with torch.cuda.device(lr.device):
+            eng.ext["lr"].copy_(lr)
+            self._draw_eps(eng, eps_std, eps, lr.device)
+            eng.run()
+            self.last = {"hr_raw": eng.ext["hr_raw"].clone()}
+            return eng.ext["hr"].clone()
+
+
+class HCFlowNet_SR(_HCFlowBase):
+    SR = True
+
+    def __init__(self, opt, step=None):
+        scale = opt_get(opt, ["scale"])
+        if scale not in (4, 8):
+            raise NotImplementedError("Scale {} is not implemented".format(scale))
+        super().__init__(opt, step)
+        self.quant = opt_get(opt, ["quant"], 256)
+        self.quantization = nn.Identity()  # parameter-free in the reference too (Basic.py:194-199)
+
+    def forward(self, hr=None, lr=None, z=None, u=None, eps_std=None, add_gt_noise=False, step=None,
+                reverse=False, training=True, *, gt=None, eps=None, dequant_noise=None):
+        if hr is None and gt is not None:
+            hr = gt
+        if reverse:
+            return self._reverse(lr, eps_std, eps)
+        return self._forward_nll(hr, lr, dequant_noise)
+
+    def _forward_nll(self, hr, lr, dequant_noise):
+        hr = self._check(hr, "hr")
+        lr = self._check(lr, "lr")
+        B, _, H, W = hr.shape
+        s = 2 ** self.flow.L
+        if H % s or W % s:
+            raise ValueError("HR size {}x{} not divisible by {}".format(H, W, s))
+        h, w = H // s, W // s
+        assert tuple(lr.shape) == (B, 3, h, w), (tuple(lr.shape), (B, 3, h, w))
+        eng = self.engine("forward", B, h, w, hr.device)
+        with torch.cuda.device(hr.device):
+            eng.ext["hr"].copy_(hr)
+            eng.ext["lr"].copy_(lr)
+            if dequant_noise is None:
+                dequant_noise = torch.rand(hr.shape, device=hr.device)
+            eng.ext["dequant"].copy_(dequant_noise.to(device=hr.device, dtype=torch.float32))
+            eng.run()
+            objective = eng.logdet.clone()  # fp64 [B]: logdet + log N(fake_lr; lr, e^-6)
+            nll = ((-objective) / float(math.log(2.0) * H * W)).mean().to(torch.float32)
+            self.last = {"z_raw": eng.ext["z_raw"].clone(), "objective": objective}
+            return eng.ext["fake_lr"].clone(), nll
+
+
+class HCFlowNet_Rescaling(_HCFlowBase):
+    SR = False
+
+    def __init__(self, opt, step=None):
+        super().__init__(opt, step)
+        self.quant = opt_get(opt, ["datasets", "train", "quant"], 256)
+
+    def forward(self, hr=None, lr=None, z=None, u=None, eps_std=None, add_gt_noise=False, step=None,
+                reverse=False, training=True, *, gt=None, eps=None):
+        if hr is None and gt is not None:
+            hr = gt
+        if reverse:
+            return self._reverse(lr, eps_std, eps)
+        hr = self._check(hr, "hr")
+        B, _, H, W = hr.shape
+        s = 2 ** self.flow.L
+        if H % s or W % s:
+            raise ValueError("HR size {}x{} not divisible by {}".format(H, W, s))
+        eng = self.engine("forward", B, H // s, W // s, hr.device)
+        with torch.cuda.device(hr.device):
+            eng.ext["hr"].copy_(hr)
+            eng.run()
+            self.last = {"z_raw": eng.ext["z_raw"].clone()}
+            return eng.ext["fake_lr"].clone(), eng.ext["fake_z1"].clone(), eng.ext["fake_z2"].clone()
+
+
+def build_net(opt, step=None):
+    """Equivalent of the reference's networks.define_G (codes/models/networks.py:36-41)."""
+    which = opt["network_G"]["which_model_G"]
+    cls = {"hcflownet_sr": HCFlowNet_SR, "hcflownet_rescaling": HCFlowNet_Rescaling}.get(
+        which.replace("_Net", "").lower())
+    if cls is None:
+        raise NotImplementedError(which)
+    return cls(opt=opt, step=step)

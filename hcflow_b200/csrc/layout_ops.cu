@@ -1,0 +1,143 @@
+// Layout plumbing: NCHW <-> NHWC at the module boundary (with the dequantisation noise /
+// clamp / 8-bit rounding of the arch wrappers folded in), squeeze2d / unsqueeze2d and the
+// Haar analysis / synthesis pair.  All memory-bound, one read + one write per element.
+#include "common.cuh"
+
+namespace hcf {
+
+constexpr int LT = 256;
+
+// thread = (b, y, x); loops channels.  NCHW side is coalesced per channel plane.
+__global__ void __launch_bounds__(LT) nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                          int B, int C, int HW, int ld,
+                                                          const float* __restrict__ noise, float noise_scale) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= B * HW) return;
+  const int b = pix / HW, r = pix % HW;
+  float* d = dst + (size_t)pix * ld;
+  for (int c = 0; c < C; ++c) {
+    const size_t i = ((size_t)b * C + c) * HW + r;
+    float v = src[i];
+    if (noise) v = v + noise[i] * noise_scale;
+    d[c] = v;
+  }
+}
+
+__device__ __forceinline__ float post_op(float v, int post) {
+  if (post >= 1) v = fminf(fmaxf(v, 0.f), 1.f);
+  if (post == 2) v = rintf(v * 255.f) / 255.f;  // torch.round = round-half-even = rintf
+  return v;
+}
+
+__global__ void __launch_bounds__(LT) nhwc_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                          int B, int C, int HW, int ld, int post) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= B * HW) return;
+  const int b = pix / HW, r = pix % HW;
+  const float* s = src + (size_t)pix * ld;
+  for (int c = 0; c < C; ++c) dst[((size_t)b * C + c) * HW + r] = post_op(s[c], post);
+}
+
+// low-res thread (b, y, x): 4C outputs  dst[c*4 + i*2 + j] = src[(2y+i, 2x+j), c]
+__global__ void __launch_bounds__(LT) squeeze_kernel(const float* __restrict__ src, float* __restrict__ dst, int B,
+                                                     int C, int H, int W, int src_ld, int dst_ld, int inverse) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= B * H * W) return;
+  const int x = pix % W, y = (pix / W) % H, b = pix / (W * H);
+  const int W2 = 2 * W, H2 = 2 * H;
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2; ++j) {
+      const size_t hi = ((size_t)(b * H2 + 2 * y + i) * W2 + 2 * x + j);
+      for (int c = 0; c < C; ++c) {
+        if (!inverse) dst[(size_t)pix * dst_ld + c * 4 + i * 2 + j] = src[hi * src_ld + c];
+        else dst[hi * dst_ld + c] = src[(size_t)pix * src_ld + c * 4 + i * 2 + j];
+      }
+    }
+}
+
+// Haar: band k of channel c at low-res channel k*C + c.
+//   k0 = (a+b+c+d)/4, k1 = (a-b+c-d)/4, k2 = (a+b-c-d)/4, k3 = (a-b-c+d)/4
+//   with a=(2y,2x) b=(2y,2x+1) c=(2y+1,2x) d=(2y+1,2x+1)            (Basic.py:455-466)
+__global__ void __launch_bounds__(LT) haar_kernel(const float* __restrict__ src, float* __restrict__ dst, int B,
+                                                  int C, int H, int W, int src_ld, int dst_ld, int inverse) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= B * H * W) return;
+  const int x = pix % W, y = (pix / W) % H, b = pix / (W * H);
+  const int W2 = 2 * W, H2 = 2 * H;
+  const size_t p00 = ((size_t)(b * H2 + 2 * y) * W2 + 2 * x);
+  const size_t p01 = p00 + 1, p10 = p00 + W2, p11 = p10 + 1;
+  for (int c = 0; c < C; ++c) {
+    if (!inverse) {
+      const float a = src[p00 * src_ld + c], bb = src[p01 * src_ld + c];
+      const float cc = src[p10 * src_ld + c], d = src[p11 * src_ld + c];
+      float* o = dst + (size_t)pix * dst_ld;
+      o[0 * C + c] = (a + bb + cc + d) * 0.25f;
+      o[1 * C + c] = (a - bb + cc - d) * 0.25f;
+      o[2 * C + c] = (a + bb - cc - d) * 0.25f;
+      o[3 * C + c] = (a - bb - cc + d) * 0.25f;
+    } else {
+      const float* s = src + (size_t)pix * src_ld;
+      const float k0 = s[0 * C + c], k1 = s[1 * C + c], k2 = s[2 * C + c], k3 = s[3 * C + c];
+      dst[p00 * dst_ld + c] = k0 + k1 + k2 + k3;
+      dst[p01 * dst_ld + c] = k0 - k1 + k2 - k3;
+      dst[p10 * dst_ld + c] = k0 + k1 - k2 - k3;
+      dst[p11 * dst_ld + c] = k0 - k1 - k2 + k3;
+    }
+  }
+}
+
+static int check_layout(const hcf_layout_args* a) {
+  HCF_REQUIRE(a && a->src && a->dst, "layout: null args");
+  HCF_REQUIRE(a->B > 0 && a->C > 0 && a->H > 0 && a->W > 0 && a->ld >= a->C, "layout: shape");
+  return 0;
+}
+
+static int check_squeeze(const hcf_squeeze_args* a, bool inverse) {
+  HCF_REQUIRE(a && a->src && a->dst, "squeeze: null args");
+  HCF_REQUIRE(a->B > 0 && a->C > 0 && a->H > 0 && a->W > 0, "squeeze: shape");
+  const int lo = 4 * a->C, hi = a->C;
+  HCF_REQUIRE(a->src_ld >= (inverse ? lo : hi) && a->dst_ld >= (inverse ? hi : lo), "squeeze: ld");
+  return 0;
+}
+
+}  // namespace hcf
+
+extern "C" int hcf_nchw_to_nhwc(const hcf_layout_args* a, void* stream) {
+  using namespace hcf;
+  int rc = check_layout(a);
+  if (rc) return rc;
+  const int n = a->B * a->H * a->W;
+  nchw_to_nhwc_kernel<<<ceil_div(n, LT), LT, 0, (cudaStream_t)stream>>>(a->src, a->dst, a->B, a->C, a->H * a->W,
+                                                                        a->ld, a->noise, a->noise_scale);
+  return finish_launch("hcf_nchw_to_nhwc");
+}
+
+extern "C" int hcf_nhwc_to_nchw(const hcf_layout_args* a, void* stream) {
+  using namespace hcf;
+  int rc = check_layout(a);
+  if (rc) return rc;
+  HCF_REQUIRE(a->post >= 0 && a->post <= 2, "nhwc_to_nchw: post %d", a->post);
+  const int n = a->B * a->H * a->W;
+  nhwc_to_nchw_kernel<<<ceil_div(n, LT), LT, 0, (cudaStream_t)stream>>>(a->src, a->dst, a->B, a->C, a->H * a->W,
+                                                                        a->ld, a->post);
+  return finish_launch("hcf_nhwc_to_nchw");
+}
+
+static int squeeze_like(const hcf_squeeze_args* a, void* stream, int inverse, int haar, const char* what) {
+  using namespace hcf;
+  int rc = check_squeeze(a, inverse != 0);
+  if (rc) return rc;
+  const int n = a->B * a->H * a->W;
+  if (haar)
+    haar_kernel<<<ceil_div(n, LT), LT, 0, (cudaStream_t)stream>>>(a->src, a->dst, a->B, a->C, a->H, a->W,
+                                                                  a->src_ld, a->dst_ld, inverse);
+  else
+    squeeze_kernel<<<ceil_div(n, LT), LT, 0, (cudaStream_t)stream>>>(a->src, a->dst, a->B, a->C, a->H, a->W,
+                                                                     a->src_ld, a->dst_ld, inverse);
+  return finish_launch(what);
+}
+
+extern "C" int hcf_squeeze2d(const hcf_squeeze_args* a, void* s) { return squeeze_like(a, s, 0, 0, "hcf_squeeze2d"); }
+extern "C" int hcf_unsqueeze2d(const hcf_squeeze_args* a, void* s) { return squeeze_like(a, s, 1, 0, "hcf_unsqueeze2d"); }
+extern "C" int hcf_haar_forward(const hcf_squeeze_args* a, void* s) { return squeeze_like(a, s, 0, 1, "hcf_haar_forward"); }
+extern "C" int hcf_haar_inverse(const hcf_squeeze_args* a, void* s) { return squeeze_like(a, s, 1, 1, "hcf_haar_inverse"); }

@@ -1,0 +1,274 @@
+"""Host side of the CUDA engine: lowers a launch plan (plan.py) to C-ABI calls.
+
+torch is used for what the task calls plumbing only: device memory (buffers, weights),
+streams, CUDA-graph capture and the RNG draws the reference itself makes with torch.
+Every arithmetic op of the hot path is a kernel of libhcflow_b200.so.  There is no CPU or
+eager-torch fallback: constructing an Engine without CUDA or without the library raises.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib as L
+from . import plan as P
+from . import prep
+
+
+class Engine:
+    """One compiled plan = (net weights, direction, B, h, w, precision) on one device."""
+
+    def __init__(self, net, direction, B, h, w, device, precision="fp32", use_graph=True):
+        if not torch.cuda.is_available():
+            raise L.HcfError("hcflow_b200 needs a CUDA device (no CPU fallback)")
+        self.lib = L.load()
+        self.net = net
+        self.device = torch.device(device)
+        self.direction, self.B, self.h, self.w = direction, B, h, w
+        self.precision = precision
+        self.plan = P.build_plan(net, direction, B, h, w)
+        self.use_graph = use_graph
+        self.graph = None
+        self._keep = []          # ctypes structs must outlive the launches
+        self._tc_plans = []
+        self.weights = {}
+        self.bufs = {}
+        self.ext = {}
+        self.calls = []
+        self.n_tc = 0
+        self.n_fp32_conv = 0
+        with torch.cuda.device(self.device):
+            self._alloc()
+            self.load_weights()
+            self._lower()
+
+    # ------------------------------------------------------------------ memory
+    def _alloc(self):
+        pl, dev, B = self.plan, self.device, self.B
+        for name, b in pl.bufs.items():
+            # zero-init so that never-written padding can not inject NaNs
+            self.bufs[name] = torch.zeros(B, b.H, b.W, b.C, dtype=torch.float32, device=dev)
+        L0 = self.net.flow.L
+        if pl.direction == "reverse":
+            self.ext["lr"] = torch.zeros(B, 3, self.h, self.w, dtype=torch.float32, device=dev)
+            for i, (c, H, W) in enumerate(pl.noise_shapes):
+                self.ext["eps{}".format(i)] = torch.zeros(B, c, H, W, dtype=torch.float32, device=dev)
+        else:
+            s = 2 ** L0
+            self.ext["hr"] = torch.zeros(B, 3, self.h * s, self.w * s, dtype=torch.float32, device=dev)
+            if pl.sr:
+                self.ext["dequant"] = torch.zeros_like(self.ext["hr"])
+                self.ext["lr"] = torch.zeros(B, 3, self.h, self.w, dtype=torch.float32, device=dev)
+        for name, (c, H, W) in pl.outputs.items():
+            self.ext[name] = torch.zeros(B, c, H, W, dtype=torch.float32, device=dev)
+        self.logdet = torch.zeros(B, dtype=torch.float64, device=dev)
+        self.logdet_init = torch.zeros(B, dtype=torch.float64, device=dev)
+
+    def _vptr(self, v):
+        t = self.bufs[v.buf.name]
+        return t.data_ptr() + 4 * v.off, v.buf.C
+
+    # ------------------------------------------------------------------ weights
+    def weight_signature(self):
+        return sum(p._version for p in self.net.parameters()), id(self.net)
+
+    def load_weights(self):
+        """(Re)pack every parameter the plan touches. Device addresses stay stable on reload."""
+        sd = {k: v.detach().cpu() for k, v in self.net.state_dict().items()}
+        dev = self.device
+
+        def put(key, t):
+            t = t.contiguous()
+            if key in self.weights and self.weights[key].shape == t.shape:
+                self.weights[key].copy_(t)
+            else:
+                self.weights[key] = t.to(dev)
+
+        for op in self.plan.ops:
+            if isinstance(op, P.ConvOp):
+                npad = prep.npad_for(op.cout)
+                segc = [v.C for v, _ in op.segs]
+                put(self._wkey(op), prep.pack_conv_weight(sd[op.weight], segc, npad))
+                if op.bias:
+                    put(op.bias + "@{}".format(npad), prep.pad_vec(prep.derive(sd, op.bias), npad, 0.0))
+                if op.scale:
+                    put(op.scale + "@{}".format(npad), prep.pad_vec(prep.derive(sd, op.scale), npad, 1.0))
+            elif isinstance(op, P.StepOp):
+                for key in (op.w, op.an_scale, op.an_bias):
+                    if key:
+                        put(key, prep.derive(sd, key))
+        self._sd_cpu = sd
+        self.logdet_const = prep.logdet_constant(sd, self.plan.logdet_terms)
+        if self.plan.direction == "forward" and self.plan.sr:
+            s = 2 ** self.net.flow.L
+            self.logdet_const += prep.quant_logdet(self.net.quant, self.h * s * self.w * s)
+        self.logdet_init.fill_(self.logdet_const)
+        self._sig = self.weight_signature()
+
+    @staticmethod
+    def _wkey(op):
+        return "{}|{}".format(op.weight, ",".join(str(v.C) for v, _ in op.segs))
+
+    # ------------------------------------------------------------------ lowering
+    def _lower(self):
+        lib = self.lib
+        B = self.B
+        for op in self.plan.ops:
+            if isinstance(op, P.ConvOp):
+                a = L.ConvArgs()
+                a.B, a.H, a.W, a.nseg = B, op.H, op.W, len(op.segs)
+                kpad = 0
+                for i, (v, up) in enumerate(op.segs):
+                    ptr, ld = self._vptr(v)
+                    a.seg[i].ptr, a.seg[i].ld, a.seg[i].C, a.seg[i].up_shift = ptr, ld, v.C, up
+                    kpad += prep.seg_pad(v.C)
+                npad = prep.npad_for(op.cout)
+                a.ks, a.kpad, a.cout, a.npad = op.ks, kpad, op.cout, npad
+                a.w = self.weights[self._wkey(op)].data_ptr()
+                a.bias = self.weights[op.bias + "@{}".format(npad)].data_ptr() if op.bias else None
+                a.scale = self.weights[op.scale + "@{}".format(npad)].data_ptr() if op.scale else None
+                a.act = op.act
+                a.out, a.out_ld = self._vptr(op.out)
+                if op.out2 is not None:
+                    a.out2, a.out2_ld = self._vptr(op.out2)
+                if op.res1 is not None:
+                    a.res1, a.res1_ld = self._vptr(op.res1)
+                    a.alpha1 = op.alpha1
+                if op.res2 is not None:
+                    a.res2, a.res2_ld = self._vptr(op.res2)
+                    a.alpha2 = op.alpha2
+                self._keep.append(a)
+                tc = self._try_tc(op, a)
+                if tc is not None:
+                    self.calls.append((lib.hcf_conv_tc_run, tc, "conv_tc:" + op.tag))
+                    self.n_tc += 1
+                else:
+                    self.calls.append((lib.hcf_conv_fp32, C.byref(a), "conv_fp32:" + op.tag))
+                    self.n_fp32_conv += 1
+            elif isinstance(op, P.StepOp):
+                a = L.StepArgs()
+                a.npix, a.pix_per_img = B * op.H * op.W, op.H * op.W
+                a.z, a.z_ld = self._vptr(op.z)
+                a.C = op.z.C
+                if op.h is not None:
+                    a.h, a.h_ld = self._vptr(op.h)
+                a.mode = 0 if op.mode == "affine" else 1
+                a.n_pass = op.n_pass
+                a.w = self.weights[op.w].data_ptr() if op.w else None
+                a.an_scale = self.weights[op.an_scale].data_ptr() if op.an_scale else None
+                a.an_bias = self.weights[op.an_bias].data_ptr() if op.an_bias else None
+                a.logdet = self.logdet.data_ptr() if self.plan.uses_logdet else None
+                fn = {"inverse": lib.hcf_step_inverse, "forward_head": lib.hcf_step_forward_head,
+                      "forward_coupling": lib.hcf_step_forward_coupling}[op.variant]
+                self._keep.append(a)
+                self.calls.append((fn, C.byref(a), "step_" + op.variant))
+            elif isinstance(op, P.PriorOp):
+                a = L.PriorArgs()
+                a.B, a.H, a.W, a.Cz = B, op.H, op.W, op.z.C
+                a.h, a.h_ld = self._vptr(op.h)
+                a.atan_logscale = 1 if op.atan_logscale else 0
+                a.z, a.z_ld = self._vptr(op.z)
+                if op.variant == "sample":
+                    a.eps_nchw = self.ext["eps{}".format(op.eps_index)].data_ptr()
+                    fn = lib.hcf_prior_sample
+                elif op.variant == "logp":
+                    a.logdet = self.logdet.data_ptr()
+                    fn = lib.hcf_prior_logp
+                else:
+                    a.out_nchw = self.ext[op.out_name].data_ptr()
+                    fn = lib.hcf_prior_standardize
+                self._keep.append(a)
+                self.calls.append((fn, C.byref(a), "prior_" + op.variant))
+            elif isinstance(op, P.LayoutOp):
+                if op.variant in ("ingest", "egress"):
+                    a = L.LayoutArgs()
+                    a.B, a.C, a.H, a.W = B, op.C, op.H, op.W
+                    if op.variant == "ingest":
+                        a.src = self.ext[op.src].data_ptr()
+                        a.dst, a.ld = self._vptr(op.dst)
+                        if op.noise:
+                            a.noise = self.ext[op.noise].data_ptr()
+                            a.noise_scale = op.noise_scale
+                        fn = lib.hcf_nchw_to_nhwc
+                    else:
+                        a.src, a.ld = self._vptr(op.src)
+                        a.dst = self.ext[op.dst].data_ptr()
+                        a.post = op.post
+                        fn = lib.hcf_nhwc_to_nchw
+                else:
+                    a = L.SqueezeArgs()
+                    a.B, a.C, a.H, a.W = B, op.C, op.H, op.W
+                    a.src, a.src_ld = self._vptr(op.src)
+                    a.dst, a.dst_ld = self._vptr(op.dst)
+                    fn = {"squeeze": lib.hcf_squeeze2d, "unsqueeze": lib.hcf_unsqueeze2d,
+                          "haar_fwd": lib.hcf_haar_forward, "haar_inv": lib.hcf_haar_inverse}[op.variant]
+                self._keep.append(a)
+                self.calls.append((fn, C.byref(a), "layout_" + op.variant))
+            elif isinstance(op, P.DiracLogpOp):
+                x, m, ld = self.ext[op.x_name].data_ptr(), self.ext[op.mean_name].data_ptr(), self.logdet.data_ptr()
+                lg, n = op.logs, op.n
+
+                def call(_unused, stream, x=x, m=m, lg=lg, n=n, ld=ld):
+                    return lib.hcf_gauss_logp_const(x, m, lg, B, n, ld, stream)
+                self.calls.append((call, None, "dirac_logp"))
+            else:
+                raise TypeError(op)
+
+    def _try_tc(self, op, a):
+        """Tensor-core plan for this conv if the precision mode asks for it and the shape fits."""
+        if self.precision == "fp32":
+            return None
+        if not self.lib.hcf_conv_tc_supported(C.byref(a)):
+            return None
+        passes = {"tf32": 1, "tf32x3": 3}[self.precision]
+        key = self._wkey(op) + "#tc"
+        if key not in self.weights:
+            w = self._sd_cpu[op.weight].float().contiguous()
+            cout, kin = w.shape[0], w.shape[1]
+            nbytes = self.lib.hcf_conv_tc_weight_bytes(kin, cout)
+            img = torch.zeros(nbytes // 4, dtype=torch.float32)
+            L.check(self.lib.hcf_conv_tc_pack_weights(w.data_ptr(), kin, cout, img.data_ptr()), "tc_pack")
+            self.weights[key] = img.to(self.device)
+        handle = C.c_void_p()
+        L.check(self.lib.hcf_conv_tc_plan_create(C.byref(a), self.weights[key].data_ptr(), passes, C.byref(handle)),
+                "tc_plan_create")
+        self._tc_plans.append(handle)
+        return handle
+
+    # ------------------------------------------------------------------ execution
+    def _launch_all(self):
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        if self.plan.uses_logdet:
+            self.logdet.copy_(self.logdet_init)
+        for fn, arg, what in self.calls:
+            rc = fn(arg, stream)
+            if rc != 0:
+                L.check(rc, what)
+
+    def run(self):
+        """Run the plan on the current stream (inputs already in self.ext)."""
+        if self.weight_signature() != self._sig:
+            self.load_weights()
+        if not self.use_graph:
+            self._launch_all()
+            return
+        if self.graph is None:
+            # warm-up outside capture (module load, lazy allocations), then capture
+            self._launch_all()
+            torch.cuda.current_stream(self.device).synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._launch_all()
+            self.graph = g
+        self.graph.replay()
+
+    @property
+    def launches_per_run(self):
+        return len(self.calls)
+
+    def __del__(self):
+        try:
+            for hnd in self._tc_plans:
+                self.lib.hcf_conv_tc_plan_destroy(hnd)
+        except Exception:
+            pass

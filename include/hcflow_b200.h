@@ -1,0 +1,204 @@
+/*
+ * hcflow_b200 -- C ABI of the B200 (sm_100a) HCFlow flow-step engine.
+ *
+ * The reference (JingyunLiang/HCFlow) is pure Python on top of torch; it has no FFI of
+ * its own.  The operators below are the device-side replacements for the torch calls its
+ * hot path makes; each entry cites the reference lines it replaces (paths relative to
+ * codes/models/modules/).  The host side (hcflow_b200/engine.py) binds them with ctypes
+ * and drives them from drop-in HCFlowNet_SR / HCFlowNet_Rescaling modules.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 unless stated; `stream` is a cudaStream_t;
+ *   - activations are NHWC ("pixel-major"): element (b,y,x,c) of a view lives at
+ *     ptr[((b*H + y)*W + x)*ld + c]; a view is a channel slice of a wider buffer, so
+ *     `ptr` already includes the channel offset and `ld` is the buffer's channel count
+ *     (this is what makes torch.cat / Split / dense-concat zero-copy);
+ *   - functions return 0 on success, a cudaError_t value (>0) if a launch failed, or a
+ *     negative HCF_E* code for a rejected argument; hcf_last_error() gives the text;
+ *   - nothing here synchronises the device or allocates memory, except the *_plan_*
+ *     functions, which own small host/device descriptors.
+ */
+#ifndef HCFLOW_B200_H_
+#define HCFLOW_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HCF_EINVAL (-1)   /* bad argument (shape / alignment / unsupported size) */
+#define HCF_ENOTSUP (-2)  /* combination not implemented by this kernel */
+
+#define HCF_ABI_VERSION 1
+
+/* ---- introspection -------------------------------------------------------------- */
+int hcf_abi_version(void);
+const char* hcf_last_error(void);
+/* number of kernel launches issued through this library since the last reset */
+uint64_t hcf_launch_count(void);
+void hcf_launch_count_reset(void);
+
+/* ---- convolution ---------------------------------------------------------------- */
+/* One input segment of a (virtually concatenated) conv input.  `up_shift` s means the
+ * segment is stored at 1/2^s resolution and read with nearest-neighbour upsampling
+ * (replaces F.interpolate(..., mode='nearest') + torch.cat, FlowNet_SR_x4.py:98,117,
+ * FlowNet_SR_x8.py:109-113,132-137). */
+typedef struct {
+  const float* ptr;
+  int32_t ld;
+  int32_t C;
+  int32_t up_shift;
+  int32_t _pad;
+} hcf_seg;
+
+#define HCF_ACT_NONE 0
+#define HCF_ACT_RELU 1
+#define HCF_ACT_LRELU 2 /* negative slope 0.2 */
+
+/* Stride-1 "same" convolution, ks in {1,3}, over the channel-concatenation of up to three
+ * segments, with a fused epilogue:
+ *     v = acc; v = (v + bias[c]) * scale[c]; v = act(v);
+ *     if (res1) v = v*alpha1 + res1;  if (res2) v = v*alpha2 + res2;
+ *     out = v; if (out2) out2 = v;
+ * Replaces nn.Conv2d / F.conv2d + the elementwise ops around it:
+ *   Basic.py:49-53  (Conv2d + ActNorm: bias=actnorm.bias, scale=exp(actnorm.logs)) + ReLU :443-444
+ *   Basic.py:70-72  (Conv2dZeros: bias, scale=exp(3*logs))
+ *   Basic.py:349-356, 377-383 (dense convs + LeakyReLU 0.2, x5*0.2 + x), :394-398 (RRDB out*0.2 + x)
+ *   ConditionalFlow.py:99-110 (conv_first, trunk_conv1 + skip)
+ * Weights are pre-packed as w[tap][k][n]: tap = ky*ks+kx, k runs over the segments with
+ * each segment zero-padded to a multiple of 8 channels (kpad = total), n < npad where
+ * npad is 16, 32 or a multiple of 64 and >= cout.  bias / scale have npad entries. */
+typedef struct {
+  int32_t B, H, W;
+  int32_t nseg;
+  hcf_seg seg[3];
+  int32_t ks;
+  int32_t kpad;
+  int32_t cout;
+  int32_t npad;
+  const float* w;
+  const float* bias;  /* may be NULL */
+  const float* scale; /* may be NULL */
+  int32_t act;
+  int32_t out_ld;
+  float* out;
+  float* out2; /* may be NULL */
+  int32_t out2_ld;
+  int32_t res1_ld;
+  const float* res1; /* may be NULL */
+  const float* res2; /* may be NULL */
+  int32_t res2_ld;
+  float alpha1;
+  float alpha2;
+  int32_t _pad;
+} hcf_conv_args;
+
+/* fp32 CUDA-core (FFMA) implementation: exact-fp32 parity mode and odd shapes. */
+int hcf_conv_fp32(const hcf_conv_args* a, void* stream);
+
+/* tcgen05 tensor-core implementation (3x3, every segment C % 32 == 0, up_shift == 0,
+ * cout in {16,32,64}).  `wtc` is the UMMA-ready weight image produced by
+ * hcf_conv_tc_pack_weights; passes = 1 (TF32) or 3 (3xTF32 split, ~fp32 accuracy).
+ * A plan owns the TMA tensor maps for one (args) tuple. */
+typedef struct hcf_conv_tc_plan hcf_conv_tc_plan;
+int hcf_conv_tc_supported(const hcf_conv_args* a);
+/* bytes needed for the packed weight image of (kin channels, cout) */
+int64_t hcf_conv_tc_weight_bytes(int32_t kin, int32_t cout);
+/* host-side packing: w_oihw [cout][kin][3][3] fp32 -> image (host pointers) */
+int hcf_conv_tc_pack_weights(const float* w_oihw, int32_t kin, int32_t cout, float* image);
+int hcf_conv_tc_plan_create(const hcf_conv_args* a, const float* wtc, int32_t passes,
+                            hcf_conv_tc_plan** out);
+int hcf_conv_tc_run(const hcf_conv_tc_plan* p, void* stream);
+void hcf_conv_tc_plan_destroy(hcf_conv_tc_plan* p);
+
+/* ---- flow step ------------------------------------------------------------------ */
+#define HCF_COUPLING_AFFINE 0       /* z[:, :n_pass] passes; rest gets affine from interleaved h */
+#define HCF_COUPLING_SHIFT_FIRST3 1 /* z[:, :3] gets a pure shift h[0..2] (Affine3shift, LRvsothers=False) */
+
+typedef struct {
+  int32_t npix;        /* B*H*W */
+  int32_t pix_per_img; /* H*W */
+  float* z;            /* in place */
+  int32_t z_ld;
+  int32_t C;
+  const float* h; /* coupling sub-net output: (shift,scale) interleaved, 2*(C-n_pass) ch; or 3 ch */
+  int32_t h_ld;
+  int32_t mode;
+  int32_t n_pass;
+  int32_t _pad;
+  const float* w;        /* [C][C] row-major mixing matrix (W on forward, W^-1 on inverse); NULL = none */
+  const float* an_scale; /* [C] exp(+logs) forward, exp(-logs) inverse */
+  const float* an_bias;  /* [C] */
+  double* logdet;        /* [B], forward only (may be NULL) */
+} hcf_step_args;
+
+/* Reverse FlowStep tail (FlowStep.py:53-64): z2 = z2*exp(-0.318*atan(2*scale)) - shift
+ * (AffineCouplings.py:65-87, :148-160), z = W^-1 z (Permutations.py:72-74,105),
+ * z = z*exp(-logs) - bias (ActNorms.py:90-93). */
+int hcf_step_inverse(const hcf_step_args* a, void* stream);
+/* Forward FlowStep head (FlowStep.py:40-47): z = (z + bias)*exp(logs) (ActNorms.py:84-88),
+ * z = W z (Permutations.py:100).  The data-independent log-dets are added by the host. */
+int hcf_step_forward_head(const hcf_step_args* a, void* stream);
+/* Forward coupling (AffineCouplings.py:28-63, :117-139): z2 = (z2 + shift)*exp(ls);
+ * logdet[b] += sum ls. */
+int hcf_step_forward_coupling(const hcf_step_args* a, void* stream);
+
+/* ---- prior (ConditionalFlow.py:44-96, Basic.py:75-100) -------------------------- */
+typedef struct {
+  int32_t B, H, W;
+  int32_t Cz;
+  const float* h; /* Conv2dZeros output, 2*Cz ch: mean = h[2c], second = h[2c+1] (cross split, thops.py:43-44) */
+  int32_t h_ld;
+  int32_t atan_logscale; /* 0: logs = second (SR);  1: logs = 0.318*atan(2*second) (Rescaling, :80,:89) */
+  const float* eps_nchw; /* [B,Cz,H,W] noise already multiplied by eps_std; NULL = zeros */
+  float* z;              /* NHWC view, Cz channels */
+  int32_t z_ld;
+  int32_t _pad;
+  double* logdet;  /* [B] (logp) */
+  float* out_nchw; /* [B,Cz,H,W] (standardize) */
+} hcf_prior_args;
+int hcf_prior_sample(const hcf_prior_args* a, void* stream);      /* z = mean + exp(logs)*eps */
+int hcf_prior_logp(const hcf_prior_args* a, void* stream);        /* logdet[b] += log N(z; mean, exp(logs)) */
+int hcf_prior_standardize(const hcf_prior_args* a, void* stream); /* out = (z-mean)*exp(-logs) */
+
+/* ---- layout / plumbing ---------------------------------------------------------- */
+typedef struct {
+  int32_t B, C, H, W;
+  const float* src;
+  float* dst;
+  int32_t ld;   /* NHWC side channel stride */
+  int32_t post; /* nhwc_to_nchw: 0 raw, 1 clamp[0,1], 2 clamp + round to 1/255 (Basic.py:186-192) */
+  const float* noise; /* nchw_to_nhwc: optional NCHW tensor added as src + noise*noise_scale
+                         (HCFlowNet_SR_arch.py:52) */
+  float noise_scale;
+  int32_t _pad;
+} hcf_layout_args;
+int hcf_nchw_to_nhwc(const hcf_layout_args* a, void* stream);
+int hcf_nhwc_to_nchw(const hcf_layout_args* a, void* stream);
+
+typedef struct {
+  int32_t B, C, H, W; /* C,H,W of the LOW-resolution (squeezed) side is (4C? no:) see below */
+  const float* src;
+  int32_t src_ld;
+  int32_t dst_ld;
+  float* dst;
+} hcf_squeeze_args;
+/* squeeze2d (Basic.py:127-140): src [B,2H,2W,C] -> dst [B,H,W,4C], dst[..., c*4+i*2+j] = src[2y+i, 2x+j, c].
+ * B,C,H,W describe: C = channels of the high-res side, H,W = low-res size. */
+int hcf_squeeze2d(const hcf_squeeze_args* a, void* stream);
+int hcf_unsqueeze2d(const hcf_squeeze_args* a, void* stream); /* Basic.py:143-157, src low-res 4C -> dst high-res C */
+/* Haar (Basic.py:470-487): forward src [B,2H,2W,C] -> dst [B,H,W,4C] with dst[..., k*C+c] = band k of channel c;
+ * inverse the other way. */
+int hcf_haar_forward(const hcf_squeeze_args* a, void* stream);
+int hcf_haar_inverse(const hcf_squeeze_args* a, void* stream);
+
+/* logdet[b] += sum_{c,h,w} log N(x; mean, exp(logs)) with a constant logs, all NCHW
+ * (HCFlowNet_SR_arch.py:63 with logs = -6). n = C*H*W elements per image. */
+int hcf_gauss_logp_const(const float* x, const float* mean, float logs, int32_t B, int32_t n,
+                         double* logdet, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HCFLOW_B200_H_ */
