@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""Benchmark of the HCFlow inverse (sampling) pass -- BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp32|tf32|tf32x3]
+    python bench.py --impl reference ...      # the reference algorithm on the host CPU cores
+
+Workload (configs[1] of BASELINE.json): 4x SR, B=16 synthetic 40x40 LR tiles per GPU ->
+160x160 HR, temperature 0.8, synthetic weights (hcflow_b200.synth, seed 1).  With N>1 every
+rank runs its own shard of a 16*N batch (weak scaling, no data-path collective: images are
+independent) and the time is the max over ranks.
+
+One JSON line on stdout (rank 0).  `value` = device-resident throughput (inputs already in
+HBM, whole pass replayed as one CUDA graph, per-step CUDA events, L2 flushed between steps);
+`e2e` = the same metric through the public module call with pinned-host LR in and HR out.
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "HR megapixels/sec inverse pass (4x SR)"
+UNIT = "MP/s"
+LR_HW = 40
+SCALE = 4
+B_PER_GPU = 16
+HEAT = 0.8
+WORKLOAD = "configs[1]: 4x SR inverse, B=16/GPU, 40x40 LR -> 160x160 HR, T=0.8"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained"),
+                "hbm_gbs": d["hbm_gbs"], "source": "measured"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.mask, self.stop_flag, self.max_mhz, self.ok = index, [], 0, False, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        while self.ok and not self.stop_flag:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                try:
+                    self.mask |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    self.mask |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz,
+                "reasons": [n for b, n in self.REASONS.items() if self.mask & b]}
+
+
+# --------------------------------------------------------------------------- CPU arms
+def oracle_inverse_mps(batch, budget_s, warmup, steps=None):
+    """Times the oracle (CPU restatement of the reference algorithm) on all host threads."""
+    from hcflow_b200 import options as popt, synth
+    from hcflow_b200.arch import build_net
+    from oracle import hcflow_oracle as orc
+    opt = popt.load_config("sr_x4")
+    net = build_net(opt)
+    sd = synth.synthetic_state_dict(net.state_dict(), seed=1)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    lr = synth.synthetic_lr(batch, LR_HW, LR_HW, seed=0)
+    eps = [HEAT * e for e in synth.synthetic_noise(orc.noise_shapes(opt, batch, LR_HW, LR_HW, True))]
+    times = []
+    with torch.no_grad():
+        for _ in range(warmup):
+            orc.sr_reverse(lr, sd, opt, eps)
+        t_end = time.perf_counter() + budget_s
+        while True:
+            t0 = time.perf_counter()
+            orc.sr_reverse(lr, sd, opt, eps)
+            times.append(time.perf_counter() - t0)
+            if steps is not None and len(times) >= steps:
+                break
+            if steps is None and (time.perf_counter() > t_end or len(times) >= 50):
+                break
+    mp = batch * (LR_HW * SCALE) ** 2 / 1e6
+    return mp, times, cores
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = 2
+    mp, times, cores = oracle_inverse_mps(batch, budget_s=0, warmup=max(1, min(args.warmup, 2)), steps=args.steps)
+    total = sum(times)
+    value = mp * len(times) / total
+    sample = "{} timed passes of B={} (of the B=16 workload), 40x40 LR -> 160x160 HR".format(len(times), batch)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference is pure Python/torch and /root/reference is absent on the GPU box: this arm times "
+                "oracle/hcflow_oracle.py (same torch CPU ops, bit-exact vs the reference goldens)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- our arm
+def conv_flops(plan, B):
+    from hcflow_b200 import plan as P
+    total = 0.0
+    for op in plan.ops:
+        if isinstance(op, P.ConvOp):
+            cin = sum(v.C for v, _ in op.segs)
+            total += 2.0 * B * op.H * op.W * op.ks * op.ks * cin * op.cout
+    return total
+
+
+def per_class_times(eng):
+    """One eager (non-graph) pass with a CUDA-event pair around every launch, on the launching
+    stream; returns {class: (n, ms, flops)}."""
+    from hcflow_b200 import plan as P
+    ops = eng.plan.ops
+    st = torch.cuda.current_stream()
+    pairs = []
+    if eng.plan.uses_logdet:
+        eng.logdet.copy_(eng.logdet_init)
+    for (fn, arg, what), op in zip(eng.calls, ops):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        rc = fn(arg, st.cuda_stream)
+        b.record(st)
+        assert rc == 0, what
+        fl = 0.0
+        if isinstance(op, P.ConvOp):
+            cin = sum(v.C for v, _ in op.segs)
+            fl = 2.0 * eng.B * op.H * op.W * op.ks * op.ks * cin * op.cout
+        pairs.append((what.split(":")[0], a, b, fl))
+    torch.cuda.synchronize()
+    out = {}
+    for cls, a, b, fl in pairs:
+        n, ms, f = out.get(cls, (0, 0.0, 0.0))
+        out[cls] = (n + 1, ms + a.elapsed_time(b), f + fl)
+    return out
+
+
+def run_ours(args):
+    from hcflow_b200 import dist as hd, options as popt, synth
+    from hcflow_b200.arch import build_net
+    from oracle import hcflow_oracle as orc  # noise shapes helper + cpu_baseline leg only
+    rank, local, world = hd.init_from_env()
+    assert world == args.gpus or world == 1, (world, args.gpus)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    opt = popt.load_config("sr_x4")
+    net = build_net(opt)
+    net.load_state_dict(synth.synthetic_state_dict(net.state_dict(), seed=1), strict=True)
+    net = net.to(dev).eval()
+    net.set_precision(args.precision)
+    B = B_PER_GPU
+    HR = LR_HW * SCALE
+    lr = synth.synthetic_lr(B, LR_HW, LR_HW, seed=rank)
+    unit = synth.synthetic_noise(orc.noise_shapes(opt, B, LR_HW, LR_HW, True), seed=123 + rank)
+    eng = net.engine("reverse", B, LR_HW, LR_HW, dev)
+    eng.ext["lr"].copy_(lr)
+    for i, e in enumerate(unit):
+        eng.ext["eps{}".format(i)].copy_(HEAT * e)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MiB > 126 MB L2
+    eng.lib.hcf_launch_count_reset()
+    eng.run()  # eager warm-up + graph capture
+    launches_per_step = int(eng.lib.hcf_launch_count()) // 2
+    for _ in range(max(args.warmup, 3)):
+        eng.run()
+    torch.cuda.synchronize()
+
+    # ---- device-resident timing
+    sampler = ClockSampler(local)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    hd.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    for k in range(args.steps):
+        flush.fill_(float(k))
+        starts[k].record()
+        eng.run()
+        ends[k].record()
+    torch.cuda.synchronize()
+    hd.barrier()
+    sampler.stop_flag = True
+    t_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    t_ms = hd.max_over_ranks(t_ms, dev)
+    mp_step = world * B * HR * HR / 1e6
+    value = mp_step * args.steps / (t_ms / 1e3)
+
+    # ---- end to end through the public module call, pinned host buffers
+    lr_host = lr.pin_memory()
+    hr_host = torch.empty(B, 3, HR, HR, dtype=torch.float32).pin_memory()
+    lr_dev = torch.empty_like(lr, device=dev)
+
+    def e2e_step():
+        lr_dev.copy_(lr_host, non_blocking=True)
+        out = net(lr=lr_dev, z=None, u=None, eps_std=HEAT, reverse=True, training=False)
+        hr_host.copy_(out, non_blocking=True)
+
+    with torch.no_grad():
+        for _ in range(3):
+            e2e_step()
+        torch.cuda.synchronize()
+        hd.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        e1.record()
+        torch.cuda.synchronize()
+        hd.barrier()
+    e2e_ms = hd.max_over_ranks(e0.elapsed_time(e1), dev)
+    e2e_value = mp_step * args.steps / (e2e_ms / 1e3)
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel class (eager pass, per-launch events)
+    net.use_graph = False
+    eng2 = net.engine("reverse", B, LR_HW, LR_HW, dev)
+    eng2.ext["lr"].copy_(lr)
+    for i, e in enumerate(unit):
+        eng2.ext["eps{}".format(i)].copy_(HEAT * e)
+    per_class_times(eng2)
+    classes = per_class_times(eng2)
+    total_ms = sum(v[1] for v in classes.values())
+    dom = max(classes, key=lambda c: classes[c][1])
+    n, ms, fl = classes[dom]
+    peaks = load_peaks()
+    achieved = fl / (ms / 1e3) / 1e12
+    roofline = {
+        "bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+        "frac": achieved / peaks["bf16_tflops"], "traffic": None,
+        "peak_source": "{} bf16 burst (TF32 tensor peak is nominally half; fp32 FFMA kernels do not use the "
+                       "tensor pipe at all)".format(peaks["source"]),
+        "launches": n, "avg_launch_ms": ms / n, "share_of_step": ms / total_ms,
+        "classes": {c: {"n": v[0], "ms": round(v[1], 4), "gflop": round(v[2] / 1e9, 3)} for c, v in classes.items()},
+    }
+    # ---- CPU baseline (rank 0, N=1 only): the oracle on the host cores, bounded sample
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        mp, times, cores = oracle_inverse_mps(1, budget_s=12.0, warmup=1)
+        cpu = {"value": mp * len(times) / sum(times), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "{} passes of configs[0] (B=1, 40x40 LR -> 160x160 HR, T=0.8), oracle on torch CPU fp32".format(
+                   len(times))}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"fp32": "fp32", "tf32": "tf32", "tf32x3": "tf32x3"}[args.precision], "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": "dp{}".format(world),
+                   "l2": "256 MiB flush between timed steps; per-step CUDA events",
+                   "conv_kernels": {"tcgen05": eng.n_tc, "fp32": eng.n_fp32_conv},
+                   "conv_tflop_per_step": conv_flops(eng.plan, B) / 1e12},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(lr.numel() * 4),
+                "d2h_bytes_per_step": int(hr_host.numel() * 4), "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches_per_step * args.steps,
+        "launches_per_step": launches_per_step,
+        "clocks": sampler.summary(),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("HCFLOW_PRECISION", "fp32"),
+                    choices=["fp32", "tf32", "tf32x3"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    with torch.no_grad():
+        run_ours(args)
+    if torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

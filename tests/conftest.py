@@ -20,3 +20,25 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+_REPORT = {}
+
+
+@pytest.fixture(scope="session")
+def report():
+    """Numbers the GPU parity tests want kept (written to gpurun_out/parity_report.json)."""
+    yield _REPORT
+
+
+def pytest_sessionfinish(session, exitstatus):
+    if not _REPORT:
+        return
+    import json
+    out = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_report.json"), "w") as f:
+            json.dump(_REPORT, f, indent=1, sort_keys=True)
+    except OSError:
+        pass

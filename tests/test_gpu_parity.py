@@ -1,0 +1,248 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the committed
+reference goldens.  Tolerances (fp32 mode): HR / z within 2e-4 max-abs on O(1)..O(10) values
+(the reference's own fp32-vs-fp64 floor is 3e-6; the CUDA kernels sum in a
+different order), log-det and NLL within 1e-5 relative."""
+import ctypes as C
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from hcflow_b200 import _lib as L
+from hcflow_b200 import options as popt
+from hcflow_b200 import synth
+from hcflow_b200.arch import build_net
+from oracle import hcflow_oracle as orc
+from tests.helpers import is_sr, load_golden, maxabs, net_and_weights
+
+pytestmark = pytest.mark.gpu
+
+TOL_X = 2e-4
+TOL_REL = 1e-5
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    return scale * torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+# ------------------------------------------------------------------------------ library
+def test_native_library_is_loaded():
+    lib = L.load()
+    assert lib.hcf_abi_version() == 1
+    with open("/proc/self/maps") as f:
+        assert "libhcflow_b200.so" in f.read()
+
+
+# ------------------------------------------------------------------------------ conv
+CONV_CASES = [
+    # name, B, H, W, [seg (C, up, ld, off)], cout, ks, bias, scale, act, res1, res2
+    ("rdb_conv1", 2, 20, 24, [(64, 0, 192, 0)], 32, 3, True, False, 2, False, False),
+    ("rdb_conv5_res2", 1, 16, 16, [(192, 0, 192, 0)], 64, 3, True, False, 0, True, True),
+    ("conv_first_lr", 2, 13, 9, [(3, 0, 24, 0)], 64, 3, True, False, 0, False, False),
+    ("conv_first_up", 1, 16, 24, [(6, 0, 12, 0), (128, 1, 128, 0)], 64, 3, True, False, 0, False, False),
+    ("conv_first_x8", 1, 16, 16, [(6, 0, 12, 0), (128, 1, 128, 0), (128, 2, 128, 0)], 64, 3, True, False, 0, False, False),
+    ("fcn_conv1_cond", 2, 11, 17, [(10, 0, 24, 3), (128, 0, 128, 0)], 64, 3, True, True, 1, False, False),
+    ("fcn_conv2_1x1", 2, 11, 17, [(64, 0, 64, 0)], 64, 1, True, True, 1, False, False),
+    ("fcn_conv3_small", 2, 11, 17, [(64, 0, 64, 0)], 22, 3, True, True, 0, False, False),
+    ("fcn_conv3_6", 1, 9, 9, [(64, 0, 64, 0)], 6, 3, True, True, 0, False, False),
+    ("prior_42", 1, 8, 40, [(128, 0, 128, 0)], 42, 3, True, True, 0, False, False),
+    ("dense_conv5", 1, 10, 10, [(9, 0, 12, 3), (128, 0, 128, 0)], 3, 3, True, False, 0, False, False),
+    ("wide_90", 1, 8, 8, [(45, 0, 48, 3)], 90, 3, True, True, 0, False, False),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_fp32_matches_torch(case, report):
+    from tests import gpu_ops
+    name, B, H, W, segs, cout, ks, has_b, has_s, act, r1, r2 = case
+    xs, segargs = [], []
+    for i, (c, up, ld, off) in enumerate(segs):
+        x = _rand(B, c, H >> up, W >> up, seed=10 + i)
+        xs.append(F.interpolate(x, scale_factor=1 << up, mode="nearest") if up else x)
+        segargs.append((x, up, ld, off))
+    cin = sum(s[0] for s in segs)
+    w = _rand(cout, cin, ks, ks, seed=3, scale=1.0 / math.sqrt(cin * ks * ks))
+    bias = _rand(cout, seed=4, scale=0.1) if has_b else None
+    scale = torch.exp(_rand(cout, seed=5, scale=0.2)) if has_s else None
+    res1 = _rand(B, cout, H, W, seed=6) if r1 else None
+    res2 = _rand(B, cout, H, W, seed=7) if r2 else None
+    got, got2 = gpu_ops.conv(segargs, w, bias, scale, act, res1, 0.2, res2, 0.2, out_ld=cout + 8, out_off=4,
+                             want_out2=True)
+    ref = F.conv2d(torch.cat(xs, 1).double(), w.double(), None, padding=ks // 2)
+    if has_b:
+        ref = ref + bias.double().view(1, -1, 1, 1)
+    if has_s:
+        ref = ref * scale.double().view(1, -1, 1, 1)
+    ref = F.relu(ref) if act == 1 else (F.leaky_relu(ref, 0.2) if act == 2 else ref)
+    if r1:
+        ref = ref * 0.2 + res1.double()
+    if r2:
+        ref = ref * 0.2 + res2.double()
+    err = maxabs(got, ref)
+    report["conv_fp32/" + name] = err
+    assert err < 2e-5, (name, err)
+    assert maxabs(got2, got) == 0.0
+
+
+# ------------------------------------------------------------------------------ flow step ops
+@pytest.mark.parametrize("cfg,pre,cond", [
+    ("sr_x4", "flow.layers.1", False), ("sr_x4", "flow.layers.16", False),
+    ("sr_x4", "flow.level1_condFlow.additional_flow_steps.0", True),
+    ("sr_x4", "flow.level0_condFlow.additional_flow_steps.3", True),
+    ("sr_x8", "flow.layers.31", False), ("sr_x8", "flow.level2_condFlow.additional_flow_steps.0", True),
+])
+def test_step_kernels_match_oracle(cfg, pre, cond, report):
+    """hcf_step_inverse / forward_head / forward_coupling against oracle.flow_step, with the
+    coupling sub-net output h taken from the oracle (isolates the per-pixel kernels)."""
+    from tests import gpu_ops
+    from hcflow_b200 import prep
+    opt, net, sd = net_and_weights(cfg)
+    Cc = sd[pre + ".actnorm.bias"].shape[1]
+    B, H, W = 2, 6, 10
+    z = _rand(B, Cc, H, W, seed=1)
+    u = _rand(B, 128, H, W, seed=2, scale=0.3) if cond else None
+    n_pass = Cc // 2
+    with torch.no_grad():
+        # inverse
+        z1 = z[:, :n_pass]
+        h = orc.fcn(z1 if u is None else torch.cat((z1, u), 1), sd, pre + ".affine.f")
+        want, _ = orc.flow_step(z, u, sd, pre, None, True, "affine", n_pass)
+        got = gpu_ops.step("inverse", z, h, "affine", n_pass, prep.derive(sd, pre + ".permute.weight#inv"),
+                           prep.derive(sd, pre + ".actnorm.logs#expneg"), prep.derive(sd, pre + ".actnorm.bias#vec"),
+                           ld=Cc + 3, off=3)
+        e_inv = maxabs(got, want)
+        # forward = head, sub-net (oracle), coupling
+        ld0 = torch.zeros(B)
+        wantf, ldw = orc.flow_step(z, u, sd, pre, ld0, False, "affine", n_pass)
+        mid = gpu_ops.step("forward_head", z, None, "affine", n_pass, prep.derive(sd, pre + ".permute.weight#mat"),
+                           prep.derive(sd, pre + ".actnorm.logs#exppos"), prep.derive(sd, pre + ".actnorm.bias#vec"))
+        m1 = mid[:, :n_pass]
+        hf = orc.fcn(m1 if u is None else torch.cat((m1, u), 1), sd, pre + ".affine.f")
+        logdet = torch.zeros(B, dtype=torch.float64, device="cuda")
+        gotf = gpu_ops.step("forward_coupling", mid, hf, "affine", n_pass, None, None, None, logdet=logdet)
+        e_fwd = maxabs(gotf, wantf)
+        const = prep.logdet_constant(sd, [(pre, True, H * W)])
+        e_ld = float(((logdet.cpu() + const) - ldw.double()).abs().max())
+    report["step/{}/{}".format(cfg, pre)] = {"inverse": e_inv, "forward": e_fwd, "logdet_abs": e_ld}
+    assert e_inv < 2e-5 and e_fwd < 2e-5 and e_ld < 2e-3
+
+
+# ------------------------------------------------------------------------------ end to end vs goldens
+def _net_cuda(cfg, precision="fp32"):
+    opt, net_cpu, sd = net_and_weights(cfg)
+    net = build_net(opt)
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    net.set_precision(precision)
+    return opt, net, sd
+
+
+def _inputs(g, opt):
+    B, h, w, heat = g["B"], g["h"], g["w"], g["heat"]
+    s = opt["scale"]
+    unit = synth.synthetic_noise(orc.noise_shapes(opt, B, h, w, is_sr(opt)))
+    return synth.synthetic_lr(B, h, w), synth.synthetic_hr(B, h * s, w * s), unit, heat
+
+
+@pytest.mark.parametrize("cfg", ["sr_x4", "sr_x8", "rescaling_x4"])
+def test_reverse_matches_reference_golden(cfg, report):
+    g = load_golden(cfg)
+    opt, net, sd = _net_cuda(cfg)
+    lr, hr, unit, heat = _inputs(g, opt)
+    with torch.no_grad():
+        out = net(lr=lr.cuda(), z=None, u=None, eps_std=heat, reverse=True, training=False, eps=unit)
+        raw = net.last["hr_raw"].cpu()
+        out0 = net(lr=lr.cuda(), eps_std=0.0, reverse=True, training=False, eps=unit)
+    e_raw, e_hr, e0 = maxabs(raw, g["inv_raw"]), maxabs(out.cpu(), g["inv_hr"]), maxabs(out0.cpu(), g["inv_hr_heat0"])
+    report["e2e_reverse/" + cfg] = {"hr_raw": e_raw, "hr": e_hr, "hr_heat0": e0,
+                                    "range": [float(g["inv_raw"].min()), float(g["inv_raw"].max())]}
+    assert e_raw < TOL_X and e_hr < TOL_X and e0 < TOL_X
+    assert float(out.min()) >= 0.0 and float(out.max()) <= 1.0
+
+
+@pytest.mark.parametrize("cfg", ["sr_x4", "sr_x8"])
+def test_sr_forward_matches_reference_golden(cfg, report):
+    g = load_golden(cfg)
+    opt, net, sd = _net_cuda(cfg)
+    lr, hr, unit, heat = _inputs(g, opt)
+    dq = torch.rand(hr.shape, generator=torch.Generator().manual_seed(77), dtype=torch.float32)
+    with torch.no_grad():
+        fake_lr, nll = net(hr=hr.cuda(), lr=lr.cuda(), u=None, reverse=False, training=False, dequant_noise=dq)
+    z = net.last["z_raw"].cpu()
+    e_z = maxabs(z, g["fwd_z"])
+    e_nll = abs(float(nll) - float(g["fwd_nll"])) / abs(float(g["fwd_nll"]))
+    # the quantised fake LR may flip one 1/255 step where z sits within rounding distance of a boundary
+    flips = int(((fake_lr.cpu() - g["fwd_fake_lr"]).abs() > 1e-6).sum())
+    # log-det alone: subtract the dirac term computed by the oracle on OUR fake_lr
+    dirac = orc.gaussian_logp(lr, -torch.ones_like(lr) * 6, fake_lr.cpu()).double()
+    ld = net.last["objective"].cpu() - dirac
+    e_ld = float(((ld - g["fwd_logdet"].double()).abs() / g["fwd_logdet"].double().abs()).max())
+    report["e2e_forward/" + cfg] = {"z": e_z, "nll_rel": e_nll, "logdet_rel": e_ld, "quant_flips": flips}
+    assert e_z < TOL_X and e_ld < TOL_REL
+    assert flips <= 2
+    if flips == 0:
+        assert e_nll < TOL_REL
+
+
+def test_rescaling_forward_matches_reference_golden(report):
+    g = load_golden("rescaling_x4")
+    opt, net, sd = _net_cuda("rescaling_x4")
+    lr, hr, unit, heat = _inputs(g, opt)
+    with torch.no_grad():
+        flr, z1, z2 = net(hr=hr.cuda(), reverse=False, training=False)
+    e = [maxabs(flr.cpu(), g["fwd_fake_lr"]), maxabs(z1.cpu(), g["fwd_z1"]), maxabs(z2.cpu(), g["fwd_z2"]),
+         maxabs(net.last["z_raw"].cpu(), g["fwd_raw_lr"])]
+    report["e2e_forward/rescaling_x4"] = e
+    assert e[0] < TOL_X and e[3] < TOL_X
+    # fake_z = (z - mean) * exp(-logscale): scaled by up to e^0.5, keep a slightly wider margin
+    assert e[1] < 5e-4 and e[2] < 5e-4
+
+
+# ------------------------------------------------------------------------------ full-size properties
+def test_full_size_inverse_then_forward_roundtrip(report):
+    """configs[1]: 4x SR, B=16, 40x40 -> 160x160.  Size-independent property: the flow is a
+    bijection, so forward(inverse(lr)) must return lr (dequantisation noise off); and the
+    first images must match the oracle run on them alone (images are independent)."""
+    opt, net, sd = _net_cuda("sr_x4")
+    B = 16
+    lr = synth.synthetic_lr(B, 40, 40, seed=5)
+    unit = synth.synthetic_noise(orc.noise_shapes(opt, B, 40, 40, True), seed=9)
+    with torch.no_grad():
+        hr = net(lr=lr.cuda(), eps_std=0.8, reverse=True, eps=unit)
+        raw = net.last["hr_raw"]
+        assert torch.isfinite(raw).all()
+        _, nll = net(hr=raw, lr=lr.cuda(), reverse=False, dequant_noise=torch.zeros_like(raw))
+        z = net.last["z_raw"].cpu()
+        # determinism of graph replay
+        hr2 = net(lr=lr.cuda(), eps_std=0.8, reverse=True, eps=unit)
+        _, raw_o = orc.sr_reverse(lr[:1], sd, opt, [0.8 * e[:1] for e in unit])
+    e_rt = maxabs(z, lr)
+    e_or = maxabs(raw[:1].cpu(), raw_o)
+    report["full_size/sr_x4_b16"] = {"roundtrip": e_rt, "vs_oracle_img0": e_or, "nll": float(nll)}
+    assert e_rt < 1e-3
+    assert e_or < TOL_X
+    assert torch.equal(hr, hr2)
+
+
+def test_eps_std_zero_is_deterministic_and_rng_path_runs():
+    opt, net, sd = _net_cuda("sr_x4")
+    lr = synth.synthetic_lr(1, 8, 8, seed=2).cuda()
+    with torch.no_grad():
+        a = net(lr=lr, eps_std=0.0, reverse=True)
+        b = net(lr=lr, eps_std=0.0, reverse=True)
+        torch.manual_seed(0)
+        c = net(lr=lr, eps_std=0.9, reverse=True)
+        torch.manual_seed(0)
+        d = net(lr=lr, eps_std=0.9, reverse=True)
+    assert torch.equal(a, b) and torch.equal(c, d) and not torch.equal(a, c)
+
+
+def test_rejects_cpu_tensors_and_bad_scale():
+    opt, net, sd = _net_cuda("sr_x4")
+    with pytest.raises(RuntimeError):
+        net(lr=torch.zeros(1, 3, 8, 8), eps_std=0.0, reverse=True)
+    bad = popt.load_config("sr_x4")
+    bad["scale"] = 3
+    with pytest.raises(NotImplementedError):
+        build_net(bad)

@@ -1,0 +1,122 @@
+"""CPU tests of the host side: C-ABI exports, state_dict layout, the install() hook,
+option handling, weight packing and the world_size-2 sharding / NLL reduction (gloo)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+import hcflow_b200
+from hcflow_b200 import _lib, options as popt, prep, synth
+from hcflow_b200.arch import HCFlowNet_Rescaling, HCFlowNet_SR, build_net
+from tests.helpers import net_and_weights
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "hcflow_b200.h")).read()
+    declared = set(re.findall(r"\b(hcf_[a-z0-9_]+)\s*\(", header))
+    declared -= {"hcf_conv_tc_plan"}
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = _lib.load()  # raises if the .so is missing or a symbol is not exported
+    assert lib.hcf_abi_version() == 1
+    assert lib.hcf_last_error() is not None
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libhcflow_b200.so")
+    with pytest.raises(_lib.HcfError):
+        _lib.load()
+
+
+def test_no_cpu_fallback():
+    opt, net, sd = net_and_weights("sr_x4")
+    with pytest.raises(RuntimeError):
+        net(lr=torch.zeros(1, 3, 8, 8), eps_std=0.0, reverse=True)
+
+
+@pytest.mark.parametrize("cfg,ntensors,nparams", [("sr_x4", 1478, 23232539), ("rescaling_x4", 532, None)])
+def test_state_dict_layout(cfg, ntensors, nparams):
+    """Tensor / parameter counts of the reference nets; key-by-key equality
+    with the reference is enforced when oracle/make_golden.py loads these weights strict=True."""
+    opt, net, sd = net_and_weights(cfg)
+    assert len(sd) == ntensors
+    if nparams:
+        assert sum(v.numel() for v in sd.values()) == nparams
+    assert "flow.layers.1.actnorm.bias" in sd and tuple(sd["flow.layers.1.actnorm.bias"].shape) == (1, 12, 1, 1)
+    assert tuple(sd["flow.level0_condFlow.f.logs"].shape) == (12, 1, 1)
+
+
+def test_install_hook_resolves_like_the_reference_factory():
+    import importlib
+    names = hcflow_b200.install()
+    try:
+        for which, cls in (("HCFlowNet_SR", HCFlowNet_SR), ("HCFlowNet_Rescaling", HCFlowNet_Rescaling)):
+            lib = importlib.import_module("models.modules." + which + "_arch")
+            target = which.replace("_Net", "").lower()
+            found = [c for n, c in lib.__dict__.items() if n.lower() == target]
+            assert found == [cls]
+    finally:
+        hcflow_b200.uninstall()
+    assert len(names) == 2
+
+
+def test_forward_signature_matches_reference():
+    import inspect
+    sig = inspect.signature(HCFlowNet_SR.forward)
+    names = list(sig.parameters)
+    assert names[:10] == ["self", "hr", "lr", "z", "u", "eps_std", "add_gt_noise", "step", "reverse", "training"]
+    assert sig.parameters["reverse"].default is False and sig.parameters["training"].default is True
+
+
+def test_pack_conv_weight_roundtrip():
+    w = torch.randn(22, 138, 3, 3)
+    p = prep.pack_conv_weight(w, [10, 128], 32)
+    assert tuple(p.shape) == (9, 16 + 128, 32)
+    assert torch.equal(p[4, 3, :22], w[:, 3, 1, 1]) and torch.equal(p[0, 16 + 5, :22], w[:, 15, 0, 0])
+    assert float(p[:, 10:16].abs().max()) == 0.0 and float(p[:, :, 22:].abs().max()) == 0.0
+
+
+def test_derive_inverse_matches_reference_arithmetic():
+    sd = {"w": torch.randn(12, 12)}
+    assert torch.equal(prep.derive(sd, "w#inv"), torch.inverse(sd["w"].double()).float())
+
+
+def test_shard_range_partitions():
+    from hcflow_b200.dist import shard_range
+    for n in (1, 7, 16, 512):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+
+
+_WORKER = r"""
+import os, sys, torch
+sys.path.insert(0, {root!r})
+from hcflow_b200 import dist as hd
+rank, local, world = hd.init_from_env(backend="gloo")
+lo, hi = hd.shard_range(10, rank, world)
+nll = torch.arange(10, dtype=torch.float32)[lo:hi]
+m = hd.batch_mean_nll(nll)
+t = hd.max_over_ranks(1.0 + rank, "cpu")
+hd.barrier()
+assert abs(float(m) - 4.5) < 1e-6, float(m)
+assert t == float(world), t
+print("OK", rank)
+"""
+
+
+def test_world_size_2_gloo_nll_reduction(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29613", str(script)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("OK") == 2
