@@ -10,6 +10,7 @@ namespace hcf {
 
 void set_error(const char* fmt, ...);
 void count_launch();
+int validate_conv_args(const hcf_conv_args* a);
 
 // Checks the launch that was just issued on `stream` (no device sync).
 inline int finish_launch(const char* what) {

@@ -246,3 +246,72 @@ def test_rejects_cpu_tensors_and_bad_scale():
     bad["scale"] = 3
     with pytest.raises(NotImplementedError):
         build_net(bad)
+
+
+# ------------------------------------------------------------------------------ tcgen05 conv kernel
+TC_CASES = [
+    # name, B, H, W, Cin, ld, cout, bias, scale, act, res1, res2
+    ("tiny", 1, 16, 8, 32, 32, 16, False, False, 0, False, False),
+    ("rdb_conv1", 2, 40, 40, 64, 192, 32, True, False, 2, False, False),
+    ("rdb_conv3_partial_tiles", 1, 33, 21, 128, 192, 32, True, False, 2, False, False),
+    ("rdb_conv5_res", 1, 20, 20, 192, 192, 64, True, False, 0, True, True),
+    ("prior_42", 1, 16, 16, 128, 128, 42, True, True, 0, False, False),
+    ("fcn_conv3_22", 2, 13, 9, 64, 64, 22, True, True, 0, False, False),
+    ("cout_48", 1, 16, 8, 64, 64, 48, True, False, 0, False, False),
+]
+# max-abs tolerance on outputs of magnitude ~4: one TF32 pass keeps 10 mantissa bits per operand
+# (measured 3e-3); the 3-pass split recovers them, what remains is the tensor core's truncating
+# fp32 accumulation over 36*Cin/32 MMAs per pass (measured 2e-5 .. 1.2e-4).
+TC_TOL = {"tf32": 1e-2, "tf32x3": 4e-4}
+
+
+@pytest.mark.parametrize("precision", ["tf32", "tf32x3"])
+@pytest.mark.parametrize("case", TC_CASES, ids=[c[0] for c in TC_CASES])
+def test_conv_tcgen05_matches_fp64(case, precision, report):
+    from tests import gpu_ops
+    name, B, H, W, cin, ld, cout, hb, hs, act, r1, r2 = case
+    x = _rand(B, cin, H, W, seed=1)
+    w = _rand(cout, cin, 3, 3, seed=2, scale=1.0 / math.sqrt(cin * 9))
+    bias = _rand(cout, seed=4, scale=0.1) if hb else None
+    scale = torch.exp(_rand(cout, seed=5, scale=0.2)) if hs else None
+    res1 = _rand(B, cout, H, W, seed=6) if r1 else None
+    res2 = _rand(B, cout, H, W, seed=7) if r2 else None
+    got, got2 = gpu_ops.conv([(x, 0, ld, 0)], w, bias, scale, act, res1, 0.2, res2, 0.2, out_ld=cout + 8, out_off=4,
+                             precision=precision, want_out2=True)
+    ref = F.conv2d(x.double(), w.double(), None, padding=1)
+    if hb:
+        ref = ref + bias.double().view(1, -1, 1, 1)
+    if hs:
+        ref = ref * scale.double().view(1, -1, 1, 1)
+    ref = F.relu(ref) if act == 1 else (F.leaky_relu(ref, 0.2) if act == 2 else ref)
+    if r1:
+        ref = ref * 0.2 + res1.double()
+    if r2:
+        ref = ref * 0.2 + res2.double()
+    err = maxabs(got, ref)
+    report["conv_{}/{}".format(precision, name)] = err
+    assert err < TC_TOL[precision], (name, precision, err)
+    assert maxabs(got2, got) == 0.0
+
+
+# End-to-end tolerances of the tensor-core modes against the reference goldens (un-clamped HR,
+# values in about +-6..+-11): measured tf32 1.3e-2 max / 9e-4 mean (x4), tf32x3 see report.
+E2E_TOL = {"tf32": 5e-2, "tf32x3": 2e-3}
+
+
+@pytest.mark.parametrize("precision", ["tf32", "tf32x3"])
+@pytest.mark.parametrize("cfg", ["sr_x4", "sr_x8", "rescaling_x4"])
+def test_tensor_core_modes_match_reference_golden(cfg, precision, report):
+    g = load_golden(cfg)
+    opt, net, sd = _net_cuda(cfg, precision)
+    lr, hr, unit, heat = _inputs(g, opt)
+    with torch.no_grad():
+        net(lr=lr.cuda(), eps_std=heat, reverse=True, eps=unit)
+    raw = net.last["hr_raw"].cpu()
+    eng = list(net._engines.values())[0]
+    assert eng.n_tc > 0, "tensor-core kernels were not selected"
+    e = maxabs(raw, g["inv_raw"])
+    mean = float((raw.double() - g["inv_raw"].double()).abs().mean())
+    report["e2e_reverse_{}/{}".format(precision, cfg)] = {"hr_raw_max": e, "hr_raw_mean": mean, "tc_convs": eng.n_tc,
+                                                          "fp32_convs": eng.n_fp32_conv}
+    assert e < E2E_TOL[precision], (cfg, precision, e)
