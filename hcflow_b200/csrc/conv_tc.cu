@@ -1,28 +1,28 @@
-// 3x3 convolution as an implicit GEMM on the 5th-generation tensor cores (tcgen05, sm_100a).
+// 3x3 convolution as a persistent implicit GEMM on the 5th-generation tensor cores
+// (tcgen05 / TMEM / TMA, sm_100a).
 //
 //   D[128 pixels, N] += A[128 pixels, 32 ch] * B[N, 32 ch]^T     per (tap, 32-channel chunk)
 //
-// One CTA owns a 16x8 pixel tile of one image (UMMA M = 128) and all N = ceil16(Cout) <= 64
-// output channels; the fp32 accumulator lives in TMEM (N columns).  Per 32-channel chunk the
-// producer thread issues
-//   * ONE 4-D TMA tile load of the 18x10 halo tile [18][10][32 ch] (128-byte swizzle, out of
-//     bounds -> 0, which is exactly the conv's zero padding), and
-//   * one bulk copy of the pre-swizzled weight slab [9 taps][N][32 ch];
-// the MMA thread then issues 9 taps x 4 K-steps of tcgen05.mma.kind::tf32.  The nine taps
-// do NOT reload the activations: tap (dy,dx) is a shared-memory descriptor whose start is
-// shifted by (dy*10+dx) 128-byte rows into the same halo tile and whose 8-row-group stride
-// (SBO) is the halo row pitch (10*128 B) -- the 128B-swizzle XOR is a function of the
-// absolute smem address bits, so a shifted view of a TMA-written tile stays consistent.
-// (HCF_TC_SAFE_A=1 selects a diagnostic variant that loads nine separate aligned tiles.)
-//
-// passes = 3 runs the K loop three times (A_raw*B_raw, A_raw*B_lo, A_lo*B_raw): the tensor
-// core reads an fp32 word as TF32 by ignoring the low 13 mantissa bits, so "hi" parts are
-// free, B_lo is precomputed on the host and A_lo = a - trunc(a) is formed in place in smem
-// by the epilogue warps before the MMA of that stage (3xTF32 split, ~fp32 accuracy).
-//
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
-// warps 2..5 = A_lo conversion during the main loop, then epilogue (tcgen05.ld -> bias /
-// scale / activation / residuals -> global).
+// Work item = MT vertically adjacent 16x8 pixel tiles of one image (UMMA M = 128 each) x all
+// N = ceil16(Cout) <= 64 output channels.  CTAs are persistent (grid = #SMs, items strided by
+// gridDim.x) and warp-specialised:
+//   warp 0      TMA producer.  Per 32-channel chunk ONE 4-D TMA tile load brings the
+//               (16*MT+2) x 10 halo tile [rows][10][32 ch] (128-byte swizzle; out-of-bounds -> 0
+//               is exactly the conv's zero padding) into the A ring; the pre-swizzled weights
+//               stream through a second ring in (chunk, dy) slabs [3 taps][N][32 ch].
+//   warp 1      TMEM owner + MMA issuer: 9 taps x 4 K-steps of tcgen05.mma.kind::tf32 per chunk
+//               and sub-tile.  The nine taps do NOT reload activations: tap (dy,dx) is a smem
+//               descriptor whose start is shifted by (dy*10+dx) 128-byte rows into the same halo
+//               tile and whose 8-row-group stride (SBO) is the halo row pitch (1280 B).  The
+//               128B-swizzle XOR is a function of the absolute smem address, so a shifted view
+//               of a TMA-written tile stays consistent (verified on B200).
+//   warps 2..5  epilogue: tcgen05.ld -> bias / scale / activation / residuals -> global.  The
+//               accumulator is double-buffered in TMEM (2 x MT x N columns), so the epilogue of
+//               item i overlaps the loads and MMAs of item i+1.
+//   warps 6..9  (PASSES == 3 only) 3xTF32 split: the tensor core reads an fp32 word as TF32 by
+//               ignoring the low 13 mantissa bits, so the "hi" parts are free; these warps form
+//               A_lo = a - trunc(a) next to every A stage, B_lo is precomputed on the host, and
+//               each K-step issues A*B, A*B_lo, A_lo*B into the same accumulator.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -32,26 +32,27 @@
 namespace hcf {
 namespace tc {
 
-constexpr int TH = 16, TW = 8;               // pixel tile (UMMA M = 128)
-constexpr int HALO_W = TW + 2, HALO_H = TH + 2;
+constexpr int TH = 16, TW = 8;               // sub-tile (UMMA M = 128)
+constexpr int HALO_W = TW + 2;
 constexpr int KCH = 32;                      // channels per K chunk (= 128 B rows)
 constexpr int ROW_BYTES = KCH * 4;           // 128
-constexpr int A_HALO_BYTES = HALO_H * HALO_W * ROW_BYTES;   // 23040
-constexpr int A_HALO_STAGE = 23552;                         // padded to a 1024 B multiple
-constexpr int A_SAFE_TILE = TH * TW * ROW_BYTES;            // 16384 per tap
-constexpr int NTHREADS = 192;
 constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int NUM_SMS_FALLBACK = 148;
+
+__host__ __device__ constexpr int halo_rows(int mt) { return TH * mt + 2; }
+__host__ __device__ constexpr int a_bytes(int mt) { return halo_rows(mt) * HALO_W * ROW_BYTES; }
+__host__ __device__ constexpr int a_part(int mt) { return (a_bytes(mt) + 1023) / 1024 * 1024; }
 
 struct Params {
   int B, H, W;
   int kchunks;   // Cin / 32
   int N;         // UMMA N (multiple of 16, <= 64)
   int cout;
-  int passes;    // 1 or 3
-  int stages;
-  int safe_a;    // diagnostic: nine aligned A tiles per stage instead of one halo tile
-  int tiles_x, tiles_y;
-  const float* wimg;   // [2][kchunks][9][N][32] pre-swizzled (raw, lo)
+  int sa, sb;    // ring depths
+  int dys;       // dy rows of taps per B slab: 3 (whole chunk) or 1
+  int debug;     // timing experiments only (HCF_TC_DEBUG): bit0 = 1024B-aligned A descriptors (wrong results)
+  int tiles_x, tiles_y, n_items;
+  const float* wimg;   // [kchunks][2 (raw, lo)][3 dy][3 dx][N][32] pre-swizzled
   const float* bias;
   const float* scale;
   int act;
@@ -109,6 +110,15 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "@px mov.s32 %0, 1;\n\t}" : "+r"(pred));
+  return pred;
+}
+
 // K-major, 128B-swizzled operand: rows of 128 B, 8-row groups `sbo_bytes` apart.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -134,41 +144,50 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 }
 
 // ------------------------------------------------------------------ kernel
-__global__ void __launch_bounds__(NTHREADS, 1)
+template <int MT, int PASSES>
+__global__ void __launch_bounds__(PASSES == 3 ? 320 : 192, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap amap, const Params p) {
+  constexpr int A_BYTES = a_bytes(MT);
+  constexpr int A_PART = a_part(MT);
+  constexpr int A_STAGE = A_PART * (PASSES == 3 ? 2 : 1);   // [raw | lo]
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stages x (A | B)] then barriers
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_stage_bytes = p.safe_a ? 9u * A_SAFE_TILE : (uint32_t)A_HALO_STAGE;
-  const uint32_t b_stage_bytes = 9u * p.N * ROW_BYTES;
-  const uint32_t stage_bytes = a_stage_bytes + b_stage_bytes;
-  const uint32_t bar_base = smem_base + p.stages * stage_bytes;
-  // barriers: full[s], empty[s], conv[s], tmem_full ; then the TMEM base address slot
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
-  auto conv_bar = [&](int s) { return bar_base + 8u * (2 * p.stages + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (3 * p.stages);
-  const uint32_t tmem_slot = tmem_full_bar + 8u;
-  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));   // generic pointer to smem_base
+  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t tap_bytes = (uint32_t)p.N * ROW_BYTES;          // one tap of B: [N][32 ch]
+  const uint32_t b_half = 3u * p.dys * tap_bytes;                // raw (or lo) taps of one slab
+  const uint32_t b_slab = b_half * (PASSES == 3 ? 2u : 1u);      // [raw taps | lo taps]
+  const int slabs = 3 / p.dys;                                   // slabs per 32-channel chunk
+  const uint32_t b_base = smem_base + p.sa * A_STAGE;
+  const uint32_t bar_base = b_base + p.sb * b_slab;
+  auto fullA = [&](int s) { return bar_base + 8u * s; };
+  auto emptyA = [&](int s) { return bar_base + 8u * (p.sa + s); };
+  auto convA = [&](int s) { return bar_base + 8u * (2 * p.sa + s); };
+  auto fullB = [&](int s) { return bar_base + 8u * (3 * p.sa + s); };
+  auto emptyB = [&](int s) { return bar_base + 8u * (3 * p.sa + p.sb + s); };
+  const uint32_t tbar = bar_base + 8u * (3 * p.sa + 2 * p.sb);
+  auto tmem_full = [&](int a) { return tbar + 8u * a; };
+  auto tmem_empty = [&](int a) { return tbar + 16u + 8u * a; };
+  const uint32_t tmem_slot = tbar + 32u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int tile = blockIdx.x;
-  const int tile_x = tile % p.tiles_x;
-  tile /= p.tiles_x;
-  const int tile_y = tile % p.tiles_y;
-  const int b = tile / p.tiles_y;
-  const int y0 = tile_y * TH, x0 = tile_x * TW;
-  const int iters = p.passes * p.kchunks;
-  const uint32_t tmem_cols = p.N <= 32 ? 32u : 64u;
+  const uint32_t need_cols = 2u * MT * p.N;
+  const uint32_t tmem_cols = need_cols <= 32 ? 32u : (need_cols <= 64 ? 64u : (need_cols <= 128 ? 128u : 256u));
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&amap) : "memory");
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), p.passes == 3 ? 129u : 1u);   // MMA commit (+ the 128 converter threads)
-      mbar_init(conv_bar(s), 128);
+    for (int s = 0; s < p.sa; ++s) {
+      mbar_init(fullA(s), 1);
+      mbar_init(emptyA(s), 1);
+      mbar_init(convA(s), 128);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < p.sb; ++s) {
+      mbar_init(fullB(s), 1);
+      mbar_init(emptyB(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full(a), 1);
+      mbar_init(tmem_empty(a), 128);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -182,137 +201,200 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap amap, const Params p) {
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+  const int per_img = p.tiles_x * p.tiles_y;
+
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        const int pass = it / p.kchunks, kc = it % p.kchunks;
-        const uint32_t a_dst = smem_base + s * stage_bytes;
-        const uint32_t b_dst = a_dst + a_stage_bytes;
-        const uint32_t a_bytes = p.safe_a ? 9u * A_SAFE_TILE : (uint32_t)A_HALO_BYTES;
-        mbar_expect_tx(full_bar(s), a_bytes + b_stage_bytes);
-        if (!p.safe_a) {
-          tma_load_4d(a_dst, &amap, full_bar(s), kc * KCH, x0 - 1, y0 - 1, b);
-        } else {
-          for (int t = 0; t < 9; ++t)
-            tma_load_4d(a_dst + t * A_SAFE_TILE, &amap, full_bar(s), kc * KCH, x0 + (t % 3) - 1, y0 + (t / 3) - 1, b);
+      uint32_t a_it = 0, b_it = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int b = item / per_img, r = item % per_img;
+        const int y0 = (r / p.tiles_x) * TH * MT, x0 = (r % p.tiles_x) * TW;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          const int sA = a_it % p.sa;
+          mbar_wait(emptyA(sA), ((a_it / p.sa) & 1u) ^ 1u);
+          mbar_expect_tx(fullA(sA), A_BYTES);
+          tma_load_4d(smem_base + sA * A_STAGE, &amap, fullA(sA), kc * KCH, x0 - 1, y0 - 1, b);
+          ++a_it;
+          for (int sl = 0; sl < slabs; ++sl) {
+            const int sB = b_it % p.sb;
+            mbar_wait(emptyB(sB), ((b_it / p.sb) & 1u) ^ 1u);
+            mbar_expect_tx(fullB(sB), b_slab);
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wimg) + (size_t)kc * (18u * tap_bytes) +
+                                 (size_t)sl * b_half;
+            bulk_load(b_base + sB * b_slab, src, b_half, fullB(sB));
+            if (PASSES == 3) bulk_load(b_base + sB * b_slab + b_half, src + 9u * tap_bytes, b_half, fullB(sB));
+            ++b_it;
+          }
         }
-        const int bpart = (pass == 1) ? 1 : 0;
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wimg) +
-                             (size_t)(bpart * p.kchunks + kc) * b_stage_bytes;
-        bulk_load(b_dst, src, b_stage_bytes, full_bar(s));
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
-      uint32_t conv_phase = 0;   // bit s = parity of the next completion of conv_bar(s)
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-        const int pass = it / p.kchunks;
-        mbar_wait(full_bar(s), ph);
-        if (pass == 2) {
-          mbar_wait(conv_bar(s), (conv_phase >> s) & 1u);
-          conv_phase ^= 1u << s;
-        }
-        tc_fence_after();
-        const uint32_t a_src = smem_base + s * stage_bytes;
-        const uint32_t b_src = a_src + a_stage_bytes;
-#pragma unroll 1
-        for (int t = 0; t < 9; ++t) {
-          const int dy = t / 3, dx = t % 3;
-          const uint32_t a_tap = p.safe_a ? a_src + t * A_SAFE_TILE : a_src + (dy * HALO_W + dx) * ROW_BYTES;
-          const uint32_t a_sbo = p.safe_a ? 8u * ROW_BYTES : (uint32_t)(HALO_W * ROW_BYTES);
-          const uint32_t b_tap = b_src + t * p.N * ROW_BYTES;
+    // The whole warp follows the barriers; one elected lane issues (warp-uniform control flow
+    // lets ptxas keep descriptors in uniform registers without a per-instruction election loop).
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
+    // Descriptor templates: everything but the 14-bit start-address field (addr >> 4).  A shared
+    // memory address is < 2^18, so adding (bytes >> 4) never carries out of the field; the
+    // per-MMA work is one add per operand (every dependent ALU op of the single issuing thread
+    // costs its full latency).
+    const uint64_t a_tmpl = make_desc(0, HALO_W * ROW_BYTES);
+    const uint64_t b_tmpl = make_desc(0, 8u * ROW_BYTES);
+    const uint32_t nb = tap_bytes >> 4;      // one tap of B in 16-byte units
+    uint32_t a_it = 0, b_it = 0, t_it = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++t_it) {
+      const uint32_t acc = t_it & 1u;
+      mbar_wait(tmem_empty(acc), ((t_it >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + acc * MT * p.N;
+      uint32_t accum = 0u;   // first MMA of the item overwrites the accumulator
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        const int sA = a_it % p.sa;
+        const uint32_t phA = (a_it / p.sa) & 1u;
+        mbar_wait(fullA(sA), phA);
+        if (PASSES == 3) mbar_wait(convA(sA), phA);
+        const uint64_t a0 = a_tmpl + ((smem_base + sA * A_STAGE) >> 4);
+        for (int sl = 0; sl < slabs; ++sl) {
+          const int sB = b_it % p.sb;
+          mbar_wait(fullB(sB), (b_it / p.sb) & 1u);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t b0 = b_tmpl + ((b_base + sB * b_slab) >> 4);
+            for (int dyl = 0; dyl < p.dys; ++dyl) {
+              uint64_t a_dy = a0 + (uint32_t)((sl * p.dys + dyl) * HALO_W * (ROW_BYTES >> 4));
+              if (p.debug & 1) a_dy = make_desc(0, 8u * ROW_BYTES) + ((smem_base + sA * A_STAGE) >> 4);
+              const uint64_t b_dy = b0 + (uint32_t)(dyl * 3) * nb;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            umma_tf32(tmem_base, make_desc(a_tap + k * 32, a_sbo), make_desc(b_tap + k * 32, 8u * ROW_BYTES), idesc,
-                      (it > 0 || t > 0 || k > 0) ? 1u : 0u);
+              for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t bd = b_dy + (dx * nb + 2u * k);
+#pragma unroll
+                  for (int mt = 0; mt < MT; ++mt) {
+                    const uint32_t d = d0 + mt * p.N;
+                    const uint64_t ad = a_dy + ((p.debug & 1) ? (uint32_t)(k * 2)
+                                                              : (uint32_t)(((mt * TH * HALO_W + dx) * ROW_BYTES + k * 32) >> 4));
+                    umma_tf32(d, ad, bd, idesc, accum);
+                    if (PASSES == 3) {
+                      umma_tf32(d, ad, bd + (b_half >> 4), idesc, 1u);
+                      umma_tf32(d, ad + (A_PART >> 4), bd, idesc, 1u);
+                    }
+                  }
+                  accum = 1u;
+                }
+              }
+            }
+            umma_commit(emptyB(sB));
+            if (sl == slabs - 1) {
+              umma_commit(emptyA(sA));
+              if (kc == p.kchunks - 1) umma_commit(tmem_full(acc));
+            }
+          }
+          __syncwarp();
+          accum = 1u;
+          ++b_it;
+        }
+        ++a_it;
+      }
+    }
+  } else if (warp < 6) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;                  // accumulator row = pixel within the sub-tile
+    uint32_t t_it = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++t_it) {
+      const int b = item / per_img, r = item % per_img;
+      const int y0 = (r / p.tiles_x) * TH * MT, x0 = (r % p.tiles_x) * TW;
+      const uint32_t acc = t_it & 1u;
+      mbar_wait(tmem_full(acc), (t_it >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+        const int gy = y0 + mt * TH + m / TW, gx = x0 + m % TW;
+        const bool inb = (gy < p.H) && (gx < p.W);
+        const size_t pix = ((size_t)b * p.H + (inb ? gy : 0)) * p.W + (inb ? gx : 0);
+#pragma unroll 1
+        for (int c0 = 0; c0 < p.N; c0 += 16) {
+          float v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (acc * MT + mt) * p.N + (uint32_t)c0, v);
+          if (!inb || c0 >= p.cout) continue;
+          if (p.bias) {   // bias / scale are padded to >= N entries and 16-byte aligned
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
+              v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
+            }
+          }
+          if (p.scale) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + j));
+              v[j] *= t4.x; v[j + 1] *= t4.y; v[j + 2] *= t4.z; v[j + 3] *= t4.w;
+            }
+          }
+          if (p.act == HCF_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (p.act == HCF_ACT_LRELU) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
+          }
+          if (p.out_vec && c0 + 15 < p.cout) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              if (p.res1) {
+                const float4 rr = __ldg(reinterpret_cast<const float4*>(p.res1 + pix * p.res1_ld + c0 + j));
+                o.x = o.x * p.alpha1 + rr.x; o.y = o.y * p.alpha1 + rr.y;
+                o.z = o.z * p.alpha1 + rr.z; o.w = o.w * p.alpha1 + rr.w;
+              }
+              if (p.res2) {
+                const float4 rr = __ldg(reinterpret_cast<const float4*>(p.res2 + pix * p.res2_ld + c0 + j));
+                o.x = o.x * p.alpha2 + rr.x; o.y = o.y * p.alpha2 + rr.y;
+                o.z = o.z * p.alpha2 + rr.z; o.w = o.w * p.alpha2 + rr.w;
+              }
+              *reinterpret_cast<float4*>(p.out + pix * p.out_ld + c0 + j) = o;
+              if (p.out2) *reinterpret_cast<float4*>(p.out2 + pix * p.out2_ld + c0 + j) = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int c = c0 + j;
+              if (c < p.cout) {
+                float t = v[j];
+                if (p.res1) t = t * p.alpha1 + __ldg(p.res1 + pix * p.res1_ld + c);
+                if (p.res2) t = t * p.alpha2 + __ldg(p.res2 + pix * p.res2_ld + c);
+                p.out[pix * p.out_ld + c] = t;
+                if (p.out2) p.out2[pix * p.out2_ld + c] = t;
+              }
+            }
           }
         }
-        umma_commit(empty_bar(s));   // frees the smem stage when these MMAs retire
       }
-      umma_commit(tmem_full_bar);    // accumulator complete
+      tc_fence_before();
+      mbar_arrive(tmem_empty(acc));   // all TMEM reads of this item are complete (wait::ld above)
     }
   } else {
-    // ===================== converter (3-pass only), then epilogue =====================
-    const int et = threadIdx.x - 64;   // 0..127
-    if (p.passes == 3) {
-      // The converters follow EVERY stage phase in order (an mbarrier waiter may never fall
-      // two phases behind) and release the stage together with the MMA commit.
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-        mbar_wait(full_bar(s), ph);
-        if (it >= 2 * p.kchunks) {
-          float4* a = reinterpret_cast<float4*>(gen_base + (size_t)s * stage_bytes);
-          const int n4 = (p.safe_a ? 9 * A_SAFE_TILE : A_HALO_BYTES) / 16;
-          for (int i = et; i < n4; i += 128) {
-            float4 v = a[i];
+    // ===================== A_lo converters (PASSES == 3) =====================
+    if (PASSES == 3) {
+      const int et = threadIdx.x - 192;   // 0..127
+      uint32_t a_it = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        for (int kc = 0; kc < p.kchunks; ++kc, ++a_it) {
+          const int sA = a_it % p.sa;
+          mbar_wait(fullA(sA), (a_it / p.sa) & 1u);
+          const float4* src = reinterpret_cast<const float4*>(gen_base + (size_t)sA * A_STAGE);
+          float4* dst = reinterpret_cast<float4*>(gen_base + (size_t)sA * A_STAGE + A_PART);
+          for (int i = et; i < A_BYTES / 16; i += 128) {
+            float4 v = src[i];
             v.x -= __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
             v.y -= __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
             v.z -= __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
             v.w -= __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-            a[i] = v;
+            dst[i] = v;
           }
           fence_async_smem();
-          mbar_arrive(conv_bar(s));
-        }
-        mbar_arrive(empty_bar(s));
-      }
-    }
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int m = q * 32 + lane;                  // accumulator row = pixel within the tile
-    const int gy = y0 + m / TW, gx = x0 + m % TW;
-    const bool inb = (gy < p.H) && (gx < p.W);
-    const size_t pix = ((size_t)b * p.H + (inb ? gy : 0)) * p.W + (inb ? gx : 0);
-    for (int c0 = 0; c0 < p.N; c0 += 16) {
-      float v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      if (!inb || c0 >= p.cout) continue;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int c = c0 + j;
-        float t = v[j];
-        if (p.bias) t += __ldg(p.bias + c);
-        if (p.scale) t *= __ldg(p.scale + c);
-        if (p.act == HCF_ACT_RELU) t = fmaxf(t, 0.f);
-        else if (p.act == HCF_ACT_LRELU) t = t > 0.f ? t : 0.2f * t;
-        v[j] = t;
-      }
-      if (p.out_vec && c0 + 15 < p.cout) {
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          if (p.res1) {
-            const float4 r = __ldg(reinterpret_cast<const float4*>(p.res1 + pix * p.res1_ld + c0 + j));
-            o.x = o.x * p.alpha1 + r.x; o.y = o.y * p.alpha1 + r.y; o.z = o.z * p.alpha1 + r.z; o.w = o.w * p.alpha1 + r.w;
-          }
-          if (p.res2) {
-            const float4 r = __ldg(reinterpret_cast<const float4*>(p.res2 + pix * p.res2_ld + c0 + j));
-            o.x = o.x * p.alpha2 + r.x; o.y = o.y * p.alpha2 + r.y; o.z = o.z * p.alpha2 + r.z; o.w = o.w * p.alpha2 + r.w;
-          }
-          *reinterpret_cast<float4*>(p.out + pix * p.out_ld + c0 + j) = o;
-          if (p.out2) *reinterpret_cast<float4*>(p.out2 + pix * p.out2_ld + c0 + j) = o;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int c = c0 + j;
-          if (c < p.cout) {
-            float t = v[j];
-            if (p.res1) t = t * p.alpha1 + __ldg(p.res1 + pix * p.res1_ld + c);
-            if (p.res2) t = t * p.alpha2 + __ldg(p.res2 + pix * p.res2_ld + c);
-            p.out[pix * p.out_ld + c] = t;
-            if (p.out2) p.out2[pix * p.out2_ld + c] = t;
-          }
+          mbar_arrive(convA(sA));
         }
       }
     }
@@ -343,12 +425,48 @@ static EncodeTiledFn get_encode() {
 
 static int n_for(int cout) { return (cout + 15) / 16 * 16; }
 
-static int stages_for(int N, int safe_a) {
-  const int a = safe_a ? 9 * A_SAFE_TILE : A_HALO_STAGE;
-  const int per = a + 9 * N * ROW_BYTES;
-  int s = (SMEM_LIMIT - 2048) / per;
-  if (s > 4) s = 4;
-  return s;
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = NUM_SMS_FALLBACK;
+  }
+  return n;
+}
+
+// ring depths and B slab granularity that fit in shared memory; false if nothing fits
+static bool pick_rings(int mt, int passes, int N, int* sa, int* sb, int* dys, size_t* smem) {
+  const int a_stage = a_part(mt) * (passes == 3 ? 2 : 1);
+  const int budget = SMEM_LIMIT - 1024 - 512;
+  // 1) whole-chunk B stages (one barrier round trip per chunk) if >= 2 of them fit beside >= 2 A stages
+  {
+    const int b_slab = 9 * N * ROW_BYTES * (passes == 3 ? 2 : 1);
+    for (int b = 3; b >= 2; --b)
+      for (int a = 4; a >= 2; --a)
+        if (a * a_stage + b * b_slab <= budget && (a >= 3 || b == 2)) {
+          *sa = a; *sb = b; *dys = 3;
+          *smem = 1024 + (size_t)a * a_stage + (size_t)b * b_slab + 512;
+          return true;
+        }
+  }
+  // 2) per-dy slabs
+  const int b_slab = 3 * N * ROW_BYTES * (passes == 3 ? 2 : 1);
+  int best_a = 0;
+  for (int a = 4; a >= 1 && !best_a; --a)
+    if (a * a_stage + 3 * b_slab <= budget) best_a = a;
+  if (!best_a) return false;
+  int best_b = (budget - best_a * a_stage) / b_slab;
+  if (best_b > 9) best_b = 9;
+  if (best_a > 2 && best_b < 4) {
+    --best_a;
+    best_b = (budget - best_a * a_stage) / b_slab;
+    if (best_b > 9) best_b = 9;
+  }
+  *sa = best_a; *sb = best_b; *dys = 1;
+  *smem = 1024 + (size_t)best_a * a_stage + (size_t)best_b * b_slab + 512;
+  return true;
 }
 
 }  // namespace tc
@@ -358,6 +476,7 @@ struct hcf_conv_tc_plan {
   CUtensorMap amap;
   hcf::tc::Params p;
   size_t smem_bytes;
+  int mt, passes;
   dim3 grid;
 };
 
@@ -372,7 +491,7 @@ extern "C" int hcf_conv_tc_supported(const hcf_conv_args* a) {
 
 extern "C" int64_t hcf_conv_tc_weight_bytes(int32_t kin, int32_t cout) {
   if (kin % 32 != 0 || cout < 1 || cout > 64) return 0;
-  return (int64_t)2 * (kin / 32) * 9 * hcf::tc::n_for(cout) * 128;
+  return (int64_t)(kin / 32) * 3 * 2 * 3 * hcf::tc::n_for(cout) * 128;
 }
 
 extern "C" int hcf_conv_tc_pack_weights(const float* w, int32_t kin, int32_t cout, float* image) {
@@ -380,21 +499,22 @@ extern "C" int hcf_conv_tc_pack_weights(const float* w, int32_t kin, int32_t cou
   HCF_REQUIRE(w && image && kin % 32 == 0 && cout >= 1 && cout <= 64, "tc_pack: bad args");
   const int N = tc::n_for(cout), KC = kin / 32;
   memset(image, 0, (size_t)hcf_conv_tc_weight_bytes(kin, cout));
-  for (int part = 0; part < 2; ++part)
-    for (int kc = 0; kc < KC; ++kc)
-      for (int t = 0; t < 9; ++t)
-        for (int n = 0; n < cout; ++n)
-          for (int j = 0; j < 32; ++j) {
-            const float v = w[(((size_t)n * kin + kc * 32 + j) * 3 + t / 3) * 3 + t % 3];
-            uint32_t bits;
-            memcpy(&bits, &v, 4);
-            bits &= 0xFFFFE000u;
-            float hi;
-            memcpy(&hi, &bits, 4);
-            const float val = part == 0 ? v : v - hi;
-            const int chunk = (j / 4) ^ (n & 7);   // 128B swizzle: 16-byte chunk index XOR row-in-atom
-            image[((((size_t)part * KC + kc) * 9 + t) * N + n) * 32 + chunk * 4 + (j & 3)] = val;
-          }
+  for (int kc = 0; kc < KC; ++kc)
+    for (int part = 0; part < 2; ++part)
+      for (int dy = 0; dy < 3; ++dy)
+        for (int dx = 0; dx < 3; ++dx)
+          for (int n = 0; n < cout; ++n)
+            for (int j = 0; j < 32; ++j) {
+              const float v = w[(((size_t)n * kin + kc * 32 + j) * 3 + dy) * 3 + dx];
+              uint32_t bits;
+              memcpy(&bits, &v, 4);
+              bits &= 0xFFFFE000u;
+              float hi;
+              memcpy(&hi, &bits, 4);
+              const float val = part == 0 ? v : v - hi;
+              const int chunk = (j / 4) ^ (n & 7);   // 128B swizzle: 16-byte chunk index XOR row-in-atom
+              image[(((((size_t)kc * 2 + part) * 3 + dy) * 3 + dx) * N + n) * 32 + chunk * 4 + (j & 3)] = val;
+            }
   return 0;
 }
 
@@ -412,20 +532,35 @@ extern "C" int hcf_conv_tc_plan_create(const hcf_conv_args* a, const float* wtc,
   HCF_REQUIRE(enc != nullptr, "tc_plan: cuTensorMapEncodeTiled entry point not found");
   hcf_conv_tc_plan* pl = new hcf_conv_tc_plan();
   tc::Params& p = pl->p;
-  const char* env = getenv("HCF_TC_SAFE_A");
-  p.safe_a = (env && env[0] == '1') ? 1 : 0;
   p.B = a->B; p.H = a->H; p.W = a->W;
   p.kchunks = a->seg[0].C / 32;
   p.N = tc::n_for(a->cout);
   p.cout = a->cout;
-  p.passes = passes;
-  p.stages = tc::stages_for(p.N, p.safe_a);
-  if (p.stages < 1) {
+  pl->passes = passes;
+  const int sms = tc::num_sms();
+  // sub-tiles per work item: 2 halves the weight traffic per pixel but quantises worse on small images
+  int mt = 1;
+  const char* env = getenv("HCF_TC_MT");
+  if (passes == 1) {
+    const long items1 = (long)a->B * ceil_div(a->H, 16) * ceil_div(a->W, 8);
+    const long items2 = (long)a->B * ceil_div(a->H, 32) * ceil_div(a->W, 8);
+    const double t1 = (double)ceil_div((int)items1, sms) * (tc::a_part(1) + 9.0 * p.N * 128);
+    const double t2 = (double)ceil_div((int)items2, sms) * (tc::a_part(2) + 9.0 * p.N * 128);
+    mt = (t2 < 0.95 * t1) ? 2 : 1;
+    if (env && (env[0] == '1' || env[0] == '2')) mt = env[0] - '0';
+  }
+  pl->mt = mt;
+  {
+    const char* dbg = getenv("HCF_TC_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+  }
+  if (!tc::pick_rings(mt, passes, p.N, &p.sa, &p.sb, &p.dys, &pl->smem_bytes)) {
     delete pl;
     set_error("tc_plan: tile does not fit in shared memory");
     return HCF_ENOTSUP;
   }
-  p.tiles_x = ceil_div(a->W, tc::TW); p.tiles_y = ceil_div(a->H, tc::TH);
+  p.tiles_x = ceil_div(a->W, tc::TW); p.tiles_y = ceil_div(a->H, tc::TH * mt);
+  p.n_items = p.tiles_x * p.tiles_y * a->B;
   p.wimg = wtc; p.bias = a->bias; p.scale = a->scale; p.act = a->act;
   p.out = a->out; p.out_ld = a->out_ld; p.out2 = a->out2; p.out2_ld = a->out2_ld;
   p.res1 = a->res1; p.res1_ld = a->res1_ld; p.alpha1 = a->alpha1;
@@ -439,22 +574,24 @@ extern "C" int hcf_conv_tc_plan_create(const hcf_conv_args* a, const float* wtc,
   const cuuint64_t dims[4] = {(cuuint64_t)a->seg[0].C, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->B};
   const cuuint64_t ld_b = (cuuint64_t)a->seg[0].ld * 4;
   const cuuint64_t strides[3] = {ld_b, ld_b * a->W, ld_b * a->W * a->H};
-  const cuuint32_t box_halo[4] = {(cuuint32_t)tc::KCH, (cuuint32_t)tc::HALO_W, (cuuint32_t)tc::HALO_H, 1};
-  const cuuint32_t box_safe[4] = {(cuuint32_t)tc::KCH, (cuuint32_t)tc::TW, (cuuint32_t)tc::TH, 1};
+  const cuuint32_t box[4] = {(cuuint32_t)tc::KCH, (cuuint32_t)tc::HALO_W, (cuuint32_t)tc::halo_rows(mt), 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(&pl->amap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a->seg[0].ptr), dims, strides,
-                   p.safe_a ? box_safe : box_halo, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     delete pl;
     set_error("tc_plan: cuTensorMapEncodeTiled failed with %d", (int)r);
     return HCF_EINVAL;
   }
-  const size_t a_stage = p.safe_a ? 9 * tc::A_SAFE_TILE : tc::A_HALO_STAGE;
-  pl->smem_bytes = 1024 + p.stages * (a_stage + 9 * p.N * tc::ROW_BYTES) + 8 * (3 * p.stages + 1) + 16;
-  pl->grid = dim3((unsigned)(p.tiles_x * p.tiles_y * p.B));
-  cudaError_t e = cudaFuncSetAttribute(tc::conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)tc::SMEM_LIMIT);
+  pl->grid = dim3((unsigned)(p.n_items < sms ? p.n_items : sms));
+  cudaError_t e;
+  if (passes == 3)
+    e = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT);
+  else if (mt == 2)
+    e = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT);
+  else
+    e = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT);
   if (e != cudaSuccess) {
     delete pl;
     set_error("tc_plan: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -467,7 +604,13 @@ extern "C" int hcf_conv_tc_plan_create(const hcf_conv_args* a, const float* wtc,
 extern "C" int hcf_conv_tc_run(const hcf_conv_tc_plan* pl, void* stream) {
   using namespace hcf;
   HCF_REQUIRE(pl != nullptr, "tc_run: null plan");
-  tc::conv3x3_tc_kernel<<<pl->grid, tc::NTHREADS, pl->smem_bytes, (cudaStream_t)stream>>>(pl->amap, pl->p);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pl->passes == 3)
+    tc::conv3x3_tc_kernel<1, 3><<<pl->grid, 320, pl->smem_bytes, st>>>(pl->amap, pl->p);
+  else if (pl->mt == 2)
+    tc::conv3x3_tc_kernel<2, 1><<<pl->grid, 192, pl->smem_bytes, st>>>(pl->amap, pl->p);
+  else
+    tc::conv3x3_tc_kernel<1, 1><<<pl->grid, 192, pl->smem_bytes, st>>>(pl->amap, pl->p);
   return finish_launch("hcf_conv_tc_run");
 }
 
