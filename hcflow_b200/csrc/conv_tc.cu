@@ -33,26 +33,28 @@ namespace hcf {
 namespace tc {
 
 constexpr int TH = 16, TW = 8;               // sub-tile (UMMA M = 128)
-constexpr int HALO_W = TW + 2;
 constexpr int KCH = 32;                      // channels per K chunk (= 128 B rows)
 constexpr int ROW_BYTES = KCH * 4;           // 128
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int NUM_SMS_FALLBACK = 148;
 
-__host__ __device__ constexpr int halo_rows(int mt) { return TH * mt + 2; }
-__host__ __device__ constexpr int a_bytes(int mt) { return halo_rows(mt) * HALO_W * ROW_BYTES; }
-__host__ __device__ constexpr int a_part(int mt) { return (a_bytes(mt) + 1023) / 1024 * 1024; }
+// ks = 3: (16*mt+2) x 10 halo tile; ks = 1: plain 16*mt x 8 tile
+__host__ __device__ constexpr int halo_w(int ks) { return TW + (ks - 1); }
+__host__ __device__ constexpr int halo_rows(int mt, int ks) { return TH * mt + (ks - 1); }
+__host__ __device__ constexpr int a_bytes(int mt, int ks) { return halo_rows(mt, ks) * halo_w(ks) * ROW_BYTES; }
+__host__ __device__ constexpr int a_part(int mt, int ks) { return (a_bytes(mt, ks) + 1023) / 1024 * 1024; }
 
 struct Params {
   int B, H, W;
-  int kchunks;   // Cin / 32
+  int kchunks;   // total 32-channel chunks over all segments
+  int kc_end0, kc_end1;   // chunks [0,kc_end0) come from tensor map 0, [kc_end0,kc_end1) from map 1, rest from map 2
   int N;         // UMMA N (multiple of 16, <= 64)
   int cout;
   int sa, sb;    // ring depths
   int dys;       // dy rows of taps per B slab: 3 (whole chunk) or 1
-  int debug;     // timing experiments only (HCF_TC_DEBUG): bit0 = 1024B-aligned A descriptors (wrong results)
+  int debug;     // timing experiments only (HCF_TC_DEBUG, wrong results): 1 = aligned A descriptors, 2 = no MMAs, 4 = no loads, 8 = no epilogue stores
   int tiles_x, tiles_y, n_items;
-  const float* wimg;   // [kchunks][2 (raw, lo)][3 dy][3 dx][N][32] pre-swizzled
+  const float* wimg;   // [kchunks][2 (raw, lo)][ks dy][ks dx][N][32] pre-swizzled
   const float* bias;
   const float* scale;
   int act;
@@ -144,19 +146,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 }
 
 // ------------------------------------------------------------------ kernel
-template <int MT, int PASSES>
+template <int MT, int PASSES, int KS>
 __global__ void __launch_bounds__(PASSES == 3 ? 320 : 192, 1)
-conv3x3_tc_kernel(const __grid_constant__ CUtensorMap amap, const Params p) {
-  constexpr int A_BYTES = a_bytes(MT);
-  constexpr int A_PART = a_part(MT);
+conv_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant__ CUtensorMap amap1,
+               const __grid_constant__ CUtensorMap amap2, const Params p) {
+  constexpr int HALO = KS / 2;
+  constexpr int HALO_W = halo_w(KS);
+  constexpr int A_BYTES = a_bytes(MT, KS);
+  constexpr int A_PART = a_part(MT, KS);
   constexpr int A_STAGE = A_PART * (PASSES == 3 ? 2 : 1);   // [raw | lo]
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  if (p.debug & 16) return;   // timing experiment: launch cost only
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t tap_bytes = (uint32_t)p.N * ROW_BYTES;          // one tap of B: [N][32 ch]
-  const uint32_t b_half = 3u * p.dys * tap_bytes;                // raw (or lo) taps of one slab
+  const uint32_t b_half = (uint32_t)KS * p.dys * tap_bytes;      // raw (or lo) taps of one slab
   const uint32_t b_slab = b_half * (PASSES == 3 ? 2u : 1u);      // [raw taps | lo taps]
-  const int slabs = 3 / p.dys;                                   // slabs per 32-channel chunk
+  const int slabs = KS / p.dys;                                  // slabs per 32-channel chunk
   const uint32_t b_base = smem_base + p.sa * A_STAGE;
   const uint32_t bar_base = b_base + p.sb * b_slab;
   auto fullA = [&](int s) { return bar_base + 8u * s; };
@@ -174,7 +180,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap amap, const Params p) {
   const uint32_t tmem_cols = need_cols <= 32 ? 32u : (need_cols <= 64 ? 64u : (need_cols <= 128 ? 128u : 256u));
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&amap) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&amap0) : "memory");
+    if (p.kc_end0 < p.kchunks) asm volatile("prefetch.tensormap [%0];" ::"l"(&amap1) : "memory");
+    if (p.kc_end1 < p.kchunks) asm volatile("prefetch.tensormap [%0];" ::"l"(&amap2) : "memory");
     for (int s = 0; s < p.sa; ++s) {
       mbar_init(fullA(s), 1);
       mbar_init(emptyA(s), 1);
@@ -202,28 +210,40 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap amap, const Params p) {
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   const int per_img = p.tiles_x * p.tiles_y;
+  const int n_items = (p.debug & 32) ? 0 : p.n_items;   // timing experiment: prologue + teardown only
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t a_it = 0, b_it = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int b = item / per_img, r = item % per_img;
         const int y0 = (r / p.tiles_x) * TH * MT, x0 = (r % p.tiles_x) * TW;
         for (int kc = 0; kc < p.kchunks; ++kc) {
           const int sA = a_it % p.sa;
           mbar_wait(emptyA(sA), ((a_it / p.sa) & 1u) ^ 1u);
-          mbar_expect_tx(fullA(sA), A_BYTES);
-          tma_load_4d(smem_base + sA * A_STAGE, &amap, fullA(sA), kc * KCH, x0 - 1, y0 - 1, b);
+          if (p.debug & 4) {
+            mbar_arrive(fullA(sA));
+          } else {
+            mbar_expect_tx(fullA(sA), A_BYTES);
+            const CUtensorMap* mp = kc < p.kc_end0 ? &amap0 : (kc < p.kc_end1 ? &amap1 : &amap2);
+            const int kl = kc < p.kc_end0 ? kc : (kc < p.kc_end1 ? kc - p.kc_end0 : kc - p.kc_end1);
+            tma_load_4d(smem_base + sA * A_STAGE, mp, fullA(sA), kl * KCH, x0 - HALO, y0 - HALO, b);
+          }
           ++a_it;
           for (int sl = 0; sl < slabs; ++sl) {
             const int sB = b_it % p.sb;
             mbar_wait(emptyB(sB), ((b_it / p.sb) & 1u) ^ 1u);
+            if (p.debug & 4) {
+              mbar_arrive(fullB(sB));
+              ++b_it;
+              continue;
+            }
             mbar_expect_tx(fullB(sB), b_slab);
-            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wimg) + (size_t)kc * (18u * tap_bytes) +
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wimg) + (size_t)kc * (2u * KS * KS * tap_bytes) +
                                  (size_t)sl * b_half;
             bulk_load(b_base + sB * b_slab, src, b_half, fullB(sB));
-            if (PASSES == 3) bulk_load(b_base + sB * b_slab + b_half, src + 9u * tap_bytes, b_half, fullB(sB));
+            if (PASSES == 3) bulk_load(b_base + sB * b_slab + b_half, src + (uint32_t)(KS * KS) * tap_bytes, b_half, fullB(sB));
             ++b_it;
           }
         }
@@ -242,7 +262,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap amap, const Params p) {
     const uint64_t b_tmpl = make_desc(0, 8u * ROW_BYTES);
     const uint32_t nb = tap_bytes >> 4;      // one tap of B in 16-byte units
     uint32_t a_it = 0, b_it = 0, t_it = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++t_it) {
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++t_it) {
       const uint32_t acc = t_it & 1u;
       mbar_wait(tmem_empty(acc), ((t_it >> 1) & 1u) ^ 1u);
       tc_fence_after();
@@ -260,12 +280,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap amap, const Params p) {
           tc_fence_after();
           if (elect_one()) {
             const uint64_t b0 = b_tmpl + ((b_base + sB * b_slab) >> 4);
-            for (int dyl = 0; dyl < p.dys; ++dyl) {
+            for (int dyl = 0; dyl < ((p.debug & 2) ? 0 : p.dys); ++dyl) {
               uint64_t a_dy = a0 + (uint32_t)((sl * p.dys + dyl) * HALO_W * (ROW_BYTES >> 4));
               if (p.debug & 1) a_dy = make_desc(0, 8u * ROW_BYTES) + ((smem_base + sA * A_STAGE) >> 4);
-              const uint64_t b_dy = b0 + (uint32_t)(dyl * 3) * nb;
+              const uint64_t b_dy = b0 + (uint32_t)(dyl * KS) * nb;
 #pragma unroll
-              for (int dx = 0; dx < 3; ++dx) {
+              for (int dx = 0; dx < KS; ++dx) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   const uint64_t bd = b_dy + (dx * nb + 2u * k);
@@ -302,7 +322,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap amap, const Params p) {
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int m = q * 32 + lane;                  // accumulator row = pixel within the sub-tile
     uint32_t t_it = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++t_it) {
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++t_it) {
       const int b = item / per_img, r = item % per_img;
       const int y0 = (r / p.tiles_x) * TH * MT, x0 = (r % p.tiles_x) * TW;
       const uint32_t acc = t_it & 1u;
@@ -317,7 +337,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap amap, const Params p) {
         for (int c0 = 0; c0 < p.N; c0 += 16) {
           float v[16];
           tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (acc * MT + mt) * p.N + (uint32_t)c0, v);
-          if (!inb || c0 >= p.cout) continue;
+          if (!inb || c0 >= p.cout || (p.debug & 8)) continue;
           if (p.bias) {   // bias / scale are padded to >= N entries and 16-byte aligned
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
@@ -379,7 +399,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap amap, const Params p) {
     if (PASSES == 3) {
       const int et = threadIdx.x - 192;   // 0..127
       uint32_t a_it = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         for (int kc = 0; kc < p.kchunks; ++kc, ++a_it) {
           const int sA = a_it % p.sa;
           mbar_wait(fullA(sA), (a_it / p.sa) & 1u);
@@ -437,20 +457,21 @@ static int num_sms() {
 }
 
 // ring depths and B slab granularity that fit in shared memory; false if nothing fits
-static bool pick_rings(int mt, int passes, int N, int* sa, int* sb, int* dys, size_t* smem) {
-  const int a_stage = a_part(mt) * (passes == 3 ? 2 : 1);
+static bool pick_rings(int mt, int passes, int ks, int N, int* sa, int* sb, int* dys, size_t* smem) {
+  const int a_stage = a_part(mt, ks) * (passes == 3 ? 2 : 1);
   const int budget = SMEM_LIMIT - 1024 - 512;
   // 1) whole-chunk B stages (one barrier round trip per chunk) if >= 2 of them fit beside >= 2 A stages
   {
-    const int b_slab = 9 * N * ROW_BYTES * (passes == 3 ? 2 : 1);
+    const int b_slab = ks * ks * N * ROW_BYTES * (passes == 3 ? 2 : 1);
     for (int b = 3; b >= 2; --b)
       for (int a = 4; a >= 2; --a)
         if (a * a_stage + b * b_slab <= budget && (a >= 3 || b == 2)) {
-          *sa = a; *sb = b; *dys = 3;
+          *sa = a; *sb = b; *dys = ks;
           *smem = 1024 + (size_t)a * a_stage + (size_t)b * b_slab + 512;
           return true;
         }
   }
+  if (ks == 1) return false;
   // 2) per-dy slabs
   const int b_slab = 3 * N * ROW_BYTES * (passes == 3 ? 2 : 1);
   int best_a = 0;
@@ -469,43 +490,59 @@ static bool pick_rings(int mt, int passes, int N, int* sa, int* sb, int* dys, si
   return true;
 }
 
+typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const Params);
+
+static KernelFn pick_kernel(int mt, int passes, int ks) {
+  if (ks == 1) return passes == 3 ? conv_tc_kernel<1, 3, 1> : conv_tc_kernel<1, 1, 1>;
+  if (passes == 3) return conv_tc_kernel<1, 3, 3>;
+  return mt == 2 ? conv_tc_kernel<2, 1, 3> : conv_tc_kernel<1, 1, 3>;
+}
+
 }  // namespace tc
 }  // namespace hcf
 
 struct hcf_conv_tc_plan {
-  CUtensorMap amap;
+  CUtensorMap amap[3];
   hcf::tc::Params p;
+  hcf::tc::KernelFn fn;
   size_t smem_bytes;
-  int mt, passes;
+  int threads;
   dim3 grid;
 };
 
+// Any channel count works per segment: the tensor map's channel extent is the segment's C and the
+// 32-channel box is zero-filled beyond it (the packed weights carry zero rows there too).
 extern "C" int hcf_conv_tc_supported(const hcf_conv_args* a) {
   if (!a) return 0;
-  if (a->ks != 3 || a->nseg != 1) return 0;
-  if (a->seg[0].up_shift != 0 || a->seg[0].C % 32 != 0 || a->seg[0].C < 32) return 0;
-  if (a->seg[0].ld % 4 != 0 || !hcf::aligned16(a->seg[0].ptr)) return 0;
+  if (a->ks != 3 && a->ks != 1) return 0;
+  if (a->nseg < 1 || a->nseg > 3) return 0;
+  for (int i = 0; i < a->nseg; ++i) {
+    if (a->seg[i].up_shift != 0 || a->seg[i].C < 1) return 0;
+    if (a->seg[i].ld % 4 != 0 || !hcf::aligned16(a->seg[i].ptr)) return 0;
+  }
   if (a->cout < 1 || a->cout > 64) return 0;
   return 1;
 }
 
-extern "C" int64_t hcf_conv_tc_weight_bytes(int32_t kin, int32_t cout) {
-  if (kin % 32 != 0 || cout < 1 || cout > 64) return 0;
-  return (int64_t)(kin / 32) * 3 * 2 * 3 * hcf::tc::n_for(cout) * 128;
+// kin = number of (segment-padded) input channels, a multiple of 32
+extern "C" int64_t hcf_conv_tc_weight_bytes(int32_t kin, int32_t cout, int32_t ks) {
+  if (kin % 32 != 0 || cout < 1 || cout > 64 || (ks != 1 && ks != 3)) return 0;
+  return (int64_t)(kin / 32) * 2 * ks * ks * hcf::tc::n_for(cout) * 128;
 }
 
-extern "C" int hcf_conv_tc_pack_weights(const float* w, int32_t kin, int32_t cout, float* image) {
+// w: [cout][kin][ks][ks] fp32 (host), kin already padded per segment to multiples of 32
+extern "C" int hcf_conv_tc_pack_weights(const float* w, int32_t kin, int32_t cout, int32_t ks, float* image) {
   using namespace hcf;
-  HCF_REQUIRE(w && image && kin % 32 == 0 && cout >= 1 && cout <= 64, "tc_pack: bad args");
+  HCF_REQUIRE(w && image && kin % 32 == 0 && cout >= 1 && cout <= 64 && (ks == 1 || ks == 3), "tc_pack: bad args");
   const int N = tc::n_for(cout), KC = kin / 32;
-  memset(image, 0, (size_t)hcf_conv_tc_weight_bytes(kin, cout));
+  memset(image, 0, (size_t)hcf_conv_tc_weight_bytes(kin, cout, ks));
   for (int kc = 0; kc < KC; ++kc)
     for (int part = 0; part < 2; ++part)
-      for (int dy = 0; dy < 3; ++dy)
-        for (int dx = 0; dx < 3; ++dx)
+      for (int dy = 0; dy < ks; ++dy)
+        for (int dx = 0; dx < ks; ++dx)
           for (int n = 0; n < cout; ++n)
             for (int j = 0; j < 32; ++j) {
-              const float v = w[(((size_t)n * kin + kc * 32 + j) * 3 + dy) * 3 + dx];
+              const float v = w[(((size_t)n * kin + kc * 32 + j) * ks + dy) * ks + dx];
               uint32_t bits;
               memcpy(&bits, &v, 4);
               bits &= 0xFFFFE000u;
@@ -513,7 +550,7 @@ extern "C" int hcf_conv_tc_pack_weights(const float* w, int32_t kin, int32_t cou
               memcpy(&hi, &bits, 4);
               const float val = part == 0 ? v : v - hi;
               const int chunk = (j / 4) ^ (n & 7);   // 128B swizzle: 16-byte chunk index XOR row-in-atom
-              image[(((((size_t)kc * 2 + part) * 3 + dy) * 3 + dx) * N + n) * 32 + chunk * 4 + (j & 3)] = val;
+              image[(((((size_t)kc * 2 + part) * ks + dy) * ks + dx) * N + n) * 32 + chunk * 4 + (j & 3)] = val;
             }
   return 0;
 }
@@ -531,30 +568,39 @@ extern "C" int hcf_conv_tc_plan_create(const hcf_conv_args* a, const float* wtc,
   tc::EncodeTiledFn enc = tc::get_encode();
   HCF_REQUIRE(enc != nullptr, "tc_plan: cuTensorMapEncodeTiled entry point not found");
   hcf_conv_tc_plan* pl = new hcf_conv_tc_plan();
+  memset(pl, 0, sizeof(*pl));
   tc::Params& p = pl->p;
+  const int ks = a->ks;
   p.B = a->B; p.H = a->H; p.W = a->W;
-  p.kchunks = a->seg[0].C / 32;
+  int kc = 0;
+  p.kc_end0 = p.kc_end1 = 1 << 30;
+  for (int i = 0; i < a->nseg; ++i) {
+    kc += (a->seg[i].C + 31) / 32;
+    if (i == 0) p.kc_end0 = kc;
+    if (i == 1) p.kc_end1 = kc;
+  }
+  p.kchunks = kc;
+  if (a->nseg == 1) p.kc_end0 = p.kc_end1 = kc;
+  if (a->nseg == 2) p.kc_end1 = kc;
   p.N = tc::n_for(a->cout);
   p.cout = a->cout;
-  pl->passes = passes;
   const int sms = tc::num_sms();
   // sub-tiles per work item: 2 halves the weight traffic per pixel but quantises worse on small images
   int mt = 1;
   const char* env = getenv("HCF_TC_MT");
-  if (passes == 1) {
+  if (passes == 1 && ks == 3) {
     const long items1 = (long)a->B * ceil_div(a->H, 16) * ceil_div(a->W, 8);
     const long items2 = (long)a->B * ceil_div(a->H, 32) * ceil_div(a->W, 8);
-    const double t1 = (double)ceil_div((int)items1, sms) * (tc::a_part(1) + 9.0 * p.N * 128);
-    const double t2 = (double)ceil_div((int)items2, sms) * (tc::a_part(2) + 9.0 * p.N * 128);
-    mt = (t2 < 0.95 * t1) ? 2 : 1;
+    const double t1 = (double)ceil_div((int)items1, sms) * (tc::a_part(1, 3) + 9.0 * p.N * 128);
+    const double t2 = (double)ceil_div((int)items2, sms) * (tc::a_part(2, 3) + 9.0 * p.N * 128);
+    mt = (t2 < 0.80 * t1) ? 2 : 1;
     if (env && (env[0] == '1' || env[0] == '2')) mt = env[0] - '0';
   }
-  pl->mt = mt;
   {
     const char* dbg = getenv("HCF_TC_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
   }
-  if (!tc::pick_rings(mt, passes, p.N, &p.sa, &p.sb, &p.dys, &pl->smem_bytes)) {
+  if (!tc::pick_rings(mt, passes, ks, p.N, &p.sa, &p.sb, &p.dys, &pl->smem_bytes)) {
     delete pl;
     set_error("tc_plan: tile does not fit in shared memory");
     return HCF_ENOTSUP;
@@ -571,27 +617,27 @@ extern "C" int hcf_conv_tc_plan_create(const hcf_conv_args* a, const float* wtc,
   if (a->res2) ov = ov && aligned16(a->res2) && a->res2_ld % 4 == 0;
   p.out_vec = ov ? 1 : 0;
 
-  const cuuint64_t dims[4] = {(cuuint64_t)a->seg[0].C, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->B};
-  const cuuint64_t ld_b = (cuuint64_t)a->seg[0].ld * 4;
-  const cuuint64_t strides[3] = {ld_b, ld_b * a->W, ld_b * a->W * a->H};
-  const cuuint32_t box[4] = {(cuuint32_t)tc::KCH, (cuuint32_t)tc::HALO_W, (cuuint32_t)tc::halo_rows(mt), 1};
+  const cuuint32_t box[4] = {(cuuint32_t)tc::KCH, (cuuint32_t)tc::halo_w(ks), (cuuint32_t)tc::halo_rows(mt, ks), 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(&pl->amap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a->seg[0].ptr), dims, strides,
-                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    delete pl;
-    set_error("tc_plan: cuTensorMapEncodeTiled failed with %d", (int)r);
-    return HCF_EINVAL;
+  for (int i = 0; i < 3; ++i) {
+    const hcf_seg& sg = a->seg[i < a->nseg ? i : 0];   // unused maps alias segment 0 (never dereferenced)
+    const cuuint64_t dims[4] = {(cuuint64_t)sg.C, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->B};
+    const cuuint64_t ld_b = (cuuint64_t)sg.ld * 4;
+    const cuuint64_t strides[3] = {ld_b, ld_b * a->W, ld_b * a->W * a->H};
+    CUresult r = enc(&pl->amap[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(sg.ptr), dims, strides,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      delete pl;
+      set_error("tc_plan: cuTensorMapEncodeTiled failed with %d (segment %d, C %d, ld %d)", (int)r, i, sg.C, sg.ld);
+      return HCF_EINVAL;
+    }
   }
   pl->grid = dim3((unsigned)(p.n_items < sms ? p.n_items : sms));
-  cudaError_t e;
-  if (passes == 3)
-    e = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT);
-  else if (mt == 2)
-    e = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT);
-  else
-    e = cudaFuncSetAttribute(tc::conv3x3_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT);
+  pl->threads = passes == 3 ? 320 : 192;
+  pl->fn = tc::pick_kernel(mt, passes, ks);
+  cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(pl->fn),
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT);
   if (e != cudaSuccess) {
     delete pl;
     set_error("tc_plan: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -604,13 +650,7 @@ extern "C" int hcf_conv_tc_plan_create(const hcf_conv_args* a, const float* wtc,
 extern "C" int hcf_conv_tc_run(const hcf_conv_tc_plan* pl, void* stream) {
   using namespace hcf;
   HCF_REQUIRE(pl != nullptr, "tc_run: null plan");
-  cudaStream_t st = (cudaStream_t)stream;
-  if (pl->passes == 3)
-    tc::conv3x3_tc_kernel<1, 3><<<pl->grid, 320, pl->smem_bytes, st>>>(pl->amap, pl->p);
-  else if (pl->mt == 2)
-    tc::conv3x3_tc_kernel<2, 1><<<pl->grid, 192, pl->smem_bytes, st>>>(pl->amap, pl->p);
-  else
-    tc::conv3x3_tc_kernel<1, 1><<<pl->grid, 192, pl->smem_bytes, st>>>(pl->amap, pl->p);
+  pl->fn<<<pl->grid, pl->threads, pl->smem_bytes, (cudaStream_t)stream>>>(pl->amap[0], pl->amap[1], pl->amap[2], pl->p);
   return finish_launch("hcf_conv_tc_run");
 }
 

@@ -55,6 +55,16 @@ __global__ void __launch_bounds__(LT) squeeze_kernel(const float* __restrict__ s
     }
 }
 
+// channel-slice copy between two NHWC views of the same spatial size (Split / cat plumbing that
+// can not be a pure view because of TMA's 16-byte alignment rule)
+__global__ void __launch_bounds__(LT) copy_view_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                       int npix, int C, int src_ld, int dst_ld) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix * C) return;
+  const int pix = i / C, c = i % C;
+  dst[(size_t)pix * dst_ld + c] = src[(size_t)pix * src_ld + c];
+}
+
 // Haar: band k of channel c at low-res channel k*C + c.
 //   k0 = (a+b+c+d)/4, k1 = (a-b+c-d)/4, k2 = (a+b-c-d)/4, k3 = (a-b-c+d)/4
 //   with a=(2y,2x) b=(2y,2x+1) c=(2y+1,2x) d=(2y+1,2x+1)            (Basic.py:455-466)
@@ -141,3 +151,13 @@ extern "C" int hcf_squeeze2d(const hcf_squeeze_args* a, void* s) { return squeez
 extern "C" int hcf_unsqueeze2d(const hcf_squeeze_args* a, void* s) { return squeeze_like(a, s, 1, 0, "hcf_unsqueeze2d"); }
 extern "C" int hcf_haar_forward(const hcf_squeeze_args* a, void* s) { return squeeze_like(a, s, 0, 1, "hcf_haar_forward"); }
 extern "C" int hcf_haar_inverse(const hcf_squeeze_args* a, void* s) { return squeeze_like(a, s, 1, 1, "hcf_haar_inverse"); }
+
+extern "C" int hcf_copy_view(const hcf_squeeze_args* a, void* stream) {
+  using namespace hcf;
+  HCF_REQUIRE(a && a->src && a->dst, "copy_view: null args");
+  HCF_REQUIRE(a->B > 0 && a->C > 0 && a->H > 0 && a->W > 0 && a->src_ld >= a->C && a->dst_ld >= a->C, "copy_view: shape");
+  const int n = a->B * a->H * a->W * a->C;
+  copy_view_kernel<<<ceil_div(n, LT), LT, 0, (cudaStream_t)stream>>>(a->src, a->dst, a->B * a->H * a->W, a->C,
+                                                                     a->src_ld, a->dst_ld);
+  return finish_launch("hcf_copy_view");
+}

@@ -201,7 +201,8 @@ class Engine:
                     a.src, a.src_ld = self._vptr(op.src)
                     a.dst, a.dst_ld = self._vptr(op.dst)
                     fn = {"squeeze": lib.hcf_squeeze2d, "unsqueeze": lib.hcf_unsqueeze2d,
-                          "haar_fwd": lib.hcf_haar_forward, "haar_inv": lib.hcf_haar_inverse}[op.variant]
+                          "haar_fwd": lib.hcf_haar_forward, "haar_inv": lib.hcf_haar_inverse,
+                          "copy": lib.hcf_copy_view}[op.variant]
                 self._keep.append(a)
                 self.calls.append((fn, C.byref(a), "layout_" + op.variant))
             elif isinstance(op, P.DiracLogpOp):
@@ -223,11 +224,11 @@ class Engine:
         passes = {"tf32": 1, "tf32x3": 3}[self.precision]
         key = self._wkey(op) + "#tc"
         if key not in self.weights:
-            w = self._sd_cpu[op.weight].float().contiguous()
-            cout, kin = w.shape[0], w.shape[1]
-            nbytes = self.lib.hcf_conv_tc_weight_bytes(kin, cout)
+            w = prep.pad_weight_for_tc(self._sd_cpu[op.weight], [v.C for v, _ in op.segs])
+            cout, kin, ks = w.shape[0], w.shape[1], w.shape[2]
+            nbytes = self.lib.hcf_conv_tc_weight_bytes(kin, cout, ks)
             img = torch.zeros(nbytes // 4, dtype=torch.float32)
-            L.check(self.lib.hcf_conv_tc_pack_weights(w.data_ptr(), kin, cout, img.data_ptr()), "tc_pack")
+            L.check(self.lib.hcf_conv_tc_pack_weights(w.data_ptr(), kin, cout, ks, img.data_ptr()), "tc_pack")
             self.weights[key] = img.to(self.device)
         handle = C.c_void_p()
         L.check(self.lib.hcf_conv_tc_plan_create(C.byref(a), self.weights[key].data_ptr(), passes, C.byref(handle)),

@@ -90,7 +90,7 @@ class PriorOp:
 @dataclass
 class LayoutOp:
     kind = "layout"
-    variant: str            # "ingest" | "egress" | "squeeze" | "unsqueeze" | "haar_fwd" | "haar_inv"
+    variant: str            # "ingest" | "egress" | "squeeze" | "unsqueeze" | "haar_fwd" | "haar_inv" | "copy"
     H: int                  # low-res size for squeeze-like ops, tensor size for ingest/egress
     W: int
     C: int                  # channels on the high-res side (squeeze-like) or tensor channels
@@ -207,7 +207,7 @@ def _emit_subnet(plan, pre, aff, z, cond, H, W, lvl):
     segs = [(z1, 0)] + ([(cond, 0)] if cond is not None else [])
     f = aff.f
     fp = pre + ".affine.f"
-    hout = plan.view("h3_l{}_c{}".format(lvl, f.cout), H, W, f.cout)
+    hout = plan.view("h3_l{}_c{}".format(lvl, f.cout), H, W, (f.cout + 3) // 4 * 4).sub(0, f.cout)
     if f.kind == "FCN":
         h1 = plan.view("h1_l{}".format(lvl), H, W, f.hidden)
         h2 = plan.view("h2_l{}".format(lvl), H, W, f.hidden)
@@ -247,6 +247,15 @@ def _emit_step(plan, pre, step, z, cond, H, W, lvl, reverse):
         plan.logdet_terms.append((pre, has_perm, H * W))
 
 
+def _cond_view(plan, lvl, H, W, a):
+    """The conditional flow's variable `a` = z[:, n_split:].  TMA needs 16-byte aligned views, so
+    when the slice starts at a channel offset that is not a multiple of 4 the conditional steps
+    run on a private buffer (copied to / from the slice once per level)."""
+    if (a.off % 4 == 0) and (a.buf.C % 4 == 0):
+        return a
+    return plan.view("acond_l{}".format(lvl), H, W, (a.C + 3) // 4 * 4).sub(0, a.C)
+
+
 def build_plan(net, direction, B, h, w):
     """net: HCFlowNet_SR / HCFlowNet_Rescaling (arch.py); direction: "reverse" | "forward";
     (h, w): LR size.  Returns a Plan."""
@@ -283,8 +292,9 @@ def build_plan(net, direction, B, h, w):
             cfm = flow.cond_flow(l)
             pre = "flow.level{}_condFlow".format(l)
             feats[l] = _emit_encoder(plan, pre, cfm, enc_segs(l), H, W, l)
-            a = zb[l].sub(ns, Cl[l] - ns)
-            hp = plan.view("prior_l{}".format(l), H, W, 2 * cfm.z_channels)
+            a_dst = zb[l].sub(ns, Cl[l] - ns)
+            a = _cond_view(plan, l, H, W, a_dst)
+            hp = plan.view("prior_l{}".format(l), H, W, (2 * cfm.z_channels + 3) // 4 * 4).sub(0, 2 * cfm.z_channels)
             plan.ops.append(ConvOp(H, W, [(feats[l], 0)], 3, 2 * cfm.z_channels, pre + ".f.weight", pre + ".f.bias",
                                    pre + ".f.logs#exp3", ACT_NONE, hp, tag="prior.conv"))
             plan.ops.append(PriorOp("sample", H, W, hp, a, not sr, eps_index=draw))
@@ -293,6 +303,8 @@ def build_plan(net, direction, B, h, w):
             for j in range(len(cfm.additional_flow_steps) - 1, -1, -1):
                 _emit_step(plan, "{}.additional_flow_steps.{}".format(pre, j), cfm.additional_flow_steps[j],
                            a, feats[l], H, W, l, True)
+            if a is not a_dst:
+                plan.ops.append(LayoutOp("copy", H, W, a.C, a, a_dst))
             for i in reversed(info[l]["steps"]):
                 _emit_step(plan, "flow.layers.{}".format(i), flow.layers[i], zb[l], None, H, W, l, True)
             variant = "haar_inv" if info[l]["haar"] else "unsqueeze"
@@ -324,11 +336,14 @@ def build_plan(net, direction, B, h, w):
         cfm = flow.cond_flow(l)
         pre = "flow.level{}_condFlow".format(l)
         feats[l] = _emit_encoder(plan, pre, cfm, enc_segs(l), H, W, l)
-        a = zb[l].sub(ns, Cl[l] - ns)
+        a_src = zb[l].sub(ns, Cl[l] - ns)
+        a = _cond_view(plan, l, H, W, a_src)
+        if a is not a_src:
+            plan.ops.append(LayoutOp("copy", H, W, a.C, a_src, a))
         for j in range(len(cfm.additional_flow_steps)):
             _emit_step(plan, "{}.additional_flow_steps.{}".format(pre, j), cfm.additional_flow_steps[j],
                        a, feats[l], H, W, l, False)
-        hp = plan.view("prior_l{}".format(l), H, W, 2 * cfm.z_channels)
+        hp = plan.view("prior_l{}".format(l), H, W, (2 * cfm.z_channels + 3) // 4 * 4).sub(0, 2 * cfm.z_channels)
         plan.ops.append(ConvOp(H, W, [(feats[l], 0)], 3, 2 * cfm.z_channels, pre + ".f.weight", pre + ".f.bias",
                                pre + ".f.logs#exp3", ACT_NONE, hp, tag="prior.conv"))
         if sr:

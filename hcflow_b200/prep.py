@@ -87,3 +87,21 @@ def logdet_constant(sd, terms):
 def quant_logdet(quant, pixels):
     """HCFlowNet_SR_arch.py:53: -log(quant) * H*W  (H*W, not C*H*W)."""
     return float(-math.log(quant) * pixels)
+
+
+def tc_pad(c):
+    return (c + 31) // 32 * 32
+
+
+def pad_weight_for_tc(w, seg_channels):
+    """w [Cout, Cin, ks, ks] -> [Cout, sum(ceil32(C_seg)), ks, ks] with zero rows after each segment
+    (the tensor-core kernel walks K in 32-channel chunks per segment)."""
+    cout, cin, ks, _ = w.shape
+    assert sum(seg_channels) == cin, (seg_channels, cin)
+    out = torch.zeros(cout, sum(tc_pad(c) for c in seg_channels), ks, ks, dtype=torch.float32)
+    src = dst = 0
+    for c in seg_channels:
+        out[:, dst:dst + c] = w[:, src:src + c].detach().float()
+        src += c
+        dst += tc_pad(c)
+    return out.contiguous()

@@ -97,16 +97,19 @@ typedef struct {
 /* fp32 CUDA-core (FFMA) implementation: exact-fp32 parity mode and odd shapes. */
 int hcf_conv_fp32(const hcf_conv_args* a, void* stream);
 
-/* tcgen05 tensor-core implementation (3x3, every segment C % 32 == 0, up_shift == 0,
- * cout in {16,32,64}).  `wtc` is the UMMA-ready weight image produced by
- * hcf_conv_tc_pack_weights; passes = 1 (TF32) or 3 (3xTF32 split, ~fp32 accuracy).
- * A plan owns the TMA tensor maps for one (args) tuple. */
+/* tcgen05 tensor-core implementation: ks in {1,3}, up to three segments without upsampling
+ * (16-byte aligned views, ld % 4 == 0, any channel count: the K axis is walked in 32-channel
+ * chunks per segment and TMA zero-fills beyond a segment's last channel), cout <= 64.
+ * `wtc` is the UMMA-ready weight image produced by hcf_conv_tc_pack_weights from weights
+ * whose input-channel axis is already padded per segment to multiples of 32 (kin);
+ * passes = 1 (TF32) or 3 (3xTF32 split, ~fp32 accuracy).  A plan owns the TMA tensor maps
+ * for one (args) tuple. */
 typedef struct hcf_conv_tc_plan hcf_conv_tc_plan;
 int hcf_conv_tc_supported(const hcf_conv_args* a);
 /* bytes needed for the packed weight image of (kin channels, cout) */
-int64_t hcf_conv_tc_weight_bytes(int32_t kin, int32_t cout);
-/* host-side packing: w_oihw [cout][kin][3][3] fp32 -> image (host pointers) */
-int hcf_conv_tc_pack_weights(const float* w_oihw, int32_t kin, int32_t cout, float* image);
+int64_t hcf_conv_tc_weight_bytes(int32_t kin, int32_t cout, int32_t ks);
+/* host-side packing: w_oihw [cout][kin][ks][ks] fp32 -> image (host pointers) */
+int hcf_conv_tc_pack_weights(const float* w_oihw, int32_t kin, int32_t cout, int32_t ks, float* image);
 int hcf_conv_tc_plan_create(const hcf_conv_args* a, const float* wtc, int32_t passes,
                             hcf_conv_tc_plan** out);
 int hcf_conv_tc_run(const hcf_conv_tc_plan* p, void* stream);
@@ -192,6 +195,10 @@ int hcf_unsqueeze2d(const hcf_squeeze_args* a, void* stream); /* Basic.py:143-15
  * inverse the other way. */
 int hcf_haar_forward(const hcf_squeeze_args* a, void* stream);
 int hcf_haar_inverse(const hcf_squeeze_args* a, void* stream);
+
+/* dst[..., :C] = src[..., :C] for two NHWC views of size [B,H,W] (Basic.py:489-499 Split / cat when a view
+ * would break TMA alignment). */
+int hcf_copy_view(const hcf_squeeze_args* a, void* stream);
 
 /* logdet[b] += sum_{c,h,w} log N(x; mean, exp(logs)) with a constant logs, all NCHW
  * (HCFlowNet_SR_arch.py:63 with logs = -6). n = C*H*W elements per image. */

@@ -125,7 +125,9 @@ class Emulator:
         else:
             src, dst = self.view(op.src), self.view(op.dst)
             C = op.C
-            if op.variant == "squeeze":   # src hi-res C -> dst low-res 4C
+            if op.variant == "copy":
+                dst.copy_(src.clone())
+            elif op.variant == "squeeze":   # src hi-res C -> dst low-res 4C
                 B, H2, W2, _ = src.shape
                 x = src.reshape(B, H2 // 2, 2, W2 // 2, 2, C).permute(0, 1, 3, 5, 2, 4)  # b,y,x,c,i,j
                 dst.copy_(x.reshape(B, H2 // 2, W2 // 2, 4 * C))

@@ -63,8 +63,8 @@ def main():
             def run():
                 return lib.hcf_conv_fp32(C.byref(a), st)
         else:
-            img = torch.zeros(lib.hcf_conv_tc_weight_bytes(cin, cout) // 4, dtype=torch.float32)
-            L.check(lib.hcf_conv_tc_pack_weights(w.contiguous().data_ptr(), cin, cout, img.data_ptr()), "pack")
+            img = torch.zeros(lib.hcf_conv_tc_weight_bytes(cin, cout, 3) // 4, dtype=torch.float32)
+            L.check(lib.hcf_conv_tc_pack_weights(w.contiguous().data_ptr(), cin, cout, 3, img.data_ptr()), "pack")
             img = img.cuda()
             h = C.c_void_p()
             L.check(lib.hcf_conv_tc_plan_create(C.byref(a), img.data_ptr(), 1 if args.precision == "tf32" else 3,

@@ -250,18 +250,23 @@ def test_rejects_cpu_tensors_and_bad_scale():
 
 # ------------------------------------------------------------------------------ tcgen05 conv kernel
 TC_CASES = [
-    # name, B, H, W, Cin, ld, cout, bias, scale, act, res1, res2
-    ("tiny", 1, 16, 8, 32, 32, 16, False, False, 0, False, False),
-    ("rdb_conv1", 2, 40, 40, 64, 192, 32, True, False, 2, False, False),
-    ("rdb_conv3_partial_tiles", 1, 33, 21, 128, 192, 32, True, False, 2, False, False),
-    ("rdb_conv5_res", 1, 20, 20, 192, 192, 64, True, False, 0, True, True),
-    ("prior_42", 1, 16, 16, 128, 128, 42, True, True, 0, False, False),
-    ("fcn_conv3_22", 2, 13, 9, 64, 64, 22, True, True, 0, False, False),
-    ("cout_48", 1, 16, 8, 64, 64, 48, True, False, 0, False, False),
+    # name, B, H, W, [seg (C, up, ld, off)], cout, ks, bias, scale, act, res1, res2
+    ("tiny", 1, 16, 8, [(32, 0, 32, 0)], 16, 3, False, False, 0, False, False),
+    ("rdb_conv1", 2, 40, 40, [(64, 0, 192, 0)], 32, 3, True, False, 2, False, False),
+    ("rdb_conv3_partial_tiles", 1, 33, 21, [(128, 0, 192, 0)], 32, 3, True, False, 2, False, False),
+    ("rdb_conv5_res", 1, 20, 20, [(192, 0, 192, 0)], 64, 3, True, False, 0, True, True),
+    ("prior_42", 1, 16, 16, [(128, 0, 128, 0)], 42, 3, True, True, 0, False, False),
+    ("fcn_conv3_22", 2, 13, 9, [(64, 0, 64, 0)], 22, 3, True, True, 0, False, False),
+    ("cout_48", 1, 16, 8, [(64, 0, 64, 0)], 48, 3, True, False, 0, False, False),
+    ("fcn_conv1_cond_2seg", 2, 11, 17, [(10, 0, 24, 0), (128, 0, 128, 0)], 64, 3, True, True, 1, False, False),
+    ("fcn_conv1_uncond_c6", 1, 24, 16, [(6, 0, 12, 0)], 64, 3, True, True, 1, False, False),
+    ("fcn_conv2_1x1", 2, 11, 17, [(64, 0, 64, 0)], 64, 1, True, True, 1, False, False),
+    ("conv_first_lr_c3", 2, 13, 9, [(3, 0, 24, 0)], 64, 3, True, False, 0, False, False),
+    ("dense_3seg", 1, 10, 10, [(9, 0, 12, 0), (128, 0, 128, 0), (96, 0, 128, 0)], 32, 3, True, False, 2, False, False),
 ]
 # max-abs tolerance on outputs of magnitude ~4: one TF32 pass keeps 10 mantissa bits per operand
 # (measured 3e-3); the 3-pass split recovers them, what remains is the tensor core's truncating
-# fp32 accumulation over 36*Cin/32 MMAs per pass (measured 2e-5 .. 1.2e-4).
+# fp32 accumulation over the MMA chain (measured 1e-5 .. 7e-5).
 TC_TOL = {"tf32": 1e-2, "tf32x3": 4e-4}
 
 
@@ -269,16 +274,21 @@ TC_TOL = {"tf32": 1e-2, "tf32x3": 4e-4}
 @pytest.mark.parametrize("case", TC_CASES, ids=[c[0] for c in TC_CASES])
 def test_conv_tcgen05_matches_fp64(case, precision, report):
     from tests import gpu_ops
-    name, B, H, W, cin, ld, cout, hb, hs, act, r1, r2 = case
-    x = _rand(B, cin, H, W, seed=1)
-    w = _rand(cout, cin, 3, 3, seed=2, scale=1.0 / math.sqrt(cin * 9))
+    name, B, H, W, segs, cout, ks, hb, hs, act, r1, r2 = case
+    xs, segargs = [], []
+    for i, (c, up, ld, off) in enumerate(segs):
+        x = _rand(B, c, H, W, seed=10 + i)
+        xs.append(x)
+        segargs.append((x, up, ld, off))
+    cin = sum(s[0] for s in segs)
+    w = _rand(cout, cin, ks, ks, seed=2, scale=1.0 / math.sqrt(cin * ks * ks))
     bias = _rand(cout, seed=4, scale=0.1) if hb else None
     scale = torch.exp(_rand(cout, seed=5, scale=0.2)) if hs else None
     res1 = _rand(B, cout, H, W, seed=6) if r1 else None
     res2 = _rand(B, cout, H, W, seed=7) if r2 else None
-    got, got2 = gpu_ops.conv([(x, 0, ld, 0)], w, bias, scale, act, res1, 0.2, res2, 0.2, out_ld=cout + 8, out_off=4,
+    got, got2 = gpu_ops.conv(segargs, w, bias, scale, act, res1, 0.2, res2, 0.2, out_ld=cout + 8, out_off=4,
                              precision=precision, want_out2=True)
-    ref = F.conv2d(x.double(), w.double(), None, padding=1)
+    ref = F.conv2d(torch.cat(xs, 1).double(), w.double(), None, padding=ks // 2)
     if hb:
         ref = ref + bias.double().view(1, -1, 1, 1)
     if hs:
