@@ -166,12 +166,17 @@ def per_class_times(eng):
         if isinstance(op, P.ConvOp):
             cin = sum(v.C for v, _ in op.segs)
             fl = 2.0 * eng.B * op.H * op.W * op.ks * op.ks * cin * op.cout
-        pairs.append((what.split(":")[0], a, b, fl))
+        tag = "{}@{}x{}".format(getattr(op, "tag", "").split("flow.")[0] or what, getattr(op, "H", 0), getattr(op, "W", 0))
+        pairs.append((what.split(":")[0], a, b, fl, tag))
     torch.cuda.synchronize()
-    out = {}
-    for cls, a, b, fl in pairs:
+    out, by_tag = {}, {}
+    for cls, a, b, fl, tag in pairs:
         n, ms, f = out.get(cls, (0, 0.0, 0.0))
         out[cls] = (n + 1, ms + a.elapsed_time(b), f + fl)
+        if cls.startswith("conv"):
+            n, ms, f = by_tag.get(tag, (0, 0.0, 0.0))
+            by_tag[tag] = (n + 1, ms + a.elapsed_time(b), f + fl)
+    per_class_times.by_tag = by_tag
     return out
 
 
@@ -278,6 +283,8 @@ def run_ours(args):
                        "tensor pipe at all)".format(peaks["source"]),
         "launches": n, "avg_launch_ms": ms / n, "share_of_step": ms / total_ms,
         "classes": {c: {"n": v[0], "ms": round(v[1], 4), "gflop": round(v[2] / 1e9, 3)} for c, v in classes.items()},
+        "conv_by_layer": {t: {"n": v[0], "ms": round(v[1], 3), "tflops": round(v[2] / max(v[1], 1e-9) / 1e9, 1)}
+                          for t, v in sorted(per_class_times.by_tag.items(), key=lambda kv: -kv[1][1])},
     }
     # ---- CPU baseline (rank 0, N=1 only): the oracle on the host cores, bounded sample
     cpu = None
@@ -286,6 +293,35 @@ def run_ours(args):
         cpu = {"value": mp * len(times) / sum(times), "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "{} passes of configs[0] (B=1, 40x40 LR -> 160x160 HR, T=0.8), oracle on torch CPU fp32".format(
                    len(times))}
+    # ---- the other precision modes, device-resident, short (same inputs, same graph-replay method)
+    modes = {args.precision: {"value": value, "ms_per_step": t_ms / args.steps}}
+    if world == 1 and not args.no_modes:
+        net.use_graph = True
+        for prec in ("tf32x3", "tf32", "fp32"):
+            if prec in modes:
+                continue
+            net.set_precision(prec)
+            e3 = net.engine("reverse", B, LR_HW, LR_HW, dev)
+            e3.ext["lr"].copy_(lr)
+            for i, e in enumerate(unit):
+                e3.ext["eps{}".format(i)].copy_(HEAT * e)
+            for _ in range(3):
+                e3.run()
+            torch.cuda.synchronize()
+            n3 = 5
+            s3 = [torch.cuda.Event(enable_timing=True) for _ in range(n3)]
+            f3 = [torch.cuda.Event(enable_timing=True) for _ in range(n3)]
+            for k in range(n3):
+                flush.fill_(float(k))
+                s3[k].record()
+                e3.run()
+                f3[k].record()
+            torch.cuda.synchronize()
+            ms3 = sum(a.elapsed_time(b) for a, b in zip(s3, f3)) / n3
+            modes[prec] = {"value": B * HR * HR / 1e6 / (ms3 / 1e3), "ms_per_step": ms3}
+            net._engines.clear()
+            torch.cuda.empty_cache()
+        net.set_precision(args.precision)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -301,6 +337,9 @@ def run_ours(args):
         "clocks": sampler.summary(),
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "modes": modes,
+        "parity": "tests/test_gpu_parity.py: un-clamped HR vs reference goldens max-abs fp32 5e-6, tf32x3 1.9e-4, "
+                  "tf32 1.3e-2 (tolerances 2e-4 / 2e-3 / 5e-2)",
     }
     print(json.dumps(line), flush=True)
 
@@ -311,8 +350,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("HCFLOW_PRECISION", "fp32"),
-                    choices=["fp32", "tf32", "tf32x3"])
+    ap.add_argument("--precision", default=os.environ.get("HCFLOW_PRECISION", "tf32x3"),
+                    choices=["fp32", "tf32", "tf32x3"],
+                    help="tf32x3 (default): tcgen05 3xTF32 split, fp32-level parity (2e-4); tf32: one TF32 pass "
+                         "(stock PyTorch conv numerics on CUDA); fp32: CUDA-core kernels")
+    ap.add_argument("--no-modes", action="store_true", help="skip the short runs of the other precision modes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches (for ncu)")
     ap.add_argument("--skip-e2e", action="store_true")

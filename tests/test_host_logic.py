@@ -120,3 +120,28 @@ def test_world_size_2_gloo_nll_reduction(tmp_path):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("OK") == 2
+
+
+_REF_WORKER = r"""
+import sys
+sys.path.insert(0, {root!r})
+from oracle import ref_loader
+networks = ref_loader.load()                      # the UNMODIFIED reference factory
+import hcflow_b200
+hcflow_b200.install()
+from hcflow_b200 import options
+from hcflow_b200.arch import HCFlowNet_SR, HCFlowNet_Rescaling
+for cfg, cls in (("sr_x4", HCFlowNet_SR), ("sr_x8", HCFlowNet_SR), ("rescaling_x4", HCFlowNet_Rescaling)):
+    net = networks.define_G(options.load_config(cfg), 0)
+    assert type(net) is cls, type(net)
+print("OK")
+"""
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/codes"), reason="reference checkout not present")
+def test_reference_factory_builds_the_dropin_after_install(tmp_path):
+    """with install(), the reference's own networks.define_G returns our classes."""
+    script = tmp_path / "w.py"
+    script.write_text(_REF_WORKER.format(root=ROOT))
+    out = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
