@@ -21,8 +21,10 @@
 //               item i overlaps the loads and MMAs of item i+1.
 //   warps 6..9  (PASSES == 3 only) 3xTF32 split: the tensor core reads an fp32 word as TF32 by
 //               ignoring the low 13 mantissa bits, so the "hi" parts are free; these warps form
-//               A_lo = a - trunc(a) next to every A stage, B_lo is precomputed on the host, and
-//               each K-step issues A*B, A*B_lo, A_lo*B into the same accumulator.
+//               A_lo = a - trunc(a) next to every A stage and B_lo = w - trunc(w) is precomputed on
+//               the host.  The three products take TWO MMAs per K-step: A x [B ; B_lo] as one
+//               2N-row operand (columns [0,N) and [N,2N) of the accumulator) and A_lo x B into
+//               columns [0,N); the epilogue adds the two column groups.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -54,7 +56,7 @@ struct Params {
   int dys;       // dy rows of taps per B slab: 3 (whole chunk) or 1
   int debug;     // timing experiments only (HCF_TC_DEBUG, wrong results): 1 = aligned A descriptors, 2 = no MMAs, 4 = no loads, 8 = no epilogue stores
   int tiles_x, tiles_y, n_items;
-  const float* wimg;   // [kchunks][2 (raw, lo)][ks dy][ks dx][N][32] pre-swizzled
+  const float* wimg;   // [kchunks][ks dy][ks dx][NB][32] pre-swizzled; NB = N (1 pass) or 2N rows: raw then lo (3 passes)
   const float* bias;
   const float* scale;
   int act;
@@ -159,9 +161,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
   if (p.debug & 16) return;   // timing experiment: launch cost only
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t tap_bytes = (uint32_t)p.N * ROW_BYTES;          // one tap of B: [N][32 ch]
-  const uint32_t b_half = (uint32_t)KS * p.dys * tap_bytes;      // raw (or lo) taps of one slab
-  const uint32_t b_slab = b_half * (PASSES == 3 ? 2u : 1u);      // [raw taps | lo taps]
+  const uint32_t NB = (uint32_t)p.N * (PASSES == 3 ? 2u : 1u);    // B rows per tap: [raw N | lo N]
+  const uint32_t tap_bytes = NB * ROW_BYTES;                     // one tap of B: [NB][32 ch]
+  const uint32_t b_slab = (uint32_t)KS * p.dys * tap_bytes;      // taps of one slab
   const int slabs = KS / p.dys;                                  // slabs per 32-channel chunk
   const uint32_t b_base = smem_base + p.sa * A_STAGE;
   const uint32_t bar_base = b_base + p.sb * b_slab;
@@ -176,7 +178,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
   const uint32_t tmem_slot = tbar + 32u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t need_cols = 2u * MT * p.N;
+  const uint32_t need_cols = 2u * MT * NB;
   const uint32_t tmem_cols = need_cols <= 32 ? 32u : (need_cols <= 64 ? 64u : (need_cols <= 128 ? 128u : 256u));
 
   if (warp == 0 && lane == 0) {
@@ -240,10 +242,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
               continue;
             }
             mbar_expect_tx(fullB(sB), b_slab);
-            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wimg) + (size_t)kc * (2u * KS * KS * tap_bytes) +
-                                 (size_t)sl * b_half;
-            bulk_load(b_base + sB * b_slab, src, b_half, fullB(sB));
-            if (PASSES == 3) bulk_load(b_base + sB * b_slab + b_half, src + (uint32_t)(KS * KS) * tap_bytes, b_half, fullB(sB));
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wimg) + (size_t)kc * ((uint32_t)(KS * KS) * tap_bytes) +
+                                 (size_t)sl * b_slab;
+            bulk_load(b_base + sB * b_slab, src, b_slab, fullB(sB));
             ++b_it;
           }
         }
@@ -253,7 +254,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
     // ===================== MMA issuer =====================
     // The whole warp follows the barriers; one elected lane issues (warp-uniform control flow
     // lets ptxas keep descriptors in uniform registers without a per-instruction election loop).
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc_n = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((NB >> 3) << 17) | ((128u >> 4) << 24);
     // Descriptor templates: everything but the 14-bit start-address field (addr >> 4).  A shared
     // memory address is < 2^18, so adding (bytes >> 4) never carries out of the field; the
     // per-MMA work is one add per operand (every dependent ALU op of the single issuing thread
@@ -266,7 +268,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
       const uint32_t acc = t_it & 1u;
       mbar_wait(tmem_empty(acc), ((t_it >> 1) & 1u) ^ 1u);
       tc_fence_after();
-      const uint32_t d0 = tmem_base + acc * MT * p.N;
+      const uint32_t d0 = tmem_base + acc * MT * NB;
       uint32_t accum = 0u;   // first MMA of the item overwrites the accumulator
       for (int kc = 0; kc < p.kchunks; ++kc) {
         const int sA = a_it % p.sa;
@@ -291,14 +293,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
                   const uint64_t bd = b_dy + (dx * nb + 2u * k);
 #pragma unroll
                   for (int mt = 0; mt < MT; ++mt) {
-                    const uint32_t d = d0 + mt * p.N;
+                    const uint32_t d = d0 + mt * NB;
                     const uint64_t ad = a_dy + ((p.debug & 1) ? (uint32_t)(k * 2)
                                                               : (uint32_t)(((mt * TH * HALO_W + dx) * ROW_BYTES + k * 32) >> 4));
-                    umma_tf32(d, ad, bd, idesc, accum);
-                    if (PASSES == 3) {
-                      umma_tf32(d, ad, bd + (b_half >> 4), idesc, 1u);
-                      umma_tf32(d, ad + (A_PART >> 4), bd, idesc, 1u);
-                    }
+                    umma_tf32(d, ad, bd, idesc, accum);                            // A x [B ; B_lo]
+                    if (PASSES == 3) umma_tf32(d, ad + (A_PART >> 4), bd, idesc_n, 1u);  // A_lo x B
                   }
                   accum = 1u;
                 }
@@ -336,7 +335,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
 #pragma unroll 1
         for (int c0 = 0; c0 < p.N; c0 += 16) {
           float v[16];
-          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (acc * MT + mt) * p.N + (uint32_t)c0, v);
+          const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (acc * MT + mt) * NB + (uint32_t)c0;
+          tmem_ld16(tcol, v);
+          if (PASSES == 3) {
+            float lo[16];
+            tmem_ld16(tcol + (uint32_t)p.N, lo);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += lo[j];
+          }
           if (!inb || c0 >= p.cout || (p.debug & 8)) continue;
           if (p.bias) {   // bias / scale are padded to >= N entries and 16-byte aligned
 #pragma unroll
@@ -459,10 +465,11 @@ static int num_sms() {
 // ring depths and B slab granularity that fit in shared memory; false if nothing fits
 static bool pick_rings(int mt, int passes, int ks, int N, int* sa, int* sb, int* dys, size_t* smem) {
   const int a_stage = a_part(mt, ks) * (passes == 3 ? 2 : 1);
+  const int NB = N * (passes == 3 ? 2 : 1);
   const int budget = SMEM_LIMIT - 1024 - 512;
   // 1) whole-chunk B stages (one barrier round trip per chunk) if >= 2 of them fit beside >= 2 A stages
   {
-    const int b_slab = ks * ks * N * ROW_BYTES * (passes == 3 ? 2 : 1);
+    const int b_slab = ks * ks * NB * ROW_BYTES;
     for (int b = 3; b >= 2; --b)
       for (int a = 4; a >= 2; --a)
         if (a * a_stage + b * b_slab <= budget && (a >= 3 || b == 2)) {
@@ -473,7 +480,7 @@ static bool pick_rings(int mt, int passes, int ks, int N, int* sa, int* sb, int*
   }
   if (ks == 1) return false;
   // 2) per-dy slabs
-  const int b_slab = 3 * N * ROW_BYTES * (passes == 3 ? 2 : 1);
+  const int b_slab = 3 * NB * ROW_BYTES;
   int best_a = 0;
   for (int a = 4; a >= 1 && !best_a; --a)
     if (a * a_stage + 3 * b_slab <= budget) best_a = a;
@@ -525,21 +532,23 @@ extern "C" int hcf_conv_tc_supported(const hcf_conv_args* a) {
 }
 
 // kin = number of (segment-padded) input channels, a multiple of 32
-extern "C" int64_t hcf_conv_tc_weight_bytes(int32_t kin, int32_t cout, int32_t ks) {
-  if (kin % 32 != 0 || cout < 1 || cout > 64 || (ks != 1 && ks != 3)) return 0;
-  return (int64_t)(kin / 32) * 2 * ks * ks * hcf::tc::n_for(cout) * 128;
+extern "C" int64_t hcf_conv_tc_weight_bytes(int32_t kin, int32_t cout, int32_t ks, int32_t passes) {
+  if (kin % 32 != 0 || cout < 1 || cout > 64 || (ks != 1 && ks != 3) || (passes != 1 && passes != 3)) return 0;
+  return (int64_t)(kin / 32) * ks * ks * hcf::tc::n_for(cout) * (passes == 3 ? 2 : 1) * 128;
 }
 
 // w: [cout][kin][ks][ks] fp32 (host), kin already padded per segment to multiples of 32
-extern "C" int hcf_conv_tc_pack_weights(const float* w, int32_t kin, int32_t cout, int32_t ks, float* image) {
+extern "C" int hcf_conv_tc_pack_weights(const float* w, int32_t kin, int32_t cout, int32_t ks, int32_t passes,
+                                        float* image) {
   using namespace hcf;
-  HCF_REQUIRE(w && image && kin % 32 == 0 && cout >= 1 && cout <= 64 && (ks == 1 || ks == 3), "tc_pack: bad args");
-  const int N = tc::n_for(cout), KC = kin / 32;
-  memset(image, 0, (size_t)hcf_conv_tc_weight_bytes(kin, cout, ks));
+  HCF_REQUIRE(w && image && kin % 32 == 0 && cout >= 1 && cout <= 64 && (ks == 1 || ks == 3) &&
+                  (passes == 1 || passes == 3), "tc_pack: bad args");
+  const int N = tc::n_for(cout), KC = kin / 32, parts = passes == 3 ? 2 : 1, NB = N * parts;
+  memset(image, 0, (size_t)hcf_conv_tc_weight_bytes(kin, cout, ks, passes));
   for (int kc = 0; kc < KC; ++kc)
-    for (int part = 0; part < 2; ++part)
-      for (int dy = 0; dy < ks; ++dy)
-        for (int dx = 0; dx < ks; ++dx)
+    for (int dy = 0; dy < ks; ++dy)
+      for (int dx = 0; dx < ks; ++dx)
+        for (int part = 0; part < parts; ++part)
           for (int n = 0; n < cout; ++n)
             for (int j = 0; j < 32; ++j) {
               const float v = w[(((size_t)n * kin + kc * 32 + j) * ks + dy) * ks + dx];
@@ -549,8 +558,9 @@ extern "C" int hcf_conv_tc_pack_weights(const float* w, int32_t kin, int32_t cou
               float hi;
               memcpy(&hi, &bits, 4);
               const float val = part == 0 ? v : v - hi;
-              const int chunk = (j / 4) ^ (n & 7);   // 128B swizzle: 16-byte chunk index XOR row-in-atom
-              image[(((((size_t)kc * 2 + part) * ks + dy) * ks + dx) * N + n) * 32 + chunk * 4 + (j & 3)] = val;
+              const int row = part * N + n;
+              const int chunk = (j / 4) ^ (row & 7);   // 128B swizzle: 16-byte chunk index XOR row-in-atom
+              image[((((size_t)kc * ks + dy) * ks + dx) * NB + row) * 32 + chunk * 4 + (j & 3)] = val;
             }
   return 0;
 }

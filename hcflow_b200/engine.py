@@ -222,13 +222,13 @@ class Engine:
         if not self.lib.hcf_conv_tc_supported(C.byref(a)):
             return None
         passes = {"tf32": 1, "tf32x3": 3}[self.precision]
-        key = self._wkey(op) + "#tc"
+        key = self._wkey(op) + "#tc{}".format(passes)
         if key not in self.weights:
             w = prep.pad_weight_for_tc(self._sd_cpu[op.weight], [v.C for v, _ in op.segs])
             cout, kin, ks = w.shape[0], w.shape[1], w.shape[2]
-            nbytes = self.lib.hcf_conv_tc_weight_bytes(kin, cout, ks)
+            nbytes = self.lib.hcf_conv_tc_weight_bytes(kin, cout, ks, passes)
             img = torch.zeros(nbytes // 4, dtype=torch.float32)
-            L.check(self.lib.hcf_conv_tc_pack_weights(w.data_ptr(), kin, cout, ks, img.data_ptr()), "tc_pack")
+            L.check(self.lib.hcf_conv_tc_pack_weights(w.data_ptr(), kin, cout, ks, passes, img.data_ptr()), "tc_pack")
             self.weights[key] = img.to(self.device)
         handle = C.c_void_p()
         L.check(self.lib.hcf_conv_tc_plan_create(C.byref(a), self.weights[key].data_ptr(), passes, C.byref(handle)),

@@ -106,10 +106,10 @@ int hcf_conv_fp32(const hcf_conv_args* a, void* stream);
  * for one (args) tuple. */
 typedef struct hcf_conv_tc_plan hcf_conv_tc_plan;
 int hcf_conv_tc_supported(const hcf_conv_args* a);
-/* bytes needed for the packed weight image of (kin channels, cout) */
-int64_t hcf_conv_tc_weight_bytes(int32_t kin, int32_t cout, int32_t ks);
+/* bytes needed for the packed weight image of (kin channels, cout); the image depends on `passes` */
+int64_t hcf_conv_tc_weight_bytes(int32_t kin, int32_t cout, int32_t ks, int32_t passes);
 /* host-side packing: w_oihw [cout][kin][ks][ks] fp32 -> image (host pointers) */
-int hcf_conv_tc_pack_weights(const float* w_oihw, int32_t kin, int32_t cout, int32_t ks, float* image);
+int hcf_conv_tc_pack_weights(const float* w_oihw, int32_t kin, int32_t cout, int32_t ks, int32_t passes, float* image);
 int hcf_conv_tc_plan_create(const hcf_conv_args* a, const float* wtc, int32_t passes,
                             hcf_conv_tc_plan** out);
 int hcf_conv_tc_run(const hcf_conv_tc_plan* p, void* stream);

@@ -79,9 +79,10 @@ def conv(segs, w, bias=None, scale=None, act=0, res1=None, alpha1=1.0, res2=None
         assert lib.hcf_conv_tc_supported(C.byref(a)), "tc kernel does not support this shape"
         wt = prep.pad_weight_for_tc(w, segc)
         kin = wt.shape[1]
-        nbytes = lib.hcf_conv_tc_weight_bytes(kin, cout, ks)
+        npass = {"tf32": 1, "tf32x3": 3}[precision]
+        nbytes = lib.hcf_conv_tc_weight_bytes(kin, cout, ks, npass)
         img = torch.zeros(nbytes // 4, dtype=torch.float32)
-        L.check(lib.hcf_conv_tc_pack_weights(wt.data_ptr(), kin, cout, ks, img.data_ptr()), "tc_pack")
+        L.check(lib.hcf_conv_tc_pack_weights(wt.data_ptr(), kin, cout, ks, npass, img.data_ptr()), "tc_pack")
         img = img.cuda()
         h = C.c_void_p()
         L.check(lib.hcf_conv_tc_plan_create(C.byref(a), img.data_ptr(), {"tf32": 1, "tf32x3": 3}[precision],

@@ -63,11 +63,12 @@ def main():
             def run():
                 return lib.hcf_conv_fp32(C.byref(a), st)
         else:
-            img = torch.zeros(lib.hcf_conv_tc_weight_bytes(cin, cout, 3) // 4, dtype=torch.float32)
-            L.check(lib.hcf_conv_tc_pack_weights(w.contiguous().data_ptr(), cin, cout, 3, img.data_ptr()), "pack")
+            npass = 1 if args.precision == "tf32" else 3
+            img = torch.zeros(lib.hcf_conv_tc_weight_bytes(cin, cout, 3, npass) // 4, dtype=torch.float32)
+            L.check(lib.hcf_conv_tc_pack_weights(w.contiguous().data_ptr(), cin, cout, 3, npass, img.data_ptr()), "pack")
             img = img.cuda()
             h = C.c_void_p()
-            L.check(lib.hcf_conv_tc_plan_create(C.byref(a), img.data_ptr(), 1 if args.precision == "tf32" else 3,
+            L.check(lib.hcf_conv_tc_plan_create(C.byref(a), img.data_ptr(), npass,
                                                 C.byref(h)), "plan")
 
             def run():
