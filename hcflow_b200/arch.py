@@ -33,6 +33,7 @@ class _HCFlowBase(nn.Module):
         self.flow = M.FlowNet((hr_size, hr_size, hr_channel), opt, SR=self.SR)
         self.precision = "fp32"
         self.use_graph = True
+        self.use_chains = True   # fuse runs of tensor-core convs into one persistent chained launch
         self._engines = {}
         self.last = {}
 
@@ -46,10 +47,11 @@ class _HCFlowBase(nn.Module):
 
     def engine(self, direction, B, h, w, device):
         from .engine import Engine
-        key = (direction, B, h, w, str(device), self.precision, self.use_graph)
+        key = (direction, B, h, w, str(device), self.precision, self.use_graph, self.use_chains)
         eng = self._engines.get(key)
         if eng is None:
-            eng = Engine(self, direction, B, h, w, device, precision=self.precision, use_graph=self.use_graph)
+            eng = Engine(self, direction, B, h, w, device, precision=self.precision, use_graph=self.use_graph,
+                         use_chains=self.use_chains)
             self._engines[key] = eng
         return eng
 

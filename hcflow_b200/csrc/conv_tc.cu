@@ -5,7 +5,12 @@
 //
 // Work item = MT vertically adjacent 16x8 pixel tiles of one image (UMMA M = 128 each) x all
 // N = ceil16(Cout) <= 64 output channels.  CTAs are persistent (grid = #SMs, items strided by
-// gridDim.x) and warp-specialised:
+// gridDim.x) and warp-specialised.  A launch executes either one convolution or a CHAIN of
+// dependent convolutions on the same pixel grid (e.g. the 211 convs of an RRDB encoder level):
+// item = (layer, tile) in layer-major order; a tile of layer l may start once the 3x3 tile
+// neighbourhood of layer l-1 is complete, tracked by per-tile counters in global memory
+// (release by the epilogue, acquire by the producer), so there is no kernel boundary, no
+// ramp-up / drain and no wave quantisation between the convs.  Roles:
 //   warp 0      TMA producer.  Per 32-channel chunk ONE 4-D TMA tile load brings the
 //               (16*MT+2) x 10 halo tile [rows][10][32 ch] (128-byte swizzle; out-of-bounds -> 0
 //               is exactly the conv's zero padding) into the A ring; the pre-swizzled weights
@@ -29,6 +34,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace hcf {
@@ -46,25 +53,41 @@ __host__ __device__ constexpr int halo_rows(int mt, int ks) { return TH * mt + (
 __host__ __device__ constexpr int a_bytes(int mt, int ks) { return halo_rows(mt, ks) * halo_w(ks) * ROW_BYTES; }
 __host__ __device__ constexpr int a_part(int mt, int ks) { return (a_bytes(mt, ks) + 1023) / 1024 * 1024; }
 
-struct Params {
-  int B, H, W;
-  int kchunks;   // total 32-channel chunks over all segments
-  int kc_end0, kc_end1;   // chunks [0,kc_end0) come from tensor map 0, [kc_end0,kc_end1) from map 1, rest from map 2
-  int N;         // UMMA N (multiple of 16, <= 64)
+constexpr int MAX_MAPS = 8;
+
+// One convolution of a chain.  Lives in global memory; every warp role reads the fields it needs
+// at the start of a work item.
+struct LayerDesc {
+  int nseg;
+  int map_idx[3];     // tensor map of each segment
+  int seg_end[3];     // chunk index where segment i ends (prefix sums)
+  int kchunks;        // total 32-channel chunks
+  int N;              // UMMA N (multiple of 16, <= 64)
   int cout;
-  int sa, sb;    // ring depths
-  int dys;       // dy rows of taps per B slab: 3 (whole chunk) or 1
-  int debug;     // timing experiments only (HCF_TC_DEBUG, wrong results): 1 = aligned A descriptors, 2 = no MMAs, 4 = no loads, 8 = no epilogue stores
-  int tiles_x, tiles_y, n_items;
-  const float* wimg;   // [kchunks][ks dy][ks dx][NB][32] pre-swizzled; NB = N (1 pass) or 2N rows: raw then lo (3 passes)
+  int act;
+  int out_vec;
+  const float* wimg;  // [kchunks][ks dy][ks dx][NB][32] pre-swizzled; NB = N (1 pass) or 2N rows: raw then lo
   const float* bias;
   const float* scale;
-  int act;
   float* out; int out_ld;
   float* out2; int out2_ld;
   const float* res1; int res1_ld; float alpha1;
   const float* res2; int res2_ld; float alpha2;
-  int out_vec;
+};
+
+struct Params {
+  int B, H, W;
+  int tiles_x, tiles_y;
+  int n_tiles;        // B * tiles_x * tiles_y  (work items per layer)
+  int n_layers;       // > 1: a chain of dependent convs executed by ONE persistent launch
+  int n_items;        // n_layers * n_tiles
+  int nb_max;         // max over layers of B rows per tap (N, or 2N in 3-pass mode)
+  int sa, sb;         // ring depths
+  int dys;            // dy rows of taps per B slab: KS (whole chunk) or 1
+  int debug;          // timing experiments only (HCF_TC_DEBUG, wrong results): 1 aligned A descriptors,
+                      // 2 no MMAs, 4 no loads, 8 no epilogue stores, 16 launch only, 32 prologue only
+  const LayerDesc* layers;
+  int* done;          // chain mode: per-tile count of completed layers (zeroed before the launch)
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -148,25 +171,38 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 }
 
 // ------------------------------------------------------------------ kernel
+template <typename T>
+__device__ __forceinline__ T* ldg_ptr(T* const* p) {
+  return reinterpret_cast<T*>(__ldg(reinterpret_cast<const unsigned long long*>(p)));
+}
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 template <int MT, int PASSES, int KS>
 __global__ void __launch_bounds__(PASSES == 3 ? 320 : 192, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant__ CUtensorMap amap1,
-               const __grid_constant__ CUtensorMap amap2, const Params p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap maps0, const __grid_constant__ CUtensorMap maps1,
+               const __grid_constant__ CUtensorMap maps2, const __grid_constant__ CUtensorMap maps3,
+               const __grid_constant__ CUtensorMap maps4, const __grid_constant__ CUtensorMap maps5,
+               const __grid_constant__ CUtensorMap maps6, const __grid_constant__ CUtensorMap maps7,
+               const Params p) {
   constexpr int HALO = KS / 2;
   constexpr int HALO_W = halo_w(KS);
   constexpr int A_BYTES = a_bytes(MT, KS);
   constexpr int A_PART = a_part(MT, KS);
   constexpr int A_STAGE = A_PART * (PASSES == 3 ? 2 : 1);   // [raw | lo]
+  constexpr uint32_t PARTS = PASSES == 3 ? 2u : 1u;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   if (p.debug & 16) return;   // timing experiment: launch cost only
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t NB = (uint32_t)p.N * (PASSES == 3 ? 2u : 1u);    // B rows per tap: [raw N | lo N]
-  const uint32_t tap_bytes = NB * ROW_BYTES;                     // one tap of B: [NB][32 ch]
-  const uint32_t b_slab = (uint32_t)KS * p.dys * tap_bytes;      // taps of one slab
-  const int slabs = KS / p.dys;                                  // slabs per 32-channel chunk
+  const uint32_t slot_bytes = (uint32_t)KS * p.dys * p.nb_max * ROW_BYTES;   // B ring slot (largest layer)
+  const int slabs = KS / p.dys;                                              // slabs per 32-channel chunk
   const uint32_t b_base = smem_base + p.sa * A_STAGE;
-  const uint32_t bar_base = b_base + p.sb * b_slab;
+  const uint32_t bar_base = b_base + p.sb * slot_bytes;
   auto fullA = [&](int s) { return bar_base + 8u * s; };
   auto emptyA = [&](int s) { return bar_base + 8u * (p.sa + s); };
   auto convA = [&](int s) { return bar_base + 8u * (2 * p.sa + s); };
@@ -176,15 +212,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
   auto tmem_full = [&](int a) { return tbar + 8u * a; };
   auto tmem_empty = [&](int a) { return tbar + 16u + 8u * a; };
   const uint32_t tmem_slot = tbar + 32u;
+  auto map_ptr = [&](int i) -> const CUtensorMap* {
+    switch (i) {
+      case 0: return &maps0; case 1: return &maps1; case 2: return &maps2; case 3: return &maps3;
+      case 4: return &maps4; case 5: return &maps5; case 6: return &maps6; default: return &maps7;
+    }
+  };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t need_cols = 2u * MT * NB;
+  const uint32_t need_cols = 2u * MT * p.nb_max;
   const uint32_t tmem_cols = need_cols <= 32 ? 32u : (need_cols <= 64 ? 64u : (need_cols <= 128 ? 128u : 256u));
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&amap0) : "memory");
-    if (p.kc_end0 < p.kchunks) asm volatile("prefetch.tensormap [%0];" ::"l"(&amap1) : "memory");
-    if (p.kc_end1 < p.kchunks) asm volatile("prefetch.tensormap [%0];" ::"l"(&amap2) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps0) : "memory");
     for (int s = 0; s < p.sa; ++s) {
       mbar_init(fullA(s), 1);
       mbar_init(emptyA(s), 1);
@@ -213,24 +253,52 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
 
   const int per_img = p.tiles_x * p.tiles_y;
   const int n_items = (p.debug & 32) ? 0 : p.n_items;   // timing experiment: prologue + teardown only
+  const bool chain = p.done != nullptr;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t a_it = 0, b_it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int b = item / per_img, r = item % per_img;
-        const int y0 = (r / p.tiles_x) * TH * MT, x0 = (r % p.tiles_x) * TW;
-        for (int kc = 0; kc < p.kchunks; ++kc) {
+        const int layer = item / p.n_tiles, tile = item - layer * p.n_tiles;
+        const LayerDesc* L = p.layers + layer;
+        const int b = tile / per_img, r = tile % per_img;
+        const int ty = r / p.tiles_x, tx = r % p.tiles_x;
+        const int y0 = ty * TH * MT, x0 = tx * TW;
+        const int kchunks = __ldg(&L->kchunks);
+        const int se0 = __ldg(&L->seg_end[0]), se1 = __ldg(&L->seg_end[1]);
+        const int m0 = __ldg(&L->map_idx[0]), m1 = __ldg(&L->map_idx[1]), m2 = __ldg(&L->map_idx[2]);
+        const uint32_t tap_bytes = (uint32_t)__ldg(&L->N) * PARTS * ROW_BYTES;
+        const uint32_t b_slab = (uint32_t)KS * p.dys * tap_bytes;
+        const uint8_t* wimg = reinterpret_cast<const uint8_t*>(ldg_ptr(&L->wimg));
+        if (chain && layer > 0) {
+          // wait until layer-1 is complete on the 3x3 tile neighbourhood (halo + WAR safety)
+          const int base = b * per_img;
+          for (;;) {
+            int ok = 1;
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+              for (int dx = -1; dx <= 1; ++dx) {
+                const int yy = ty + dy, xx = tx + dx;
+                if (yy >= 0 && yy < p.tiles_y && xx >= 0 && xx < p.tiles_x)
+                  ok &= (ld_acquire(p.done + base + yy * p.tiles_x + xx) >= layer) ? 1 : 0;
+              }
+            if (ok) break;
+            __nanosleep(64);
+          }
+          asm volatile("fence.proxy.async;" ::: "memory");   // order the TMA reads after the acquire
+        }
+        for (int kc = 0; kc < kchunks; ++kc) {
           const int sA = a_it % p.sa;
           mbar_wait(emptyA(sA), ((a_it / p.sa) & 1u) ^ 1u);
           if (p.debug & 4) {
             mbar_arrive(fullA(sA));
           } else {
             mbar_expect_tx(fullA(sA), A_BYTES);
-            const CUtensorMap* mp = kc < p.kc_end0 ? &amap0 : (kc < p.kc_end1 ? &amap1 : &amap2);
-            const int kl = kc < p.kc_end0 ? kc : (kc < p.kc_end1 ? kc - p.kc_end0 : kc - p.kc_end1);
-            tma_load_4d(smem_base + sA * A_STAGE, mp, fullA(sA), kl * KCH, x0 - HALO, y0 - HALO, b);
+            const int mi = kc < se0 ? m0 : (kc < se1 ? m1 : m2);
+            const int kl = kc < se0 ? kc : (kc < se1 ? kc - se0 : kc - se1);
+            tma_load_4d(smem_base + sA * A_STAGE, map_ptr(mi), fullA(sA), kl * KCH, x0 - HALO, y0 - HALO, b);
           }
           ++a_it;
           for (int sl = 0; sl < slabs; ++sl) {
@@ -238,13 +306,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
             mbar_wait(emptyB(sB), ((b_it / p.sb) & 1u) ^ 1u);
             if (p.debug & 4) {
               mbar_arrive(fullB(sB));
-              ++b_it;
-              continue;
+            } else {
+              mbar_expect_tx(fullB(sB), b_slab);
+              bulk_load(b_base + sB * slot_bytes,
+                        wimg + (size_t)kc * ((uint32_t)(KS * KS) * tap_bytes) + (size_t)sl * b_slab, b_slab, fullB(sB));
             }
-            mbar_expect_tx(fullB(sB), b_slab);
-            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wimg) + (size_t)kc * ((uint32_t)(KS * KS) * tap_bytes) +
-                                 (size_t)sl * b_slab;
-            bulk_load(b_base + sB * b_slab, src, b_slab, fullB(sB));
             ++b_it;
           }
         }
@@ -254,23 +320,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
     // ===================== MMA issuer =====================
     // The whole warp follows the barriers; one elected lane issues (warp-uniform control flow
     // lets ptxas keep descriptors in uniform registers without a per-instruction election loop).
-    const uint32_t idesc_n = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((NB >> 3) << 17) | ((128u >> 4) << 24);
     // Descriptor templates: everything but the 14-bit start-address field (addr >> 4).  A shared
     // memory address is < 2^18, so adding (bytes >> 4) never carries out of the field; the
     // per-MMA work is one add per operand (every dependent ALU op of the single issuing thread
     // costs its full latency).
     const uint64_t a_tmpl = make_desc(0, HALO_W * ROW_BYTES);
     const uint64_t b_tmpl = make_desc(0, 8u * ROW_BYTES);
-    const uint32_t nb = tap_bytes >> 4;      // one tap of B in 16-byte units
     uint32_t a_it = 0, b_it = 0, t_it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++t_it) {
+      const int layer = item / p.n_tiles;
+      const LayerDesc* L = p.layers + layer;
+      const int kchunks = __ldg(&L->kchunks);
+      const uint32_t N = (uint32_t)__ldg(&L->N);
+      const uint32_t NB = N * PARTS;
+      const uint32_t nb = NB * (ROW_BYTES >> 4);      // one tap of B in 16-byte units
+      const uint32_t idesc_n = (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((NB >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t acc = t_it & 1u;
       mbar_wait(tmem_empty(acc), ((t_it >> 1) & 1u) ^ 1u);
       tc_fence_after();
-      const uint32_t d0 = tmem_base + acc * MT * NB;
+      const uint32_t d0 = tmem_base + acc * MT * p.nb_max;
       uint32_t accum = 0u;   // first MMA of the item overwrites the accumulator
-      for (int kc = 0; kc < p.kchunks; ++kc) {
+      for (int kc = 0; kc < kchunks; ++kc) {
         const int sA = a_it % p.sa;
         const uint32_t phA = (a_it / p.sa) & 1u;
         mbar_wait(fullA(sA), phA);
@@ -281,7 +352,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
           mbar_wait(fullB(sB), (b_it / p.sb) & 1u);
           tc_fence_after();
           if (elect_one()) {
-            const uint64_t b0 = b_tmpl + ((b_base + sB * b_slab) >> 4);
+            const uint64_t b0 = b_tmpl + ((b_base + sB * slot_bytes) >> 4);
             for (int dyl = 0; dyl < ((p.debug & 2) ? 0 : p.dys); ++dyl) {
               uint64_t a_dy = a0 + (uint32_t)((sl * p.dys + dyl) * HALO_W * (ROW_BYTES >> 4));
               if (p.debug & 1) a_dy = make_desc(0, 8u * ROW_BYTES) + ((smem_base + sA * A_STAGE) >> 4);
@@ -293,10 +364,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
                   const uint64_t bd = b_dy + (dx * nb + 2u * k);
 #pragma unroll
                   for (int mt = 0; mt < MT; ++mt) {
-                    const uint32_t d = d0 + mt * NB;
+                    const uint32_t d = d0 + mt * p.nb_max;
                     const uint64_t ad = a_dy + ((p.debug & 1) ? (uint32_t)(k * 2)
                                                               : (uint32_t)(((mt * TH * HALO_W + dx) * ROW_BYTES + k * 32) >> 4));
-                    umma_tf32(d, ad, bd, idesc, accum);                            // A x [B ; B_lo]
+                    umma_tf32(d, ad, bd, idesc, accum);                                  // A x [B ; B_lo]
                     if (PASSES == 3) umma_tf32(d, ad + (A_PART >> 4), bd, idesc_n, 1u);  // A_lo x B
                   }
                   accum = 1u;
@@ -306,7 +377,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
             umma_commit(emptyB(sB));
             if (sl == slabs - 1) {
               umma_commit(emptyA(sA));
-              if (kc == p.kchunks - 1) umma_commit(tmem_full(acc));
+              if (kc == kchunks - 1) umma_commit(tmem_full(acc));
             }
           }
           __syncwarp();
@@ -322,8 +393,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
     const int m = q * 32 + lane;                  // accumulator row = pixel within the sub-tile
     uint32_t t_it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++t_it) {
-      const int b = item / per_img, r = item % per_img;
+      const int layer = item / p.n_tiles, tile = item - layer * p.n_tiles;
+      const LayerDesc* L = p.layers + layer;
+      const int b = tile / per_img, r = tile % per_img;
       const int y0 = (r / p.tiles_x) * TH * MT, x0 = (r % p.tiles_x) * TW;
+      const int N = __ldg(&L->N), cout = __ldg(&L->cout), act = __ldg(&L->act), out_vec = __ldg(&L->out_vec);
+      const float* bias = ldg_ptr(&L->bias);
+      const float* scale = ldg_ptr(&L->scale);
+      float* out = ldg_ptr(&L->out);
+      float* out2 = ldg_ptr(&L->out2);
+      const float* res1 = ldg_ptr(&L->res1);
+      const float* res2 = ldg_ptr(&L->res2);
+      const int out_ld = __ldg(&L->out_ld), out2_ld = __ldg(&L->out2_ld);
+      const int res1_ld = __ldg(&L->res1_ld), res2_ld = __ldg(&L->res2_ld);
+      const float alpha1 = __ldg(&L->alpha1), alpha2 = __ldg(&L->alpha2);
       const uint32_t acc = t_it & 1u;
       mbar_wait(tmem_full(acc), (t_it >> 1) & 1u);
       tc_fence_after();
@@ -333,65 +416,66 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
         const bool inb = (gy < p.H) && (gx < p.W);
         const size_t pix = ((size_t)b * p.H + (inb ? gy : 0)) * p.W + (inb ? gx : 0);
 #pragma unroll 1
-        for (int c0 = 0; c0 < p.N; c0 += 16) {
+        for (int c0 = 0; c0 < N; c0 += 16) {
           float v[16];
-          const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (acc * MT + mt) * NB + (uint32_t)c0;
+          const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (acc * MT + mt) * p.nb_max + (uint32_t)c0;
           tmem_ld16(tcol, v);
           if (PASSES == 3) {
             float lo[16];
-            tmem_ld16(tcol + (uint32_t)p.N, lo);
+            tmem_ld16(tcol + (uint32_t)N, lo);
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] += lo[j];
           }
-          if (!inb || c0 >= p.cout || (p.debug & 8)) continue;
-          if (p.bias) {   // bias / scale are padded to >= N entries and 16-byte aligned
+          if (!inb || c0 >= cout || (p.debug & 8)) continue;
+          if (bias) {   // bias / scale are padded to >= N entries and 16-byte aligned
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
-              const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
+              const float4 t4 = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));
               v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
             }
           }
-          if (p.scale) {
+          if (scale) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
-              const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + j));
+              const float4 t4 = __ldg(reinterpret_cast<const float4*>(scale + c0 + j));
               v[j] *= t4.x; v[j + 1] *= t4.y; v[j + 2] *= t4.z; v[j + 3] *= t4.w;
             }
           }
-          if (p.act == HCF_ACT_RELU) {
+          if (act == HCF_ACT_RELU) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-          } else if (p.act == HCF_ACT_LRELU) {
+          } else if (act == HCF_ACT_LRELU) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
           }
-          if (p.out_vec && c0 + 15 < p.cout) {
+          // residuals may have been written by another SM earlier in this launch: L2-coherent loads
+          if (out_vec && c0 + 15 < cout) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
               float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              if (p.res1) {
-                const float4 rr = __ldg(reinterpret_cast<const float4*>(p.res1 + pix * p.res1_ld + c0 + j));
-                o.x = o.x * p.alpha1 + rr.x; o.y = o.y * p.alpha1 + rr.y;
-                o.z = o.z * p.alpha1 + rr.z; o.w = o.w * p.alpha1 + rr.w;
+              if (res1) {
+                const float4 rr = __ldcg(reinterpret_cast<const float4*>(res1 + pix * res1_ld + c0 + j));
+                o.x = o.x * alpha1 + rr.x; o.y = o.y * alpha1 + rr.y;
+                o.z = o.z * alpha1 + rr.z; o.w = o.w * alpha1 + rr.w;
               }
-              if (p.res2) {
-                const float4 rr = __ldg(reinterpret_cast<const float4*>(p.res2 + pix * p.res2_ld + c0 + j));
-                o.x = o.x * p.alpha2 + rr.x; o.y = o.y * p.alpha2 + rr.y;
-                o.z = o.z * p.alpha2 + rr.z; o.w = o.w * p.alpha2 + rr.w;
+              if (res2) {
+                const float4 rr = __ldcg(reinterpret_cast<const float4*>(res2 + pix * res2_ld + c0 + j));
+                o.x = o.x * alpha2 + rr.x; o.y = o.y * alpha2 + rr.y;
+                o.z = o.z * alpha2 + rr.z; o.w = o.w * alpha2 + rr.w;
               }
-              *reinterpret_cast<float4*>(p.out + pix * p.out_ld + c0 + j) = o;
-              if (p.out2) *reinterpret_cast<float4*>(p.out2 + pix * p.out2_ld + c0 + j) = o;
+              *reinterpret_cast<float4*>(out + pix * out_ld + c0 + j) = o;
+              if (out2) *reinterpret_cast<float4*>(out2 + pix * out2_ld + c0 + j) = o;
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int c = c0 + j;
-              if (c < p.cout) {
+              if (c < cout) {
                 float t = v[j];
-                if (p.res1) t = t * p.alpha1 + __ldg(p.res1 + pix * p.res1_ld + c);
-                if (p.res2) t = t * p.alpha2 + __ldg(p.res2 + pix * p.res2_ld + c);
-                p.out[pix * p.out_ld + c] = t;
-                if (p.out2) p.out2[pix * p.out2_ld + c] = t;
+                if (res1) t = t * alpha1 + __ldcg(res1 + pix * res1_ld + c);
+                if (res2) t = t * alpha2 + __ldcg(res2 + pix * res2_ld + c);
+                out[pix * out_ld + c] = t;
+                if (out2) out2[pix * out2_ld + c] = t;
               }
             }
           }
@@ -399,6 +483,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
       }
       tc_fence_before();
       mbar_arrive(tmem_empty(acc));   // all TMEM reads of this item are complete (wait::ld above)
+      if (chain) {
+        // publish: every epilogue thread's stores -> gpu-scope fence -> 128-thread barrier -> counter
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) atomicAdd(p.done + tile, 1);
+      }
     }
   } else {
     // ===================== A_lo converters (PASSES == 3) =====================
@@ -406,7 +496,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
       const int et = threadIdx.x - 192;   // 0..127
       uint32_t a_it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        for (int kc = 0; kc < p.kchunks; ++kc, ++a_it) {
+        const int kchunks = __ldg(&(p.layers + item / p.n_tiles)->kchunks);
+        for (int kc = 0; kc < kchunks; ++kc, ++a_it) {
           const int sA = a_it % p.sa;
           mbar_wait(fullA(sA), (a_it / p.sa) & 1u);
           const float4* src = reinterpret_cast<const float4*>(gen_base + (size_t)sA * A_STAGE);
@@ -463,9 +554,8 @@ static int num_sms() {
 }
 
 // ring depths and B slab granularity that fit in shared memory; false if nothing fits
-static bool pick_rings(int mt, int passes, int ks, int N, int* sa, int* sb, int* dys, size_t* smem) {
+static bool pick_rings(int mt, int passes, int ks, int NB, int* sa, int* sb, int* dys, size_t* smem) {
   const int a_stage = a_part(mt, ks) * (passes == 3 ? 2 : 1);
-  const int NB = N * (passes == 3 ? 2 : 1);
   const int budget = SMEM_LIMIT - 1024 - 512;
   // 1) whole-chunk B stages (one barrier round trip per chunk) if >= 2 of them fit beside >= 2 A stages
   {
@@ -497,7 +587,8 @@ static bool pick_rings(int mt, int passes, int ks, int N, int* sa, int* sb, int*
   return true;
 }
 
-typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const Params);
+typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                         const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const Params);
 
 static KernelFn pick_kernel(int mt, int passes, int ks) {
   if (ks == 1) return passes == 3 ? conv_tc_kernel<1, 3, 1> : conv_tc_kernel<1, 1, 1>;
@@ -509,9 +600,10 @@ static KernelFn pick_kernel(int mt, int passes, int ks) {
 }  // namespace hcf
 
 struct hcf_conv_tc_plan {
-  CUtensorMap amap[3];
+  CUtensorMap maps[hcf::tc::MAX_MAPS];
   hcf::tc::Params p;
   hcf::tc::KernelFn fn;
+  hcf::tc::LayerDesc* d_layers;
   size_t smem_bytes;
   int threads;
   dim3 grid;
@@ -565,44 +657,46 @@ extern "C" int hcf_conv_tc_pack_weights(const float* w, int32_t kin, int32_t cou
   return 0;
 }
 
-extern "C" int hcf_conv_tc_plan_create(const hcf_conv_args* a, const float* wtc, int32_t passes,
-                                       hcf_conv_tc_plan** out) {
+// A chain of n convolutions on the same [B,H,W] grid with the same kernel size, each TC-eligible,
+// executed by one persistent launch.  Conv i may read anything convs < i wrote (dependencies are
+// tracked per 3x3 tile neighbourhood, which also covers write-after-read).  `done_flags`
+// (device, B*ceil(H/16)*ceil(W/8) int32) must be zeroed before every run; NULL is allowed for n == 1.
+extern "C" int hcf_conv_chain_create(const hcf_conv_args* args, const float* const* wtc, int32_t n, int32_t passes,
+                                     int32_t* done_flags, hcf_conv_tc_plan** out) {
   using namespace hcf;
-  HCF_REQUIRE(out != nullptr, "tc_plan: null out");
+  HCF_REQUIRE(out != nullptr, "tc_chain: null out");
   *out = nullptr;
-  int rc = validate_conv_args(a);
-  if (rc) return rc;
-  HCF_REQUIRE(hcf_conv_tc_supported(a), "tc_plan: unsupported shape");
-  HCF_REQUIRE(wtc && aligned16(wtc), "tc_plan: weight image alignment");
-  HCF_REQUIRE(passes == 1 || passes == 3, "tc_plan: passes %d", passes);
+  HCF_REQUIRE(args && wtc && n >= 1, "tc_chain: bad args");
+  HCF_REQUIRE(n == 1 || done_flags != nullptr, "tc_chain: a chain needs the done-flag array");
+  HCF_REQUIRE(passes == 1 || passes == 3, "tc_chain: passes %d", passes);
+  const int ks = args[0].ks;
+  for (int i = 0; i < n; ++i) {
+    int rc = validate_conv_args(&args[i]);
+    if (rc) return rc;
+    HCF_REQUIRE(hcf_conv_tc_supported(&args[i]), "tc_chain: conv %d: unsupported shape", i);
+    HCF_REQUIRE(wtc[i] && aligned16(wtc[i]), "tc_chain: conv %d: weight image alignment", i);
+    HCF_REQUIRE(args[i].ks == ks && args[i].B == args[0].B && args[i].H == args[0].H && args[i].W == args[0].W,
+                "tc_chain: conv %d: all convs of a chain share ks and [B,H,W]", i);
+  }
   tc::EncodeTiledFn enc = tc::get_encode();
-  HCF_REQUIRE(enc != nullptr, "tc_plan: cuTensorMapEncodeTiled entry point not found");
+  HCF_REQUIRE(enc != nullptr, "tc_chain: cuTensorMapEncodeTiled entry point not found");
+  const hcf_conv_args* a0 = &args[0];
   hcf_conv_tc_plan* pl = new hcf_conv_tc_plan();
   memset(pl, 0, sizeof(*pl));
   tc::Params& p = pl->p;
-  const int ks = a->ks;
-  p.B = a->B; p.H = a->H; p.W = a->W;
-  int kc = 0;
-  p.kc_end0 = p.kc_end1 = 1 << 30;
-  for (int i = 0; i < a->nseg; ++i) {
-    kc += (a->seg[i].C + 31) / 32;
-    if (i == 0) p.kc_end0 = kc;
-    if (i == 1) p.kc_end1 = kc;
-  }
-  p.kchunks = kc;
-  if (a->nseg == 1) p.kc_end0 = p.kc_end1 = kc;
-  if (a->nseg == 2) p.kc_end1 = kc;
-  p.N = tc::n_for(a->cout);
-  p.cout = a->cout;
+  p.B = a0->B; p.H = a0->H; p.W = a0->W;
   const int sms = tc::num_sms();
+  int nmax = 0;
+  for (int i = 0; i < n; ++i) nmax = nmax > tc::n_for(args[i].cout) ? nmax : tc::n_for(args[i].cout);
+  p.nb_max = nmax * (passes == 3 ? 2 : 1);
   // sub-tiles per work item: 2 halves the weight traffic per pixel but quantises worse on small images
   int mt = 1;
   const char* env = getenv("HCF_TC_MT");
-  if (passes == 1 && ks == 3) {
-    const long items1 = (long)a->B * ceil_div(a->H, 16) * ceil_div(a->W, 8);
-    const long items2 = (long)a->B * ceil_div(a->H, 32) * ceil_div(a->W, 8);
-    const double t1 = (double)ceil_div((int)items1, sms) * (tc::a_part(1, 3) + 9.0 * p.N * 128);
-    const double t2 = (double)ceil_div((int)items2, sms) * (tc::a_part(2, 3) + 9.0 * p.N * 128);
+  if (passes == 1 && ks == 3 && n == 1) {
+    const long items1 = (long)a0->B * ceil_div(a0->H, 16) * ceil_div(a0->W, 8);
+    const long items2 = (long)a0->B * ceil_div(a0->H, 32) * ceil_div(a0->W, 8);
+    const double t1 = (double)ceil_div((int)items1, sms) * (tc::a_part(1, 3) + 9.0 * nmax * 128);
+    const double t2 = (double)ceil_div((int)items2, sms) * (tc::a_part(2, 3) + 9.0 * nmax * 128);
     mt = (t2 < 0.80 * t1) ? 2 : 1;
     if (env && (env[0] == '1' || env[0] == '2')) mt = env[0] - '0';
   }
@@ -610,58 +704,125 @@ extern "C" int hcf_conv_tc_plan_create(const hcf_conv_args* a, const float* wtc,
     const char* dbg = getenv("HCF_TC_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
   }
-  if (!tc::pick_rings(mt, passes, ks, p.N, &p.sa, &p.sb, &p.dys, &pl->smem_bytes)) {
+  if (!tc::pick_rings(mt, passes, ks, p.nb_max, &p.sa, &p.sb, &p.dys, &pl->smem_bytes)) {
     delete pl;
-    set_error("tc_plan: tile does not fit in shared memory");
+    set_error("tc_chain: tile does not fit in shared memory");
     return HCF_ENOTSUP;
   }
-  p.tiles_x = ceil_div(a->W, tc::TW); p.tiles_y = ceil_div(a->H, tc::TH * mt);
-  p.n_items = p.tiles_x * p.tiles_y * a->B;
-  p.wimg = wtc; p.bias = a->bias; p.scale = a->scale; p.act = a->act;
-  p.out = a->out; p.out_ld = a->out_ld; p.out2 = a->out2; p.out2_ld = a->out2_ld;
-  p.res1 = a->res1; p.res1_ld = a->res1_ld; p.alpha1 = a->alpha1;
-  p.res2 = a->res2; p.res2_ld = a->res2_ld; p.alpha2 = a->alpha2;
-  bool ov = aligned16(a->out) && a->out_ld % 4 == 0;
-  if (a->out2) ov = ov && aligned16(a->out2) && a->out2_ld % 4 == 0;
-  if (a->res1) ov = ov && aligned16(a->res1) && a->res1_ld % 4 == 0;
-  if (a->res2) ov = ov && aligned16(a->res2) && a->res2_ld % 4 == 0;
-  p.out_vec = ov ? 1 : 0;
+  p.tiles_x = ceil_div(a0->W, tc::TW); p.tiles_y = ceil_div(a0->H, tc::TH * mt);
+  p.n_tiles = p.tiles_x * p.tiles_y * a0->B;
+  p.n_layers = n;
+  p.n_items = p.n_tiles * n;
+  p.done = n > 1 ? done_flags : nullptr;
 
+  // ---- tensor maps, de-duplicated.  A segment whose channel count is a multiple of 32 never reads
+  // beyond its last chunk, so such segments of one buffer share a map of the widest extent seen.
+  struct MapKey { const float* ptr; int ld; int C; bool ragged; };
+  std::vector<MapKey> keys;
+  std::vector<tc::LayerDesc> layers(n);
+  for (int i = 0; i < n; ++i) {
+    const hcf_conv_args& a = args[i];
+    tc::LayerDesc& L = layers[i];
+    memset(&L, 0, sizeof(L));
+    L.nseg = a.nseg;
+    int kc = 0;
+    for (int s = 0; s < 3; ++s) {
+      if (s < a.nseg) {
+        const hcf_seg& sg = a.seg[s];
+        const bool ragged = (sg.C % 32) != 0;
+        int found = -1;
+        for (size_t k = 0; k < keys.size(); ++k)
+          if (keys[k].ptr == sg.ptr && keys[k].ld == sg.ld && keys[k].ragged == ragged && (!ragged || keys[k].C == sg.C))
+            found = (int)k;
+        if (found < 0) {
+          keys.push_back({sg.ptr, sg.ld, sg.C, ragged});
+          found = (int)keys.size() - 1;
+        } else if (!ragged && keys[found].C < sg.C) {
+          keys[found].C = sg.C;
+        }
+        L.map_idx[s] = found;
+        kc += (sg.C + 31) / 32;
+      }
+      L.seg_end[s] = s < a.nseg ? kc : (1 << 30);
+    }
+    L.seg_end[a.nseg - 1] = 1 << 30;
+    L.kchunks = kc;
+    L.N = tc::n_for(a.cout);
+    L.cout = a.cout;
+    L.act = a.act;
+    L.wimg = wtc[i]; L.bias = a.bias; L.scale = a.scale;
+    L.out = a.out; L.out_ld = a.out_ld; L.out2 = a.out2; L.out2_ld = a.out2_ld;
+    L.res1 = a.res1; L.res1_ld = a.res1_ld; L.alpha1 = a.alpha1;
+    L.res2 = a.res2; L.res2_ld = a.res2_ld; L.alpha2 = a.alpha2;
+    bool ov = aligned16(a.out) && a.out_ld % 4 == 0;
+    if (a.out2) ov = ov && aligned16(a.out2) && a.out2_ld % 4 == 0;
+    if (a.res1) ov = ov && aligned16(a.res1) && a.res1_ld % 4 == 0;
+    if (a.res2) ov = ov && aligned16(a.res2) && a.res2_ld % 4 == 0;
+    L.out_vec = ov ? 1 : 0;
+  }
+  if ((int)keys.size() > tc::MAX_MAPS) {
+    delete pl;
+    set_error("tc_chain: %d distinct input views (max %d)", (int)keys.size(), tc::MAX_MAPS);
+    return HCF_ENOTSUP;
+  }
   const cuuint32_t box[4] = {(cuuint32_t)tc::KCH, (cuuint32_t)tc::halo_w(ks), (cuuint32_t)tc::halo_rows(mt, ks), 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
-  for (int i = 0; i < 3; ++i) {
-    const hcf_seg& sg = a->seg[i < a->nseg ? i : 0];   // unused maps alias segment 0 (never dereferenced)
-    const cuuint64_t dims[4] = {(cuuint64_t)sg.C, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->B};
-    const cuuint64_t ld_b = (cuuint64_t)sg.ld * 4;
-    const cuuint64_t strides[3] = {ld_b, ld_b * a->W, ld_b * a->W * a->H};
-    CUresult r = enc(&pl->amap[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(sg.ptr), dims, strides,
+  for (int i = 0; i < tc::MAX_MAPS; ++i) {
+    const MapKey& k = keys[i < (int)keys.size() ? i : 0];   // unused maps alias map 0 (never dereferenced)
+    const cuuint64_t dims[4] = {(cuuint64_t)k.C, (cuuint64_t)a0->W, (cuuint64_t)a0->H, (cuuint64_t)a0->B};
+    const cuuint64_t ld_b = (cuuint64_t)k.ld * 4;
+    const cuuint64_t strides[3] = {ld_b, ld_b * a0->W, ld_b * a0->W * a0->H};
+    CUresult r = enc(&pl->maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(k.ptr), dims, strides,
                      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       delete pl;
-      set_error("tc_plan: cuTensorMapEncodeTiled failed with %d (segment %d, C %d, ld %d)", (int)r, i, sg.C, sg.ld);
+      set_error("tc_chain: cuTensorMapEncodeTiled failed with %d (view %d, C %d, ld %d)", (int)r, i, k.C, k.ld);
       return HCF_EINVAL;
     }
   }
-  pl->grid = dim3((unsigned)(p.n_items < sms ? p.n_items : sms));
+  cudaError_t e = cudaMalloc(&pl->d_layers, sizeof(tc::LayerDesc) * n);
+  if (e == cudaSuccess)
+    e = cudaMemcpy(pl->d_layers, layers.data(), sizeof(tc::LayerDesc) * n, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    if (pl->d_layers) cudaFree(pl->d_layers);
+    delete pl;
+    set_error("tc_chain: layer table upload: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  p.layers = pl->d_layers;
+  pl->grid = dim3((unsigned)(p.n_tiles < sms ? p.n_tiles : sms));
   pl->threads = passes == 3 ? 320 : 192;
   pl->fn = tc::pick_kernel(mt, passes, ks);
-  cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(pl->fn),
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT);
+  e = cudaFuncSetAttribute(reinterpret_cast<const void*>(pl->fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           tc::SMEM_LIMIT);
   if (e != cudaSuccess) {
+    cudaFree(pl->d_layers);
     delete pl;
-    set_error("tc_plan: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    set_error("tc_chain: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return (int)e;
   }
   *out = pl;
   return 0;
 }
 
+extern "C" int hcf_conv_tc_plan_create(const hcf_conv_args* a, const float* wtc, int32_t passes,
+                                       hcf_conv_tc_plan** out) {
+  return hcf_conv_chain_create(a, &wtc, 1, passes, nullptr, out);
+}
+
+extern "C" int32_t hcf_conv_tc_plan_layers(const hcf_conv_tc_plan* pl) { return pl ? pl->p.n_layers : 0; }
+
 extern "C" int hcf_conv_tc_run(const hcf_conv_tc_plan* pl, void* stream) {
   using namespace hcf;
   HCF_REQUIRE(pl != nullptr, "tc_run: null plan");
-  pl->fn<<<pl->grid, pl->threads, pl->smem_bytes, (cudaStream_t)stream>>>(pl->amap[0], pl->amap[1], pl->amap[2], pl->p);
+  pl->fn<<<pl->grid, pl->threads, pl->smem_bytes, (cudaStream_t)stream>>>(
+      pl->maps[0], pl->maps[1], pl->maps[2], pl->maps[3], pl->maps[4], pl->maps[5], pl->maps[6], pl->maps[7], pl->p);
   return finish_launch("hcf_conv_tc_run");
 }
 
-extern "C" void hcf_conv_tc_plan_destroy(hcf_conv_tc_plan* p) { delete p; }
+extern "C" void hcf_conv_tc_plan_destroy(hcf_conv_tc_plan* p) {
+  if (!p) return;
+  if (p->d_layers) cudaFree(p->d_layers);
+  delete p;
+}

@@ -18,7 +18,7 @@ from . import prep
 class Engine:
     """One compiled plan = (net weights, direction, B, h, w, precision) on one device."""
 
-    def __init__(self, net, direction, B, h, w, device, precision="fp32", use_graph=True):
+    def __init__(self, net, direction, B, h, w, device, precision="fp32", use_graph=True, use_chains=True):
         if not torch.cuda.is_available():
             raise L.HcfError("hcflow_b200 needs a CUDA device (no CPU fallback)")
         self.lib = L.load()
@@ -37,6 +37,9 @@ class Engine:
         self.calls = []
         self.n_tc = 0
         self.n_fp32_conv = 0
+        self.n_chains = 0
+        self.call_info = []      # per call: {"cls", "tag", "flops", "convs"}
+        self.use_chains = use_chains
         with torch.cuda.device(self.device):
             self._alloc()
             self.load_weights()
@@ -113,7 +116,8 @@ class Engine:
     def _lower(self):
         lib = self.lib
         B = self.B
-        for op in self.plan.ops:
+        pending = []
+        for idx, op in enumerate(self.plan.ops):
             if isinstance(op, P.ConvOp):
                 a = L.ConvArgs()
                 a.B, a.H, a.W, a.nseg = B, op.H, op.W, len(op.segs)
@@ -138,12 +142,21 @@ class Engine:
                     a.res2, a.res2_ld = self._vptr(op.res2)
                     a.alpha2 = op.alpha2
                 self._keep.append(a)
-                tc = self._try_tc(op, a)
-                if tc is not None:
-                    self.calls.append((lib.hcf_conv_tc_run, tc, "conv_tc:" + op.tag))
-                    self.n_tc += 1
+                cin = sum(v.C for v, _ in op.segs)
+                flops = 2.0 * B * op.H * op.W * op.ks * op.ks * cin * op.cout
+                tag = "{}@{}x{}".format(op.tag, op.H, op.W)
+                if self._tc_eligible(a):
+                    pending.append((op, a, flops, tag))
+                    nxt = self.plan.ops[idx + 1] if idx + 1 < len(self.plan.ops) else None
+                    same = (isinstance(nxt, P.ConvOp) and self.use_chains and nxt.ks == 3 and op.ks == 3
+                            and (nxt.H, nxt.W) == (op.H, op.W))
+                    if not same:
+                        self._flush_tc(pending)
+                        pending = []
                 else:
-                    self.calls.append((lib.hcf_conv_fp32, C.byref(a), "conv_fp32:" + op.tag))
+                    self._flush_tc(pending)
+                    pending = []
+                    self._add_call(lib.hcf_conv_fp32, C.byref(a), "conv_fp32", tag, flops, 1)
                     self.n_fp32_conv += 1
             elif isinstance(op, P.StepOp):
                 a = L.StepArgs()
@@ -161,7 +174,7 @@ class Engine:
                 fn = {"inverse": lib.hcf_step_inverse, "forward_head": lib.hcf_step_forward_head,
                       "forward_coupling": lib.hcf_step_forward_coupling}[op.variant]
                 self._keep.append(a)
-                self.calls.append((fn, C.byref(a), "step_" + op.variant))
+                self._add_call(fn, C.byref(a), "step_" + op.variant)
             elif isinstance(op, P.PriorOp):
                 a = L.PriorArgs()
                 a.B, a.H, a.W, a.Cz = B, op.H, op.W, op.z.C
@@ -178,7 +191,7 @@ class Engine:
                     a.out_nchw = self.ext[op.out_name].data_ptr()
                     fn = lib.hcf_prior_standardize
                 self._keep.append(a)
-                self.calls.append((fn, C.byref(a), "prior_" + op.variant))
+                self._add_call(fn, C.byref(a), "prior_" + op.variant)
             elif isinstance(op, P.LayoutOp):
                 if op.variant in ("ingest", "egress"):
                     a = L.LayoutArgs()
@@ -204,24 +217,26 @@ class Engine:
                           "haar_fwd": lib.hcf_haar_forward, "haar_inv": lib.hcf_haar_inverse,
                           "copy": lib.hcf_copy_view}[op.variant]
                 self._keep.append(a)
-                self.calls.append((fn, C.byref(a), "layout_" + op.variant))
+                self._add_call(fn, C.byref(a), "layout_" + op.variant)
             elif isinstance(op, P.DiracLogpOp):
                 x, m, ld = self.ext[op.x_name].data_ptr(), self.ext[op.mean_name].data_ptr(), self.logdet.data_ptr()
                 lg, n = op.logs, op.n
 
                 def call(_unused, stream, x=x, m=m, lg=lg, n=n, ld=ld):
                     return lib.hcf_gauss_logp_const(x, m, lg, B, n, ld, stream)
-                self.calls.append((call, None, "dirac_logp"))
+                self._add_call(call, None, "dirac_logp")
             else:
                 raise TypeError(op)
+        self._flush_tc(pending)
 
-    def _try_tc(self, op, a):
-        """Tensor-core plan for this conv if the precision mode asks for it and the shape fits."""
-        if self.precision == "fp32":
-            return None
-        if not self.lib.hcf_conv_tc_supported(C.byref(a)):
-            return None
-        passes = {"tf32": 1, "tf32x3": 3}[self.precision]
+    def _add_call(self, fn, arg, cls, tag="", flops=0.0, convs=0):
+        self.calls.append((fn, arg, cls))
+        self.call_info.append({"cls": cls, "tag": tag or cls, "flops": flops, "convs": convs})
+
+    def _tc_eligible(self, a):
+        return self.precision != "fp32" and bool(self.lib.hcf_conv_tc_supported(C.byref(a)))
+
+    def _tc_weights(self, op, passes):
         key = self._wkey(op) + "#tc{}".format(passes)
         if key not in self.weights:
             w = prep.pad_weight_for_tc(self._sd_cpu[op.weight], [v.C for v, _ in op.segs])
@@ -230,11 +245,46 @@ class Engine:
             img = torch.zeros(nbytes // 4, dtype=torch.float32)
             L.check(self.lib.hcf_conv_tc_pack_weights(w.data_ptr(), kin, cout, ks, passes, img.data_ptr()), "tc_pack")
             self.weights[key] = img.to(self.device)
-        handle = C.c_void_p()
-        L.check(self.lib.hcf_conv_tc_plan_create(C.byref(a), self.weights[key].data_ptr(), passes, C.byref(handle)),
-                "tc_plan_create")
-        self._tc_plans.append(handle)
-        return handle
+        return self.weights[key]
+
+    def _flush_tc(self, pending):
+        """Lower a run of consecutive tensor-core convs: one persistent chained launch when the run
+        has more than one conv (same grid, 3x3), otherwise a single-conv launch."""
+        if not pending:
+            return
+        lib = self.lib
+        passes = {"tf32": 1, "tf32x3": 3}[self.precision]
+        if len(pending) > 1:
+            n = len(pending)
+            arr = (L.ConvArgs * n)()
+            wptr = (C.c_void_p * n)()
+            for i, (op, a, _, _) in enumerate(pending):
+                C.memmove(C.byref(arr[i]), C.byref(a), C.sizeof(L.ConvArgs))
+                wptr[i] = self._tc_weights(op, passes).data_ptr()
+            op0 = pending[0][0]
+            tiles = self.B * ((op0.H + 15) // 16) * ((op0.W + 7) // 8)
+            flags = torch.zeros(tiles, dtype=torch.int32, device=self.device)
+            handle = C.c_void_p()
+            rc = lib.hcf_conv_chain_create(arr, wptr, n, passes, flags.data_ptr(), C.byref(handle))
+            if rc == 0:
+                self._keep += [arr, wptr, flags]
+                self._tc_plans.append(handle)
+                self._add_call(lambda _a, _s, f=flags: (f.zero_(), 0)[1], None, "flags_zero")
+                flops = sum(p[2] for p in pending)
+                self._add_call(lib.hcf_conv_tc_run, handle, "conv_tc_chain",
+                               "chain[{}..{}]x{}".format(pending[0][3], pending[-1][3], n), flops, n)
+                self.n_tc += n
+                self.n_chains += 1
+                return
+            if rc != -2:   # anything but "not supported as a chain" is a real error
+                L.check(rc, "conv_chain_create")
+        for op, a, flops, tag in pending:
+            handle = C.c_void_p()
+            L.check(lib.hcf_conv_tc_plan_create(C.byref(a), self._tc_weights(op, passes).data_ptr(), passes,
+                                                C.byref(handle)), "tc_plan_create")
+            self._tc_plans.append(handle)
+            self._add_call(lib.hcf_conv_tc_run, handle, "conv_tc", tag, flops, 1)
+            self.n_tc += 1
 
     # ------------------------------------------------------------------ execution
     def _launch_all(self):

@@ -325,3 +325,29 @@ def test_tensor_core_modes_match_reference_golden(cfg, precision, report):
     report["e2e_reverse_{}/{}".format(precision, cfg)] = {"hr_raw_max": e, "hr_raw_mean": mean, "tc_convs": eng.n_tc,
                                                           "fp32_convs": eng.n_fp32_conv}
     assert e < E2E_TOL[precision], (cfg, precision, e)
+
+
+@pytest.mark.parametrize("precision", ["tf32", "tf32x3"])
+def test_chained_launch_is_bit_identical_to_separate_launches(precision, report):
+    """The persistent chained launch (one kernel for all convs of an encoder level, inter-tile
+    dependency counters) must reproduce the conv-by-conv launches bit for bit at full size
+    (B=16, 40x40 -> 160x160: 240 / 800 tiles per layer over 148 CTAs), three times in a row."""
+    opt, net, sd = _net_cuda("sr_x4", precision)
+    B = 16
+    lr = synth.synthetic_lr(B, 40, 40, seed=5).cuda()
+    unit = synth.synthetic_noise(orc.noise_shapes(opt, B, 40, 40, True), seed=9)
+    with torch.no_grad():
+        net.use_chains = False
+        net(lr=lr, eps_std=0.8, reverse=True, eps=unit)
+        want = net.last["hr_raw"].clone()
+        e0 = [e for e in net._engines.values()][-1]
+        assert e0.n_chains == 0
+        net.use_chains = True
+        for rep in range(3):
+            net(lr=lr, eps_std=0.8, reverse=True, eps=unit)
+            got = net.last["hr_raw"]
+            assert torch.equal(got, want), (rep, float((got - want).abs().max()))
+        e1 = [e for e in net._engines.values()][-1]
+        assert e1.n_chains >= 2 and e1.launches_per_run < e0.launches_per_run
+    report["chain/{}".format(precision)] = {"launches_chained": e1.launches_per_run,
+                                            "launches_separate": e0.launches_per_run, "chains": e1.n_chains}
