@@ -265,25 +265,32 @@ def run_ours(args):
     per_class_times(eng2)
     classes = per_class_times(eng2)
     total_ms = sum(v[1] for c, v in classes.items() if c != "conv_tc_all")
-    # dominant class = all tcgen05 conv launches (single + chained) if any, else the largest class
+    # dominant kernel = the single largest launch (the chained tcgen05 encoder kernel of the 80x80 level);
+    # the aggregate over every tcgen05 conv launch is reported next to it
     tc_keys = [c for c in classes if c.startswith("conv_tc")]
-    if tc_keys:
-        classes["conv_tc_all"] = (sum(classes[c][0] for c in tc_keys), sum(classes[c][1] for c in tc_keys),
-                                  sum(classes[c][2] for c in tc_keys))
-    dom = "conv_tc_all" if tc_keys else max(classes, key=lambda c: classes[c][1])
-    n, ms, fl = classes[dom]
     peaks = load_peaks()
+    by_tag = per_class_times.by_tag
+    top_tag = max(by_tag, key=lambda t: by_tag[t][1] / by_tag[t][0])
+    n, ms, fl = by_tag[top_tag]
     achieved = fl / (ms / 1e3) / 1e12
+    # DRAM bytes per launch of that kernel from the committed ncu --set full capture (profiles/README.md)
+    ncu_traffic = {"tf32x3": 5.76e9, "tf32": 5.42e9}.get(args.precision) if "chain" in top_tag else None
     roofline = {
-        "bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-        "frac": achieved / peaks["bf16_tflops"], "traffic": None,
-        "peak_source": "{} bf16 burst (TF32 tensor peak is nominally half; fp32 FFMA kernels do not use the "
-                       "tensor pipe at all)".format(peaks["source"]),
+        "bound": "tensor", "kernel": "conv_tc_kernel " + top_tag, "achieved": achieved, "peak": peaks["bf16_tflops"],
+        "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"], "traffic": ncu_traffic,
+        "traffic_note": "dram__bytes_read+write per launch, ncu --set full, profiles/r01_prof_chain_L0_*_summary.csv; "
+                        "algorithmic bytes of that launch = 2.34e9",
+        "peak_source": "{} bf16 burst from MEASURED_PEAKS.json (the kernel computes in TF32, nominal peak = half "
+                       "of it; tf32x3 issues 2 MMAs per useful K-step)".format(peaks["source"]),
         "launches": n, "avg_launch_ms": ms / n, "share_of_step": ms / total_ms,
         "classes": {c: {"n": v[0], "ms": round(v[1], 4), "gflop": round(v[2] / 1e9, 3)} for c, v in classes.items()},
         "conv_by_layer": {t: {"n": v[0], "ms": round(v[1], 3), "tflops": round(v[2] / max(v[1], 1e-9) / 1e9, 1)}
-                          for t, v in sorted(per_class_times.by_tag.items(), key=lambda kv: -kv[1][1])},
+                          for t, v in sorted(by_tag.items(), key=lambda kv: -kv[1][1])},
     }
+    if tc_keys:
+        a_n, a_ms, a_fl = (sum(classes[c][k] for c in tc_keys) for k in range(3))
+        roofline["all_tcgen05_convs"] = {"launches": a_n, "ms": round(a_ms, 3), "tflops": round(a_fl / a_ms / 1e9, 1),
+                                         "frac": a_fl / a_ms / 1e9 / peaks["bf16_tflops"], "share_of_step": a_ms / total_ms}
     # ---- CPU baseline (rank 0, N=1 only): the oracle on the host cores, bounded sample
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
