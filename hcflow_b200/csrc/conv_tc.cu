@@ -4,7 +4,7 @@
 //   D[128 pixels, N] += A[128 pixels, 32 ch] * B[N, 32 ch]^T     per (tap, 32-channel chunk)
 //
 // Work item = MT vertically adjacent 16x8 pixel tiles of one image (UMMA M = 128 each) x all
-// N = ceil16(Cout) <= 64 output channels.  CTAs are persistent (grid = #SMs, items strided by
+// N = ceil16(Cout) <= 128 output channels.  CTAs are persistent (grid = #SMs, items strided by
 // gridDim.x) and warp-specialised.  A launch executes either one convolution or a CHAIN of
 // dependent convolutions on the same pixel grid (e.g. the 211 convs of an RRDB encoder level):
 // item = (layer, tile) in layer-major order; a tile of layer l may start once the 3x3 tile
@@ -62,7 +62,7 @@ struct LayerDesc {
   int map_idx[3];     // tensor map of each segment
   int seg_end[3];     // chunk index where segment i ends (prefix sums)
   int kchunks;        // total 32-channel chunks
-  int N;              // UMMA N (multiple of 16, <= 64)
+  int N;              // UMMA N (multiple of 16, <= 128)
   int cout;
   int act;
   int out_vec;
@@ -83,7 +83,7 @@ struct Params {
   int n_items;        // n_layers * n_tiles
   int nb_max;         // max over layers of B rows per tap (N, or 2N in 3-pass mode)
   int sa, sb;         // ring depths
-  int dys;            // dy rows of taps per B slab: KS (whole chunk) or 1
+  int slab_taps;      // taps per B ring slot: KS*KS (whole chunk), KS (one dy row) or 1
   int debug;          // timing experiments only (HCF_TC_DEBUG, wrong results): 1 aligned A descriptors,
                       // 2 no MMAs, 4 no loads, 8 no epilogue stores, 16 launch only, 32 prologue only
   const LayerDesc* layers;
@@ -199,8 +199,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap maps0, const __grid_constant_
   if (p.debug & 16) return;   // timing experiment: launch cost only
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t slot_bytes = (uint32_t)KS * p.dys * p.nb_max * ROW_BYTES;   // B ring slot (largest layer)
-  const int slabs = KS / p.dys;                                              // slabs per 32-channel chunk
+  const uint32_t slot_bytes = (uint32_t)p.slab_taps * p.nb_max * ROW_BYTES;  // B ring slot (largest layer)
+  const int slabs = (KS * KS) / p.slab_taps;                                 // slabs per 32-channel chunk
   const uint32_t b_base = smem_base + p.sa * A_STAGE;
   const uint32_t bar_base = b_base + p.sb * slot_bytes;
   auto fullA = [&](int s) { return bar_base + 8u * s; };
@@ -221,7 +221,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap maps0, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t need_cols = 2u * MT * p.nb_max;
-  const uint32_t tmem_cols = need_cols <= 32 ? 32u : (need_cols <= 64 ? 64u : (need_cols <= 128 ? 128u : 256u));
+  const uint32_t tmem_cols =
+      need_cols <= 32 ? 32u : (need_cols <= 64 ? 64u : (need_cols <= 128 ? 128u : (need_cols <= 256 ? 256u : 512u)));
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&maps0) : "memory");
@@ -269,7 +270,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap maps0, const __grid_constant_
         const int se0 = __ldg(&L->seg_end[0]), se1 = __ldg(&L->seg_end[1]);
         const int m0 = __ldg(&L->map_idx[0]), m1 = __ldg(&L->map_idx[1]), m2 = __ldg(&L->map_idx[2]);
         const uint32_t tap_bytes = (uint32_t)__ldg(&L->N) * PARTS * ROW_BYTES;
-        const uint32_t b_slab = (uint32_t)KS * p.dys * tap_bytes;
+        const uint32_t b_slab = (uint32_t)p.slab_taps * tap_bytes;
         const uint8_t* wimg = reinterpret_cast<const uint8_t*>(ldg_ptr(&L->wimg));
         if (chain && layer > 0) {
           // wait until layer-1 is complete on the 3x3 tile neighbourhood (halo + WAR safety)
@@ -337,7 +338,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap maps0, const __grid_constant_
       const uint32_t idesc_n = (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((NB >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t acc = t_it & 1u;
-      mbar_wait(tmem_empty(acc), ((t_it >> 1) & 1u) ^ 1u);
+      mbar_wait(tmem_empty(acc), ((t_it >> 1) & 1u) ^ 1u);   // all lanes poll: measured faster than lane 0 + syncwarp
       tc_fence_after();
       const uint32_t d0 = tmem_base + acc * MT * p.nb_max;
       uint32_t accum = 0u;   // first MMA of the item overwrites the accumulator
@@ -353,25 +354,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap maps0, const __grid_constant_
           tc_fence_after();
           if (elect_one()) {
             const uint64_t b0 = b_tmpl + ((b_base + sB * slot_bytes) >> 4);
-            for (int dyl = 0; dyl < ((p.debug & 2) ? 0 : p.dys); ++dyl) {
-              uint64_t a_dy = a0 + (uint32_t)((sl * p.dys + dyl) * HALO_W * (ROW_BYTES >> 4));
-              if (p.debug & 1) a_dy = make_desc(0, 8u * ROW_BYTES) + ((smem_base + sA * A_STAGE) >> 4);
-              const uint64_t b_dy = b0 + (uint32_t)(dyl * KS) * nb;
+            for (int t = 0; t < ((p.debug & 2) ? 0 : p.slab_taps); ++t) {
+              const int tap = sl * p.slab_taps + t;
+              const int dy = tap / KS, dx = tap - dy * KS;
+              uint64_t a_tap = a0 + (uint32_t)((dy * HALO_W + dx) * (ROW_BYTES >> 4));
+              if (p.debug & 1) a_tap = make_desc(0, 8u * ROW_BYTES) + ((smem_base + sA * A_STAGE) >> 4);
+              const uint64_t b_tap = b0 + (uint32_t)t * nb;
 #pragma unroll
-              for (int dx = 0; dx < KS; ++dx) {
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t bd = b_tap + 2u * k;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const uint64_t bd = b_dy + (dx * nb + 2u * k);
-#pragma unroll
-                  for (int mt = 0; mt < MT; ++mt) {
-                    const uint32_t d = d0 + mt * p.nb_max;
-                    const uint64_t ad = a_dy + ((p.debug & 1) ? (uint32_t)(k * 2)
-                                                              : (uint32_t)(((mt * TH * HALO_W + dx) * ROW_BYTES + k * 32) >> 4));
-                    umma_tf32(d, ad, bd, idesc, accum);                                  // A x [B ; B_lo]
-                    if (PASSES == 3) umma_tf32(d, ad + (A_PART >> 4), bd, idesc_n, 1u);  // A_lo x B
-                  }
-                  accum = 1u;
+                for (int mt = 0; mt < MT; ++mt) {
+                  const uint32_t d = d0 + mt * p.nb_max;
+                  const uint64_t ad = a_tap + (uint32_t)((mt * TH * HALO_W * ROW_BYTES + k * 32) >> 4);
+                  umma_tf32(d, ad, bd, idesc, accum);                                  // A x [B ; B_lo]
+                  if (PASSES == 3) umma_tf32(d, ad + (A_PART >> 4), bd, idesc_n, 1u);  // A_lo x B
                 }
+                accum = 1u;
               }
             }
             umma_commit(emptyB(sB));
@@ -553,38 +552,44 @@ static int num_sms() {
   return n;
 }
 
-// ring depths and B slab granularity that fit in shared memory; false if nothing fits
-static bool pick_rings(int mt, int passes, int ks, int NB, int* sa, int* sb, int* dys, size_t* smem) {
+// ring depths and B slot granularity that fit in shared memory; false if nothing fits
+static bool pick_rings(int mt, int passes, int ks, int NB, int* sa, int* sb, int* slab_taps, size_t* smem) {
   const int a_stage = a_part(mt, ks) * (passes == 3 ? 2 : 1);
   const int budget = SMEM_LIMIT - 1024 - 512;
-  // 1) whole-chunk B stages (one barrier round trip per chunk) if >= 2 of them fit beside >= 2 A stages
-  {
-    const int b_slab = ks * ks * NB * ROW_BYTES;
-    for (int b = 3; b >= 2; --b)
-      for (int a = 4; a >= 2; --a)
-        if (a * a_stage + b * b_slab <= budget && (a >= 3 || b == 2)) {
-          *sa = a; *sb = b; *dys = ks;
-          *smem = 1024 + (size_t)a * a_stage + (size_t)b * b_slab + 512;
-          return true;
-        }
-  }
+  const int tap = NB * ROW_BYTES;
+  const int taps = ks * ks;
+  auto done = [&](int a, int b, int st) {
+    *sa = a; *sb = b; *slab_taps = st;
+    *smem = 1024 + (size_t)a * a_stage + (size_t)b * st * tap + 512;
+    return true;
+  };
+  // 1) whole-chunk slots (one barrier round trip per chunk): >= 2 of them beside >= 2 A stages
+  for (int b = 3; b >= 2; --b)
+    for (int a = 4; a >= 2; --a)
+      if (a * a_stage + b * taps * tap <= budget && (a >= 3 || b == 2)) return done(a, b, taps);
   if (ks == 1) return false;
-  // 2) per-dy slabs
-  const int b_slab = 3 * NB * ROW_BYTES;
-  int best_a = 0;
-  for (int a = 4; a >= 1 && !best_a; --a)
-    if (a * a_stage + 3 * b_slab <= budget) best_a = a;
-  if (!best_a) return false;
-  int best_b = (budget - best_a * a_stage) / b_slab;
-  if (best_b > 9) best_b = 9;
-  if (best_a > 2 && best_b < 4) {
-    --best_a;
-    best_b = (budget - best_a * a_stage) / b_slab;
-    if (best_b > 9) best_b = 9;
-  }
-  *sa = best_a; *sb = best_b; *dys = 1;
-  *smem = 1024 + (size_t)best_a * a_stage + (size_t)best_b * b_slab + 512;
-  return true;
+  // 2) one dy row of taps per slot beside >= 2 A stages.  Measured (tools/gpu_rings.sh): double-buffered A
+  //    with only two row slots beats a single A stage with a whole chunk of B in flight, and per-tap
+  //    slots lose to both (every slot costs a barrier round trip).
+  for (int a = 4; a >= 2; --a)
+    if (a * a_stage + 2 * ks * tap <= budget) {
+      int b = (budget - a * a_stage) / (ks * tap);
+      if (b > 9) b = 9;
+      if (a > 2 && b < 4) {
+        --a;
+        b = (budget - a * a_stage) / (ks * tap);
+        if (b > 9) b = 9;
+      }
+      return done(a, b, ks);
+    }
+  // 3) single-tap slots: two A stages if at least 6 taps of B still fit, else one
+  for (int a = 2; a >= 1; --a)
+    if (a * a_stage + (a == 2 ? 6 : 3) * tap <= budget) {
+      int b = (budget - a * a_stage) / tap;
+      if (b > 18) b = 18;
+      return done(a, b, 1);
+    }
+  return false;
 }
 
 typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
@@ -619,13 +624,13 @@ extern "C" int hcf_conv_tc_supported(const hcf_conv_args* a) {
     if (a->seg[i].up_shift != 0 || a->seg[i].C < 1) return 0;
     if (a->seg[i].ld % 4 != 0 || !hcf::aligned16(a->seg[i].ptr)) return 0;
   }
-  if (a->cout < 1 || a->cout > 64) return 0;
+  if (a->cout < 1 || a->cout > 128) return 0;
   return 1;
 }
 
 // kin = number of (segment-padded) input channels, a multiple of 32
 extern "C" int64_t hcf_conv_tc_weight_bytes(int32_t kin, int32_t cout, int32_t ks, int32_t passes) {
-  if (kin % 32 != 0 || cout < 1 || cout > 64 || (ks != 1 && ks != 3) || (passes != 1 && passes != 3)) return 0;
+  if (kin % 32 != 0 || cout < 1 || cout > 128 || (ks != 1 && ks != 3) || (passes != 1 && passes != 3)) return 0;
   return (int64_t)(kin / 32) * ks * ks * hcf::tc::n_for(cout) * (passes == 3 ? 2 : 1) * 128;
 }
 
@@ -633,7 +638,7 @@ extern "C" int64_t hcf_conv_tc_weight_bytes(int32_t kin, int32_t cout, int32_t k
 extern "C" int hcf_conv_tc_pack_weights(const float* w, int32_t kin, int32_t cout, int32_t ks, int32_t passes,
                                         float* image) {
   using namespace hcf;
-  HCF_REQUIRE(w && image && kin % 32 == 0 && cout >= 1 && cout <= 64 && (ks == 1 || ks == 3) &&
+  HCF_REQUIRE(w && image && kin % 32 == 0 && cout >= 1 && cout <= 128 && (ks == 1 || ks == 3) &&
                   (passes == 1 || passes == 3), "tc_pack: bad args");
   const int N = tc::n_for(cout), KC = kin / 32, parts = passes == 3 ? 2 : 1, NB = N * parts;
   memset(image, 0, (size_t)hcf_conv_tc_weight_bytes(kin, cout, ks, passes));
@@ -704,10 +709,22 @@ extern "C" int hcf_conv_chain_create(const hcf_conv_args* args, const float* con
     const char* dbg = getenv("HCF_TC_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
   }
-  if (!tc::pick_rings(mt, passes, ks, p.nb_max, &p.sa, &p.sb, &p.dys, &pl->smem_bytes)) {
+  if (!tc::pick_rings(mt, passes, ks, p.nb_max, &p.sa, &p.sb, &p.slab_taps, &pl->smem_bytes)) {
     delete pl;
     set_error("tc_chain: tile does not fit in shared memory");
     return HCF_ENOTSUP;
+  }
+  if (const char* rings = getenv(n > 1 ? "HCF_TC_RINGS" : "HCF_TC_RINGS_SINGLE")) {   // tuning: "sa,sb,slab_taps"
+    int ra = 0, rb = 0, rs = 0;
+    if (sscanf(rings, "%d,%d,%d", &ra, &rb, &rs) == 3 && ra >= 1 && ra <= 4 && rb >= 2 && rb <= 18 &&
+        (rs == 1 || rs == ks || rs == ks * ks)) {
+      const size_t need = 1024 + (size_t)ra * tc::a_part(mt, ks) * (passes == 3 ? 2 : 1) +
+                          (size_t)rb * rs * p.nb_max * tc::ROW_BYTES + 512;
+      if (need <= (size_t)tc::SMEM_LIMIT) {
+        p.sa = ra; p.sb = rb; p.slab_taps = rs;
+        pl->smem_bytes = need;
+      }
+    }
   }
   p.tiles_x = ceil_div(a0->W, tc::TW); p.tiles_y = ceil_div(a0->H, tc::TH * mt);
   p.n_tiles = p.tiles_x * p.tiles_y * a0->B;

@@ -280,8 +280,13 @@ class Engine:
                 L.check(rc, "conv_chain_create")
         for op, a, flops, tag in pending:
             handle = C.c_void_p()
-            L.check(lib.hcf_conv_tc_plan_create(C.byref(a), self._tc_weights(op, passes).data_ptr(), passes,
-                                                C.byref(handle)), "tc_plan_create")
+            rc = lib.hcf_conv_tc_plan_create(C.byref(a), self._tc_weights(op, passes).data_ptr(), passes,
+                                             C.byref(handle))
+            if rc == -2:   # shape does not fit the tensor-core kernel's shared memory: CUDA-core kernel
+                self._add_call(lib.hcf_conv_fp32, C.byref(a), "conv_fp32", tag, flops, 1)
+                self.n_fp32_conv += 1
+                continue
+            L.check(rc, "tc_plan_create")
             self._tc_plans.append(handle)
             self._add_call(lib.hcf_conv_tc_run, handle, "conv_tc", tag, flops, 1)
             self.n_tc += 1

@@ -204,6 +204,11 @@ def _emit_encoder(plan, pre, cf_mod, segs, H, W, lvl):
 def _emit_subnet(plan, pre, aff, z, cond, H, W, lvl):
     """Coupling sub-net f(cat(z1, u)) -> h view (AffineCouplings.py:31,68; Basic.py:349-356,442-447)."""
     z1 = z.sub(0, aff.n_pass) if aff.mode == "affine" else z.sub(3, aff.n_pass)
+    if z1.off % 4 != 0 or z1.buf.C % 4 != 0:
+        # TMA needs 16-byte aligned views: stage the conditioning slice once per step
+        z1s = plan.view("z1s_l{}_c{}".format(lvl, z1.C), H, W, (z1.C + 3) // 4 * 4).sub(0, z1.C)
+        plan.ops.append(LayoutOp("copy", H, W, z1.C, z1, z1s))
+        z1 = z1s
     segs = [(z1, 0)] + ([(cond, 0)] if cond is not None else [])
     f = aff.f
     fp = pre + ".affine.f"

@@ -99,7 +99,7 @@ int hcf_conv_fp32(const hcf_conv_args* a, void* stream);
 
 /* tcgen05 tensor-core implementation: ks in {1,3}, up to three segments without upsampling
  * (16-byte aligned views, ld % 4 == 0, any channel count: the K axis is walked in 32-channel
- * chunks per segment and TMA zero-fills beyond a segment's last channel), cout <= 64.
+ * chunks per segment and TMA zero-fills beyond a segment's last channel), cout <= 128.
  * `wtc` is the UMMA-ready weight image produced by hcf_conv_tc_pack_weights from weights
  * whose input-channel axis is already padded per segment to multiples of 32 (kin);
  * passes = 1 (TF32) or 3 (3xTF32 split, ~fp32 accuracy).  A plan owns the TMA tensor maps

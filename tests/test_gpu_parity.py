@@ -263,6 +263,8 @@ TC_CASES = [
     ("fcn_conv2_1x1", 2, 11, 17, [(64, 0, 64, 0)], 64, 1, True, True, 1, False, False),
     ("conv_first_lr_c3", 2, 13, 9, [(3, 0, 24, 0)], 64, 3, True, False, 0, False, False),
     ("dense_3seg", 1, 10, 10, [(9, 0, 12, 0), (128, 0, 128, 0), (96, 0, 128, 0)], 32, 3, True, False, 2, False, False),
+    ("dense_conv5_cout90", 1, 18, 10, [(45, 0, 48, 0), (128, 0, 128, 0)], 90, 3, True, False, 0, False, False),
+    ("cout_128", 1, 16, 16, [(64, 0, 64, 0)], 128, 3, True, True, 1, False, False),
 ]
 # max-abs tolerance on outputs of magnitude ~4: one TF32 pass keeps 10 mantissa bits per operand
 # (measured 3e-3); the 3-pass split recovers them, what remains is the tensor core's truncating
