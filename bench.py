@@ -274,7 +274,7 @@ def run_ours(args):
     n, ms, fl = by_tag[top_tag]
     achieved = fl / (ms / 1e3) / 1e12
     # DRAM bytes per launch of that kernel from the committed ncu --set full capture (profiles/README.md)
-    ncu_traffic = {"tf32x3": 5.76e9, "tf32": 5.42e9}.get(args.precision) if "chain" in top_tag else None
+    ncu_traffic = {"tf32x3": 5.76e9, "tf32x3_all": 5.76e9, "tf32": 5.42e9}.get(args.precision) if "chain" in top_tag else None
     roofline = {
         "bound": "tensor", "kernel": "conv_tc_kernel " + top_tag, "achieved": achieved, "peak": peaks["bf16_tflops"],
         "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"], "traffic": ncu_traffic,
@@ -330,7 +330,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"fp32": "fp32", "tf32": "tf32", "tf32x3": "tf32x3"}[args.precision], "data": "synthetic",
+        "dtype": args.precision, "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": "dp{}".format(world),
                    "l2": "256 MiB flush between timed steps; per-step CUDA events",
                    "conv_kernels": {"tcgen05": eng.n_tc, "fp32": eng.n_fp32_conv, "chained_launches": eng.n_chains},
@@ -356,7 +356,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("HCFLOW_PRECISION", "tf32x3"),
-                    choices=["fp32", "tf32", "tf32x3"],
+                    choices=["fp32", "tf32", "tf32x3", "tf32x3_all"],
                     help="tf32x3 (default): tcgen05 3xTF32 split, fp32-level parity (2e-4); tf32: one TF32 pass "
                          "(stock PyTorch conv numerics on CUDA); fp32: CUDA-core kernels")
     ap.add_argument("--no-modes", action="store_true", help="skip the short runs of the other precision modes")
