@@ -75,8 +75,8 @@ SYMBOLS = {
     "hcf_conv_tc_weight_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "hcf_conv_tc_pack_weights": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "hcf_conv_tc_plan_create": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]),
-    "hcf_conv_chain_create": (C.c_int, [C.POINTER(ConvArgs), C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_void_p,
-                                        C.POINTER(C.c_void_p)]),
+    "hcf_conv_chain_create": (C.c_int, [C.POINTER(ConvArgs), C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32,
+                                        C.c_void_p, C.POINTER(C.c_void_p)]),
     "hcf_conv_tc_plan_layers": (C.c_int32, [C.c_void_p]),
     "hcf_conv_tc_run": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hcf_conv_tc_plan_destroy": (None, [C.c_void_p]),

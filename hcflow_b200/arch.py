@@ -39,8 +39,9 @@ class _HCFlowBase(nn.Module):
 
     # ---- engine management -------------------------------------------------------------
     def set_precision(self, precision):
-        """"fp32" (CUDA-core exact), "tf32" (tcgen05, 1 pass), "tf32x3" (tcgen05 3xTF32 split for the encoder /
-        prior / dense sub-nets, 1 pass for the FCN sub-nets) or "tf32x3_all" (3xTF32 everywhere)."""
+        """"fp32" (CUDA-core exact), "tf32" (tcgen05, 1 pass), "tf32x3" (tcgen05; 3xTF32 split for the convs that
+        write the encoder's residual stream, the prior and the dense sub-nets, 1 pass elsewhere -- see
+        Engine._passes_for) or "tf32x3_all" (3xTF32 everywhere)."""
         assert precision in ("fp32", "tf32", "tf32x3", "tf32x3_all")
         if precision != self.precision:
             self.precision = precision

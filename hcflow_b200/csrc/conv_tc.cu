@@ -66,7 +66,9 @@ struct LayerDesc {
   int cout;
   int act;
   int out_vec;
-  const float* wimg;  // [kchunks][ks dy][ks dx][NB][32] pre-swizzled; NB = N (1 pass) or 2N rows: raw then lo
+  int parts;          // 1: one TF32 pass (B rows = N);  2: 3xTF32 split (B rows = [raw N ; lo N], plus A_lo x B)
+  int slab_taps;      // taps of this layer per B ring slot: KS*KS, KS or 1 (largest that fits the slot)
+  const float* wimg;  // [kchunks][ks dy][ks dx][NB][32] pre-swizzled; NB = N * parts
   const float* bias;
   const float* scale;
   float* out; int out_ld;
@@ -83,7 +85,7 @@ struct Params {
   int n_items;        // n_layers * n_tiles
   int nb_max;         // max over layers of B rows per tap (N, or 2N in 3-pass mode)
   int sa, sb;         // ring depths
-  int slab_taps;      // taps per B ring slot: KS*KS (whole chunk), KS (one dy row) or 1
+  int slot_bytes;     // bytes of one B ring slot
   int debug;          // timing experiments only (HCF_TC_DEBUG, wrong results): 1 aligned A descriptors,
                       // 2 no MMAs, 4 no loads, 8 no epilogue stores, 16 launch only, 32 prologue only
   const LayerDesc* layers;
@@ -194,13 +196,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap maps0, const __grid_constant_
   constexpr int A_BYTES = a_bytes(MT, KS);
   constexpr int A_PART = a_part(MT, KS);
   constexpr int A_STAGE = A_PART * (PASSES == 3 ? 2 : 1);   // [raw | lo]
-  constexpr uint32_t PARTS = PASSES == 3 ? 2u : 1u;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   if (p.debug & 16) return;   // timing experiment: launch cost only
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t slot_bytes = (uint32_t)p.slab_taps * p.nb_max * ROW_BYTES;  // B ring slot (largest layer)
-  const int slabs = (KS * KS) / p.slab_taps;                                 // slabs per 32-channel chunk
+  const uint32_t slot_bytes = (uint32_t)p.slot_bytes;                        // B ring slot
   const uint32_t b_base = smem_base + p.sa * A_STAGE;
   const uint32_t bar_base = b_base + p.sb * slot_bytes;
   auto fullA = [&](int s) { return bar_base + 8u * s; };
@@ -269,8 +269,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap maps0, const __grid_constant_
         const int kchunks = __ldg(&L->kchunks);
         const int se0 = __ldg(&L->seg_end[0]), se1 = __ldg(&L->seg_end[1]);
         const int m0 = __ldg(&L->map_idx[0]), m1 = __ldg(&L->map_idx[1]), m2 = __ldg(&L->map_idx[2]);
-        const uint32_t tap_bytes = (uint32_t)__ldg(&L->N) * PARTS * ROW_BYTES;
-        const uint32_t b_slab = (uint32_t)p.slab_taps * tap_bytes;
+        const uint32_t tap_bytes = (uint32_t)(__ldg(&L->N) * __ldg(&L->parts)) * ROW_BYTES;
+        const int slab_taps = __ldg(&L->slab_taps);
+        const int slabs = (KS * KS) / slab_taps;
+        const uint32_t b_slab = (uint32_t)slab_taps * tap_bytes;
         const uint8_t* wimg = reinterpret_cast<const uint8_t*>(ldg_ptr(&L->wimg));
         if (chain && layer > 0) {
           // wait until layer-1 is complete on the 3x3 tile neighbourhood (halo + WAR safety)
@@ -333,7 +335,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap maps0, const __grid_constant_
       const LayerDesc* L = p.layers + layer;
       const int kchunks = __ldg(&L->kchunks);
       const uint32_t N = (uint32_t)__ldg(&L->N);
-      const uint32_t NB = N * PARTS;
+      const uint32_t parts = (uint32_t)__ldg(&L->parts);
+      const uint32_t NB = N * parts;
+      const int slab_taps = __ldg(&L->slab_taps);
+      const int slabs = (KS * KS) / slab_taps;
       const uint32_t nb = NB * (ROW_BYTES >> 4);      // one tap of B in 16-byte units
       const uint32_t idesc_n = (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((NB >> 3) << 17) | ((128u >> 4) << 24);
@@ -354,8 +359,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap maps0, const __grid_constant_
           tc_fence_after();
           if (elect_one()) {
             const uint64_t b0 = b_tmpl + ((b_base + sB * slot_bytes) >> 4);
-            for (int t = 0; t < ((p.debug & 2) ? 0 : p.slab_taps); ++t) {
-              const int tap = sl * p.slab_taps + t;
+            for (int t = 0; t < ((p.debug & 2) ? 0 : slab_taps); ++t) {
+              const int tap = sl * slab_taps + t;
               const int dy = tap / KS, dx = tap - dy * KS;
               uint64_t a_tap = a0 + (uint32_t)((dy * HALO_W + dx) * (ROW_BYTES >> 4));
               if (p.debug & 1) a_tap = make_desc(0, 8u * ROW_BYTES) + ((smem_base + sA * A_STAGE) >> 4);
@@ -368,7 +373,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap maps0, const __grid_constant_
                   const uint32_t d = d0 + mt * p.nb_max;
                   const uint64_t ad = a_tap + (uint32_t)((mt * TH * HALO_W * ROW_BYTES + k * 32) >> 4);
                   umma_tf32(d, ad, bd, idesc, accum);                                  // A x [B ; B_lo]
-                  if (PASSES == 3) umma_tf32(d, ad + (A_PART >> 4), bd, idesc_n, 1u);  // A_lo x B
+                  if (PASSES == 3 && parts == 2) umma_tf32(d, ad + (A_PART >> 4), bd, idesc_n, 1u);  // A_lo x B
                 }
                 accum = 1u;
               }
@@ -397,6 +402,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap maps0, const __grid_constant_
       const int b = tile / per_img, r = tile % per_img;
       const int y0 = (r / p.tiles_x) * TH * MT, x0 = (r % p.tiles_x) * TW;
       const int N = __ldg(&L->N), cout = __ldg(&L->cout), act = __ldg(&L->act), out_vec = __ldg(&L->out_vec);
+      const int parts = __ldg(&L->parts);
       const float* bias = ldg_ptr(&L->bias);
       const float* scale = ldg_ptr(&L->scale);
       float* out = ldg_ptr(&L->out);
@@ -419,7 +425,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap maps0, const __grid_constant_
           float v[16];
           const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (acc * MT + mt) * p.nb_max + (uint32_t)c0;
           tmem_ld16(tcol, v);
-          if (PASSES == 3) {
+          if (PASSES == 3 && parts == 2) {
             float lo[16];
             tmem_ld16(tcol + (uint32_t)N, lo);
 #pragma unroll
@@ -495,13 +501,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap maps0, const __grid_constant_
       const int et = threadIdx.x - 192;   // 0..127
       uint32_t a_it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int kchunks = __ldg(&(p.layers + item / p.n_tiles)->kchunks);
+        const LayerDesc* L = p.layers + item / p.n_tiles;
+        const int kchunks = __ldg(&L->kchunks);
+        const int n4 = __ldg(&L->parts) == 2 ? A_BYTES / 16 : 0;   // one-pass layers need no A_lo
         for (int kc = 0; kc < kchunks; ++kc, ++a_it) {
           const int sA = a_it % p.sa;
           mbar_wait(fullA(sA), (a_it / p.sa) & 1u);
           const float4* src = reinterpret_cast<const float4*>(gen_base + (size_t)sA * A_STAGE);
           float4* dst = reinterpret_cast<float4*>(gen_base + (size_t)sA * A_STAGE + A_PART);
-          for (int i = et; i < A_BYTES / 16; i += 128) {
+          for (int i = et; i < n4; i += 128) {
             float4 v = src[i];
             v.x -= __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
             v.y -= __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
@@ -666,14 +674,18 @@ extern "C" int hcf_conv_tc_pack_weights(const float* w, int32_t kin, int32_t cou
 // executed by one persistent launch.  Conv i may read anything convs < i wrote (dependencies are
 // tracked per 3x3 tile neighbourhood, which also covers write-after-read).  `done_flags`
 // (device, B*ceil(H/16)*ceil(W/8) int32) must be zeroed before every run; NULL is allowed for n == 1.
-extern "C" int hcf_conv_chain_create(const hcf_conv_args* args, const float* const* wtc, int32_t n, int32_t passes,
-                                     int32_t* done_flags, hcf_conv_tc_plan** out) {
+extern "C" int hcf_conv_chain_create(const hcf_conv_args* args, const float* const* wtc, const int32_t* layer_passes,
+                                     int32_t n, int32_t* done_flags, hcf_conv_tc_plan** out) {
   using namespace hcf;
   HCF_REQUIRE(out != nullptr, "tc_chain: null out");
   *out = nullptr;
-  HCF_REQUIRE(args && wtc && n >= 1, "tc_chain: bad args");
+  HCF_REQUIRE(args && wtc && layer_passes && n >= 1, "tc_chain: bad args");
   HCF_REQUIRE(n == 1 || done_flags != nullptr, "tc_chain: a chain needs the done-flag array");
-  HCF_REQUIRE(passes == 1 || passes == 3, "tc_chain: passes %d", passes);
+  int passes = 1;   // kernel variant: 3 as soon as one layer uses the 3xTF32 split
+  for (int i = 0; i < n; ++i) {
+    HCF_REQUIRE(layer_passes[i] == 1 || layer_passes[i] == 3, "tc_chain: conv %d: passes %d", i, layer_passes[i]);
+    if (layer_passes[i] == 3) passes = 3;
+  }
   const int ks = args[0].ks;
   for (int i = 0; i < n; ++i) {
     int rc = validate_conv_args(&args[i]);
@@ -691,9 +703,13 @@ extern "C" int hcf_conv_chain_create(const hcf_conv_args* args, const float* con
   tc::Params& p = pl->p;
   p.B = a0->B; p.H = a0->H; p.W = a0->W;
   const int sms = tc::num_sms();
-  int nmax = 0;
-  for (int i = 0; i < n; ++i) nmax = nmax > tc::n_for(args[i].cout) ? nmax : tc::n_for(args[i].cout);
-  p.nb_max = nmax * (passes == 3 ? 2 : 1);
+  int nmax = 0, nbmax = 0;
+  for (int i = 0; i < n; ++i) {
+    const int nn = tc::n_for(args[i].cout), nb = nn * (layer_passes[i] == 3 ? 2 : 1);
+    nmax = nmax > nn ? nmax : nn;
+    nbmax = nbmax > nb ? nbmax : nb;
+  }
+  p.nb_max = nbmax;
   // sub-tiles per work item: 2 halves the weight traffic per pixel but quantises worse on small images
   int mt = 1;
   const char* env = getenv("HCF_TC_MT");
@@ -709,7 +725,8 @@ extern "C" int hcf_conv_chain_create(const hcf_conv_args* args, const float* con
     const char* dbg = getenv("HCF_TC_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
   }
-  if (!tc::pick_rings(mt, passes, ks, p.nb_max, &p.sa, &p.sb, &p.slab_taps, &pl->smem_bytes)) {
+  int slot_taps = 0;
+  if (!tc::pick_rings(mt, passes, ks, p.nb_max, &p.sa, &p.sb, &slot_taps, &pl->smem_bytes)) {
     delete pl;
     set_error("tc_chain: tile does not fit in shared memory");
     return HCF_ENOTSUP;
@@ -721,11 +738,12 @@ extern "C" int hcf_conv_chain_create(const hcf_conv_args* args, const float* con
       const size_t need = 1024 + (size_t)ra * tc::a_part(mt, ks) * (passes == 3 ? 2 : 1) +
                           (size_t)rb * rs * p.nb_max * tc::ROW_BYTES + 512;
       if (need <= (size_t)tc::SMEM_LIMIT) {
-        p.sa = ra; p.sb = rb; p.slab_taps = rs;
+        p.sa = ra; p.sb = rb; slot_taps = rs;
         pl->smem_bytes = need;
       }
     }
   }
+  p.slot_bytes = slot_taps * p.nb_max * tc::ROW_BYTES;
   p.tiles_x = ceil_div(a0->W, tc::TW); p.tiles_y = ceil_div(a0->H, tc::TH * mt);
   p.n_tiles = p.tiles_x * p.tiles_y * a0->B;
   p.n_layers = n;
@@ -765,6 +783,11 @@ extern "C" int hcf_conv_chain_create(const hcf_conv_args* args, const float* con
     L.seg_end[a.nseg - 1] = 1 << 30;
     L.kchunks = kc;
     L.N = tc::n_for(a.cout);
+    L.parts = layer_passes[i] == 3 ? 2 : 1;
+    {   // largest tap count (whole chunk, one dy row, one tap) of this layer that fits a ring slot
+      const int tap = L.N * L.parts * tc::ROW_BYTES;
+      L.slab_taps = (ks * ks * tap <= p.slot_bytes) ? ks * ks : ((ks * tap <= p.slot_bytes) ? ks : 1);
+    }
     L.cout = a.cout;
     L.act = a.act;
     L.wimg = wtc[i]; L.bias = a.bias; L.scale = a.scale;
@@ -825,7 +848,7 @@ extern "C" int hcf_conv_chain_create(const hcf_conv_args* args, const float* con
 
 extern "C" int hcf_conv_tc_plan_create(const hcf_conv_args* a, const float* wtc, int32_t passes,
                                        hcf_conv_tc_plan** out) {
-  return hcf_conv_chain_create(a, &wtc, 1, passes, nullptr, out);
+  return hcf_conv_chain_create(a, &wtc, &passes, 1, nullptr, out);
 }
 
 extern "C" int32_t hcf_conv_tc_plan_layers(const hcf_conv_tc_plan* pl) { return pl ? pl->p.n_layers : 0; }

@@ -115,9 +115,10 @@ int hcf_conv_tc_plan_create(const hcf_conv_args* a, const float* wtc, int32_t pa
 /* A chain of n dependent convolutions on the same [B,H,W] grid and kernel size (e.g. the 211 convs
  * of one RRDB encoder level, ConditionalFlow.py:99-110) executed by ONE persistent launch: conv i
  * may read anything convs < i wrote; readiness is tracked per 3x3 tile neighbourhood through
- * `done_flags` (device int32[B*ceil(H/16)*ceil(W/8)], zeroed by the caller before every run). */
-int hcf_conv_chain_create(const hcf_conv_args* args, const float* const* wtc, int32_t n, int32_t passes,
-                          int32_t* done_flags, hcf_conv_tc_plan** out);
+ * `done_flags` (device int32[B*ceil(H/16)*ceil(W/8)], zeroed by the caller before every run).
+ * `layer_passes[i]` in {1,3} selects TF32 / 3xTF32 per conv; wtc[i] must be packed with the same value. */
+int hcf_conv_chain_create(const hcf_conv_args* args, const float* const* wtc, const int32_t* layer_passes,
+                          int32_t n, int32_t* done_flags, hcf_conv_tc_plan** out);
 int32_t hcf_conv_tc_plan_layers(const hcf_conv_tc_plan* p);
 int hcf_conv_tc_run(const hcf_conv_tc_plan* p, void* stream);
 void hcf_conv_tc_plan_destroy(hcf_conv_tc_plan* p);
