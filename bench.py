@@ -302,7 +302,7 @@ def run_ours(args):
     modes = {args.precision: {"value": value, "ms_per_step": t_ms / args.steps}}
     if world == 1 and not args.no_modes:
         net.use_graph = True
-        for prec in ("tf32x3", "tf32", "fp32"):
+        for prec in ("f16x3", "f16", "tf32x3", "tf32", "fp32"):
             if prec in modes:
                 continue
             net.set_precision(prec)
@@ -356,7 +356,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("HCFLOW_PRECISION", "tf32x3"),
-                    choices=["fp32", "tf32", "tf32x3", "tf32x3_all"],
+                    choices=["fp32", "tf32", "tf32x3", "tf32x3_all", "f16", "f16x3"],
                     help="tf32x3 (default): tcgen05 3xTF32 split, fp32-level parity (2e-4); tf32: one TF32 pass "
                          "(stock PyTorch conv numerics on CUDA); fp32: CUDA-core kernels")
     ap.add_argument("--no-modes", action="store_true", help="skip the short runs of the other precision modes")

@@ -64,6 +64,12 @@ class SqueezeArgs(C.Structure):
     ]
 
 
+class Shadow16(C.Structure):
+    _fields_ = [("f32", C.c_void_p), ("bytes", C.c_int64), ("hi", C.c_void_p), ("lo", C.c_void_p)]
+
+
+OUT_F32, OUT_HI, OUT_LO = 1, 2, 4
+
 # every symbol include/hcflow_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "hcf_abi_version": (C.c_int, []),
@@ -77,6 +83,13 @@ SYMBOLS = {
     "hcf_conv_tc_plan_create": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]),
     "hcf_conv_chain_create": (C.c_int, [C.POINTER(ConvArgs), C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32,
                                         C.c_void_p, C.POINTER(C.c_void_p)]),
+    "hcf_conv_tc16_supported": (C.c_int, [C.POINTER(ConvArgs)]),
+    "hcf_conv_tc16_weight_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "hcf_conv_tc16_pack_weights": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "hcf_conv_chain16_create": (C.c_int, [C.POINTER(ConvArgs), C.POINTER(C.c_void_p), C.POINTER(C.c_int32),
+                                          C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.POINTER(Shadow16), C.c_int32,
+                                          C.POINTER(C.c_void_p)]),
+    "hcf_split16": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hcf_conv_tc_plan_layers": (C.c_int32, [C.c_void_p]),
     "hcf_conv_tc_run": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hcf_conv_tc_plan_destroy": (None, [C.c_void_p]),

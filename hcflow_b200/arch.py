@@ -41,8 +41,10 @@ class _HCFlowBase(nn.Module):
     def set_precision(self, precision):
         """"fp32" (CUDA-core exact), "tf32" (tcgen05, 1 pass), "tf32x3" (tcgen05; 3xTF32 split for the convs that
         write the encoder's residual stream, the prior and the dense sub-nets, 1 pass elsewhere -- see
-        Engine._passes_for) or "tf32x3_all" (3xTF32 everywhere)."""
-        assert precision in ("fp32", "tf32", "tf32x3", "tf32x3_all")
+        Engine._passes_for) or "tf32x3_all" (3xTF32 everywhere).  "f16" / "f16x3" are "tf32" / "tf32x3" with the
+        chained encoder convs on FP16 operands (hi / lo planes, kind::f16: half the operand bytes per MAC; the split
+        layers of "f16x3" use hi + lo on both operands, ~fp32 accuracy; operand range |x| < 65504)."""
+        assert precision in ("fp32", "tf32", "tf32x3", "tf32x3_all", "f16", "f16x3")
         if precision != self.precision:
             self.precision = precision
             self._engines.clear()

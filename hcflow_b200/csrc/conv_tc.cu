@@ -31,6 +31,7 @@
 //               2N-row operand (columns [0,N) and [N,2N) of the accumulator) and A_lo x B into
 //               columns [0,N); the epilogue adds the two column groups.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -44,8 +45,12 @@ namespace tc {
 constexpr int TH = 16, TW = 8;               // sub-tile (UMMA M = 128)
 constexpr int KCH = 32;                      // channels per K chunk (= 128 B rows)
 constexpr int ROW_BYTES = KCH * 4;           // 128
+constexpr int KCH16 = 64;                    // fp16 kernels: channels per 128-byte row
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int NUM_SMS_FALLBACK = 148;
+constexpr int BAR_BYTES = 512;               // mbarriers + TMEM slot
+constexpr int STAGE_BYTES = 4 * 32 * 32 * 4;  // epilogue staging: 4 warps x 32 pixels x 32 channels fp32
+constexpr int TAIL_BYTES = BAR_BYTES + 1024 + STAGE_BYTES;   // + per-layer bias / scale + staging
 
 // ks = 3: (16*mt+2) x 10 halo tile; ks = 1: plain 16*mt x 8 tile
 __host__ __device__ constexpr int halo_w(int ks) { return TW + (ks - 1); }
@@ -53,13 +58,15 @@ __host__ __device__ constexpr int halo_rows(int mt, int ks) { return TH * mt + (
 __host__ __device__ constexpr int a_bytes(int mt, int ks) { return halo_rows(mt, ks) * halo_w(ks) * ROW_BYTES; }
 __host__ __device__ constexpr int a_part(int mt, int ks) { return (a_bytes(mt, ks) + 1023) / 1024 * 1024; }
 
-constexpr int MAX_MAPS = 8;
+constexpr int MAX_MAPS = 16;
+struct Maps { CUtensorMap m[MAX_MAPS]; };
 
 // One convolution of a chain.  Lives in global memory; every warp role reads the fields it needs
 // at the start of a work item.
 struct LayerDesc {
   int nseg;
-  int map_idx[3];     // tensor map of each segment
+  int map_idx[3];     // tensor map of each segment (fp16 kernels: the hi plane)
+  int map_lo[3];      // fp16 kernels, split layers: tensor map of the lo plane
   int seg_end[3];     // chunk index where segment i ends (prefix sums)
   int kchunks;        // total 32-channel chunks
   int N;              // UMMA N (multiple of 16, <= 128)
@@ -73,6 +80,8 @@ struct LayerDesc {
   const float* scale;
   float* out; int out_ld;
   float* out2; int out2_ld;
+  __half* out_hi; __half* out_lo;     // fp16 kernels: hi / lo planes shadowing out (same ld), may be null
+  __half* out2_hi; __half* out2_lo;
   const float* res1; int res1_ld; float alpha1;
   const float* res2; int res2_ld; float alpha2;
 };
@@ -87,9 +96,11 @@ struct Params {
   int sa, sb;         // ring depths
   int slot_bytes;     // bytes of one B ring slot
   int debug;          // timing experiments only (HCF_TC_DEBUG, wrong results): 1 aligned A descriptors,
-                      // 2 no MMAs, 4 no loads, 8 no epilogue stores, 16 launch only, 32 prologue only
+                      // 2 no MMAs, 4 no loads, 8 no epilogue stores, 16 launch only, 32 prologue only,
+                      // 64 no dependency waits
   const LayerDesc* layers;
   int* done;          // chain mode: per-tile count of completed layers (zeroed before the launch)
+  long long* prof;    // HCF_TC_PROF=1: cycles per role / wait class summed over CTAs (see PROF_* below)
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -135,6 +146,14 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -172,30 +191,74 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// fp16 operand format: a = hi + lo / 2048 with hi = fp16(a), lo = fp16((a - hi) * 2048) (the scaling keeps the
+// residual out of the fp16 subnormal range); hi alone carries 11 significant bits (round-to-nearest), hi + lo 22.
+__device__ __forceinline__ uint2 split_hi(const float4 o) {
+  const __half2 a = __floats2half2_rn(o.x, o.y), b = __floats2half2_rn(o.z, o.w);
+  return make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+}
+__device__ __forceinline__ uint2 split_lo(const float4 o, const uint2 hi) {
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hi.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&hi.y));
+  const __half2 la = __floats2half2_rn((o.x - a.x) * 2048.0f, (o.y - a.y) * 2048.0f);
+  const __half2 lb = __floats2half2_rn((o.z - b.x) * 2048.0f, (o.w - b.y) * 2048.0f);
+  return make_uint2(*reinterpret_cast<const uint32_t*>(&la), *reinterpret_cast<const uint32_t*>(&lb));
+}
+struct Out16 { __half* hi; __half* lo; __half* hi2; __half* lo2; };
+
 // ------------------------------------------------------------------ kernel
+// profile slots (HCF_TC_PROF=1): cycles summed over CTAs, printed by hcf_conv_tc_plan_destroy
+enum { PROF_P_TOTAL = 0, PROF_P_DEPS, PROF_P_EMPTYA, PROF_P_EMPTYB, PROF_M_TOTAL, PROF_M_TMEM, PROF_M_FULLA, PROF_M_FULLB,
+       PROF_M_CONVA, PROF_E_TOTAL, PROF_E_TMEMFULL, PROF_E_BODY, PROF_E_PUBLISH, PROF_E_LAYER, PROF_E_ROW, PROF_E_COAL, PROF_LAUNCHES, PROF_N };
+#define HCF_T(var) const long long var = prof_on ? clock64() : 0ll
+#define HCF_ACC(slot, a, b) do { if (prof_on) pacc[slot] += (b) - (a); } while (0)
 template <typename T>
 __device__ __forceinline__ T* ldg_ptr(T* const* p) {
   return reinterpret_cast<T*>(__ldg(reinterpret_cast<const unsigned long long*>(p)));
 }
 
-__device__ __forceinline__ int ld_acquire(const int* p) {
+// Dependency counters are polled with RELAXED loads (nine in flight at once) and ordered by ONE
+// gpu-scope fence after the poll succeeds: nine ld.acquire in a row serialise into nine L2 round
+// trips (~5k cycles per work item, measured), which is what used to bound the chained kernel.
+__device__ __forceinline__ int ld_relaxed(const int* p) {
   int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void fence_acquire_gpu() { asm volatile("fence.acquire.gpu;" ::: "memory"); }
+__device__ __forceinline__ void red_release_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
-template <int MT, int PASSES, int KS>
-__global__ void __launch_bounds__(PASSES == 3 ? 320 : 192, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap maps0, const __grid_constant__ CUtensorMap maps1,
-               const __grid_constant__ CUtensorMap maps2, const __grid_constant__ CUtensorMap maps3,
-               const __grid_constant__ CUtensorMap maps4, const __grid_constant__ CUtensorMap maps5,
-               const __grid_constant__ CUtensorMap maps6, const __grid_constant__ CUtensorMap maps7,
-               const Params p) {
+// completed-layer counters of the 3x3 tile neighbourhood of (b, ty, tx); missing neighbours read as "done"
+struct Deps { int v[9]; };
+__device__ __forceinline__ void load_deps(Deps& d, const int* done, int base, int ty, int tx, int tiles_y, int tiles_x) {
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int yy = ty + dy, xx = tx + dx;
+      const bool in = yy >= 0 && yy < tiles_y && xx >= 0 && xx < tiles_x;
+      d.v[(dy + 1) * 3 + dx + 1] = in ? ld_relaxed(done + base + yy * tiles_x + xx) : 0x7fffffff;
+    }
+}
+__device__ __forceinline__ bool deps_ready(const Deps& d, int layer) {
+  int m = d.v[0];
+#pragma unroll
+  for (int i = 1; i < 9; ++i) m = min(m, d.v[i]);
+  return m >= layer;
+}
+
+// F16: operands are fp16 (hi / lo planes, 64 channels per 128-byte row, kind::f16); otherwise fp32 words read as TF32.
+template <int MT, int PASSES, int KS, bool F16>
+__global__ void __launch_bounds__((PASSES == 3 && !F16) ? 320 : 192, 1)
+conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
   constexpr int HALO = KS / 2;
   constexpr int HALO_W = halo_w(KS);
   constexpr int A_BYTES = a_bytes(MT, KS);
   constexpr int A_PART = a_part(MT, KS);
-  constexpr int A_STAGE = A_PART * (PASSES == 3 ? 2 : 1);   // [raw | lo]
+  constexpr int A_STAGE = A_PART * (PASSES == 3 ? 2 : 1);   // [raw | lo]  (fp16: [hi | lo], both loaded by TMA)
+  constexpr int KCHX = F16 ? KCH16 : KCH;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   if (p.debug & 16) return;   // timing experiment: launch cost only
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -212,12 +275,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap maps0, const __grid_constant_
   auto tmem_full = [&](int a) { return tbar + 8u * a; };
   auto tmem_empty = [&](int a) { return tbar + 16u + 8u * a; };
   const uint32_t tmem_slot = tbar + 32u;
-  auto map_ptr = [&](int i) -> const CUtensorMap* {
-    switch (i) {
-      case 0: return &maps0; case 1: return &maps1; case 2: return &maps2; case 3: return &maps3;
-      case 4: return &maps4; case 5: return &maps5; case 6: return &maps6; default: return &maps7;
-    }
-  };
+  auto map_ptr = [&](int i) -> const CUtensorMap* { return &maps.m[i]; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t need_cols = 2u * MT * p.nb_max;
@@ -225,7 +283,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap maps0, const __grid_constant_
       need_cols <= 32 ? 32u : (need_cols <= 64 ? 64u : (need_cols <= 128 ? 128u : (need_cols <= 256 ? 256u : 512u)));
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.m[0]) : "memory");
     for (int s = 0; s < p.sa; ++s) {
       mbar_init(fullA(s), 1);
       mbar_init(emptyA(s), 1);
@@ -255,58 +313,92 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap maps0, const __grid_constant_
   const int per_img = p.tiles_x * p.tiles_y;
   const int n_items = (p.debug & 32) ? 0 : p.n_items;   // timing experiment: prologue + teardown only
   const bool chain = p.done != nullptr;
+  const bool prof_on = p.prof != nullptr;
+  long long pacc[PROF_N];
+#pragma unroll
+  for (int i = 0; i < PROF_N; ++i) pacc[i] = 0;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t a_it = 0, b_it = 0;
+      // per-layer fields stay in registers; a CTA sees the same layer for ~n_tiles/gridDim.x items in a row
+      int cur_layer = -1, kchunks = 0, se0 = 0, se1 = 0, m0 = 0, m1 = 0, m2 = 0, slab_taps = 1, slabs = 1;
+      int l0 = 0, l1 = 0, l2 = 0, lparts = 1;
+      uint32_t tap_bytes = 0, b_slab = 0;
+      const uint8_t* wimg = nullptr;
+      Deps deps;
+      HCF_T(tp0);
+      if (chain && (int)blockIdx.x < n_items) {   // counters of the first item (prefetched one item ahead below)
+        const int tile = blockIdx.x % p.n_tiles;
+        const int b = tile / per_img, r = tile % per_img;
+        load_deps(deps, p.done, b * per_img, r / p.tiles_x, r % p.tiles_x, p.tiles_y, p.tiles_x);
+      }
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int layer = item / p.n_tiles, tile = item - layer * p.n_tiles;
-        const LayerDesc* L = p.layers + layer;
         const int b = tile / per_img, r = tile % per_img;
         const int ty = r / p.tiles_x, tx = r % p.tiles_x;
         const int y0 = ty * TH * MT, x0 = tx * TW;
-        const int kchunks = __ldg(&L->kchunks);
-        const int se0 = __ldg(&L->seg_end[0]), se1 = __ldg(&L->seg_end[1]);
-        const int m0 = __ldg(&L->map_idx[0]), m1 = __ldg(&L->map_idx[1]), m2 = __ldg(&L->map_idx[2]);
-        const uint32_t tap_bytes = (uint32_t)(__ldg(&L->N) * __ldg(&L->parts)) * ROW_BYTES;
-        const int slab_taps = __ldg(&L->slab_taps);
-        const int slabs = (KS * KS) / slab_taps;
-        const uint32_t b_slab = (uint32_t)slab_taps * tap_bytes;
-        const uint8_t* wimg = reinterpret_cast<const uint8_t*>(ldg_ptr(&L->wimg));
-        if (chain && layer > 0) {
-          // wait until layer-1 is complete on the 3x3 tile neighbourhood (halo + WAR safety)
-          const int base = b * per_img;
-          for (;;) {
-            int ok = 1;
-#pragma unroll
-            for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-              for (int dx = -1; dx <= 1; ++dx) {
-                const int yy = ty + dy, xx = tx + dx;
-                if (yy >= 0 && yy < p.tiles_y && xx >= 0 && xx < p.tiles_x)
-                  ok &= (ld_acquire(p.done + base + yy * p.tiles_x + xx) >= layer) ? 1 : 0;
-              }
-            if (ok) break;
-            __nanosleep(64);
+        if (layer != cur_layer) {
+          cur_layer = layer;
+          const LayerDesc* L = p.layers + layer;
+          kchunks = __ldg(&L->kchunks);
+          se0 = __ldg(&L->seg_end[0]); se1 = __ldg(&L->seg_end[1]);
+          m0 = __ldg(&L->map_idx[0]); m1 = __ldg(&L->map_idx[1]); m2 = __ldg(&L->map_idx[2]);
+          l0 = __ldg(&L->map_lo[0]); l1 = __ldg(&L->map_lo[1]); l2 = __ldg(&L->map_lo[2]);
+          lparts = __ldg(&L->parts);
+          tap_bytes = (uint32_t)(__ldg(&L->N) * __ldg(&L->parts)) * ROW_BYTES;
+          slab_taps = __ldg(&L->slab_taps);
+          slabs = (KS * KS) / slab_taps;
+          b_slab = (uint32_t)slab_taps * tap_bytes;
+          wimg = reinterpret_cast<const uint8_t*>(ldg_ptr(&L->wimg));
+        }
+        if (chain) {
+          if (layer > 0 && !(p.debug & 64)) {
+            // wait until layer-1 is complete on the 3x3 tile neighbourhood (halo + WAR safety)
+            HCF_T(td0);
+            while (!deps_ready(deps, layer)) {
+              __nanosleep(32);
+              load_deps(deps, p.done, b * per_img, ty, tx, p.tiles_y, p.tiles_x);
+            }
+            fence_acquire_gpu();                                      // acquire side of the epilogue's release
+            asm volatile("fence.proxy.async.global;" ::: "memory");   // order the TMA (async proxy) reads after it
+            HCF_T(td1);
+            HCF_ACC(PROF_P_DEPS, td0, td1);
           }
-          asm volatile("fence.proxy.async;" ::: "memory");   // order the TMA reads after the acquire
+          const int nitem = item + gridDim.x;                  // counters of the next item: in flight during this item's loads
+          if (nitem < n_items) {
+            const int nt = nitem % p.n_tiles;
+            const int nb = nt / per_img, nr = nt % per_img;
+            load_deps(deps, p.done, nb * per_img, nr / p.tiles_x, nr % p.tiles_x, p.tiles_y, p.tiles_x);
+          }
         }
         for (int kc = 0; kc < kchunks; ++kc) {
           const int sA = a_it % p.sa;
+          HCF_T(ta0);
           mbar_wait(emptyA(sA), ((a_it / p.sa) & 1u) ^ 1u);
+          HCF_T(ta1);
+          HCF_ACC(PROF_P_EMPTYA, ta0, ta1);
           if (p.debug & 4) {
             mbar_arrive(fullA(sA));
           } else {
-            mbar_expect_tx(fullA(sA), A_BYTES);
+            const bool two = F16 && PASSES == 3 && lparts == 2;   // split layer of an fp16 chain: hi and lo planes
+            mbar_expect_tx(fullA(sA), two ? 2 * A_BYTES : A_BYTES);
             const int mi = kc < se0 ? m0 : (kc < se1 ? m1 : m2);
             const int kl = kc < se0 ? kc : (kc < se1 ? kc - se0 : kc - se1);
-            tma_load_4d(smem_base + sA * A_STAGE, map_ptr(mi), fullA(sA), kl * KCH, x0 - HALO, y0 - HALO, b);
+            tma_load_4d(smem_base + sA * A_STAGE, map_ptr(mi), fullA(sA), kl * KCHX, x0 - HALO, y0 - HALO, b);
+            if (two) {
+              const int li = kc < se0 ? l0 : (kc < se1 ? l1 : l2);
+              tma_load_4d(smem_base + sA * A_STAGE + A_PART, map_ptr(li), fullA(sA), kl * KCHX, x0 - HALO, y0 - HALO, b);
+            }
           }
           ++a_it;
           for (int sl = 0; sl < slabs; ++sl) {
             const int sB = b_it % p.sb;
+            HCF_T(tb0);
             mbar_wait(emptyB(sB), ((b_it / p.sb) & 1u) ^ 1u);
+            HCF_T(tb1);
+            HCF_ACC(PROF_P_EMPTYB, tb0, tb1);
             if (p.debug & 4) {
               mbar_arrive(fullB(sB));
             } else {
@@ -318,6 +410,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap maps0, const __grid_constant_
           }
         }
       }
+      HCF_T(tp1);
+      HCF_ACC(PROF_P_TOTAL, tp0, tp1);
+      if (prof_on)
+        for (int i = PROF_P_TOTAL; i <= PROF_P_EMPTYB; ++i) atomicAdd((unsigned long long*)p.prof + i, (unsigned long long)pacc[i]);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -330,33 +426,52 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap maps0, const __grid_constant_
     const uint64_t a_tmpl = make_desc(0, HALO_W * ROW_BYTES);
     const uint64_t b_tmpl = make_desc(0, 8u * ROW_BYTES);
     uint32_t a_it = 0, b_it = 0, t_it = 0;
+    int cur_layer = -1, kchunks = 0, slab_taps = 1, slabs = 1;
+    uint32_t parts = 1, nb = 0, idesc_n = 0, idesc = 0, n_cols = 0;
+    HCF_T(tm0);
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++t_it) {
       const int layer = item / p.n_tiles;
-      const LayerDesc* L = p.layers + layer;
-      const int kchunks = __ldg(&L->kchunks);
-      const uint32_t N = (uint32_t)__ldg(&L->N);
-      const uint32_t parts = (uint32_t)__ldg(&L->parts);
-      const uint32_t NB = N * parts;
-      const int slab_taps = __ldg(&L->slab_taps);
-      const int slabs = (KS * KS) / slab_taps;
-      const uint32_t nb = NB * (ROW_BYTES >> 4);      // one tap of B in 16-byte units
-      const uint32_t idesc_n = (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((NB >> 3) << 17) | ((128u >> 4) << 24);
+      if (layer != cur_layer) {
+        cur_layer = layer;
+        const LayerDesc* L = p.layers + layer;
+        kchunks = __ldg(&L->kchunks);
+        const uint32_t N = (uint32_t)__ldg(&L->N);
+        parts = (uint32_t)__ldg(&L->parts);
+        const uint32_t NB = N * parts;
+        slab_taps = __ldg(&L->slab_taps);
+        slabs = (KS * KS) / slab_taps;
+        nb = NB * (ROW_BYTES >> 4);      // one tap of B in 16-byte units
+        const uint32_t fmt = F16 ? 0u : 2u;   // A / B format: F16 = 0, TF32 = 2; D = F32
+        idesc_n = (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((128u >> 4) << 24);
+        idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((NB >> 3) << 17) | ((128u >> 4) << 24);
+        n_cols = N;
+      }
       const uint32_t acc = t_it & 1u;
+      HCF_T(tt0);
       mbar_wait(tmem_empty(acc), ((t_it >> 1) & 1u) ^ 1u);   // all lanes poll: measured faster than lane 0 + syncwarp
       tc_fence_after();
+      HCF_T(tt1);
+      HCF_ACC(PROF_M_TMEM, tt0, tt1);
       const uint32_t d0 = tmem_base + acc * MT * p.nb_max;
       uint32_t accum = 0u;   // first MMA of the item overwrites the accumulator
       for (int kc = 0; kc < kchunks; ++kc) {
         const int sA = a_it % p.sa;
         const uint32_t phA = (a_it / p.sa) & 1u;
+        HCF_T(tfa0);
         mbar_wait(fullA(sA), phA);
-        if (PASSES == 3) mbar_wait(convA(sA), phA);
+        HCF_T(tfa1);
+        if (PASSES == 3 && !F16) mbar_wait(convA(sA), phA);
+        HCF_T(tfa2);
+        HCF_ACC(PROF_M_FULLA, tfa0, tfa1);
+        HCF_ACC(PROF_M_CONVA, tfa1, tfa2);
         const uint64_t a0 = a_tmpl + ((smem_base + sA * A_STAGE) >> 4);
         for (int sl = 0; sl < slabs; ++sl) {
           const int sB = b_it % p.sb;
+          HCF_T(tfb0);
           mbar_wait(fullB(sB), (b_it / p.sb) & 1u);
           tc_fence_after();
+          HCF_T(tfb1);
+          HCF_ACC(PROF_M_FULLB, tfb0, tfb1);
           if (elect_one()) {
             const uint64_t b0 = b_tmpl + ((b_base + sB * slot_bytes) >> 4);
             for (int t = 0; t < ((p.debug & 2) ? 0 : slab_taps); ++t) {
@@ -372,8 +487,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap maps0, const __grid_constant_
                 for (int mt = 0; mt < MT; ++mt) {
                   const uint32_t d = d0 + mt * p.nb_max;
                   const uint64_t ad = a_tap + (uint32_t)((mt * TH * HALO_W * ROW_BYTES + k * 32) >> 4);
-                  umma_tf32(d, ad, bd, idesc, accum);                                  // A x [B ; B_lo]
-                  if (PASSES == 3 && parts == 2) umma_tf32(d, ad + (A_PART >> 4), bd, idesc_n, 1u);  // A_lo x B
+                  if (F16) {
+                    // cols [0,N) += A_hi x B_hi, cols [N,2N) += A_hi x B_lo' + A_lo' x B_hi (lo' = lo * 2048)
+                    umma_f16(d, ad, bd, idesc, accum);
+                    if (PASSES == 3 && parts == 2) umma_f16(d + n_cols, ad + (A_PART >> 4), bd, idesc_n, 1u);
+                  } else {
+                    umma_tf32(d, ad, bd, idesc, accum);                                  // A x [B ; B_lo]
+                    if (PASSES == 3 && parts == 2) umma_tf32(d, ad + (A_PART >> 4), bd, idesc_n, 1u);  // A_lo x B
+                  }
                 }
                 accum = 1u;
               }
@@ -391,113 +512,201 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap maps0, const __grid_constant_
         ++a_it;
       }
     }
+    HCF_T(tm1);
+    HCF_ACC(PROF_M_TOTAL, tm0, tm1);
+    if (prof_on && lane == 0)
+      for (int i = PROF_M_TOTAL; i <= PROF_M_CONVA; ++i) atomicAdd((unsigned long long*)p.prof + i, (unsigned long long)pacc[i]);
   } else if (warp < 6) {
     // ===================== epilogue =====================
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int m = q * 32 + lane;                  // accumulator row = pixel within the sub-tile
+    const int et = threadIdx.x - 64;              // 0..127
+    float* s_bias = reinterpret_cast<float*>(gen_base + (bar_base + BAR_BYTES - smem_base));   // [128] bias | [128] scale
+    float* s_scale = s_bias + 128;
+    float4* stage = reinterpret_cast<float4*>(s_bias + 256) + q * 256;   // this warp's [32 pixels][8 x 16 B]
+    Out16 o16 = {nullptr, nullptr, nullptr, nullptr};
     uint32_t t_it = 0;
+    // per-layer fields stay in registers, bias / scale in shared memory (every thread needs all N of them)
+    int cur_layer = -1, N = 0, cout = 0, act = 0, out_vec = 0, parts = 1;
+    int out_ld = 0, out2_ld = 0, res1_ld = 0, res2_ld = 0;
+    bool has_bias = false, has_scale = false;
+    float* out = nullptr; float* out2 = nullptr;
+    const float* res1 = nullptr; const float* res2 = nullptr;
+    float alpha1 = 0.f, alpha2 = 0.f;
+    HCF_T(te0);
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++t_it) {
       const int layer = item / p.n_tiles, tile = item - layer * p.n_tiles;
-      const LayerDesc* L = p.layers + layer;
       const int b = tile / per_img, r = tile % per_img;
       const int y0 = (r / p.tiles_x) * TH * MT, x0 = (r % p.tiles_x) * TW;
-      const int N = __ldg(&L->N), cout = __ldg(&L->cout), act = __ldg(&L->act), out_vec = __ldg(&L->out_vec);
-      const int parts = __ldg(&L->parts);
-      const float* bias = ldg_ptr(&L->bias);
-      const float* scale = ldg_ptr(&L->scale);
-      float* out = ldg_ptr(&L->out);
-      float* out2 = ldg_ptr(&L->out2);
-      const float* res1 = ldg_ptr(&L->res1);
-      const float* res2 = ldg_ptr(&L->res2);
-      const int out_ld = __ldg(&L->out_ld), out2_ld = __ldg(&L->out2_ld);
-      const int res1_ld = __ldg(&L->res1_ld), res2_ld = __ldg(&L->res2_ld);
-      const float alpha1 = __ldg(&L->alpha1), alpha2 = __ldg(&L->alpha2);
+      HCF_T(tl0);
+      if (layer != cur_layer) {
+        cur_layer = layer;
+        const LayerDesc* L = p.layers + layer;
+        N = __ldg(&L->N); cout = __ldg(&L->cout); act = __ldg(&L->act); out_vec = __ldg(&L->out_vec);
+        parts = __ldg(&L->parts);
+        const float* bias = ldg_ptr(&L->bias);
+        const float* scale = ldg_ptr(&L->scale);
+        has_bias = bias != nullptr; has_scale = scale != nullptr;
+        out = ldg_ptr(&L->out); out2 = ldg_ptr(&L->out2);
+        if (F16) {
+          o16.hi = ldg_ptr(&L->out_hi); o16.lo = ldg_ptr(&L->out_lo);
+          o16.hi2 = ldg_ptr(&L->out2_hi); o16.lo2 = ldg_ptr(&L->out2_lo);
+        }
+        res1 = ldg_ptr(&L->res1); res2 = ldg_ptr(&L->res2);
+        out_ld = __ldg(&L->out_ld); out2_ld = __ldg(&L->out2_ld);
+        res1_ld = __ldg(&L->res1_ld); res2_ld = __ldg(&L->res2_ld);
+        alpha1 = __ldg(&L->alpha1); alpha2 = __ldg(&L->alpha2);
+        asm volatile("bar.sync 1, 128;" ::: "memory");      // everyone is done with the previous layer's bias / scale
+        if (et < N) {                                       // bias / scale are padded to >= N entries
+          s_bias[et] = has_bias ? __ldg(bias + et) : 0.f;
+          s_scale[et] = has_scale ? __ldg(scale + et) : 1.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
       const uint32_t acc = t_it & 1u;
+      HCF_T(tl1);
       mbar_wait(tmem_full(acc), (t_it >> 1) & 1u);
       tc_fence_after();
+      HCF_T(tl2);
+      HCF_ACC(PROF_E_LAYER, tl0, tl1);
+      HCF_ACC(PROF_E_TMEMFULL, tl1, tl2);
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
-        const int gy = y0 + mt * TH + m / TW, gx = x0 + m % TW;
-        const bool inb = (gy < p.H) && (gx < p.W);
-        const size_t pix = ((size_t)b * p.H + (inb ? gy : 0)) * p.W + (inb ? gx : 0);
 #pragma unroll 1
-        for (int c0 = 0; c0 < N; c0 += 16) {
-          float v[16];
-          const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (acc * MT + mt) * p.nb_max + (uint32_t)c0;
-          tmem_ld16(tcol, v);
-          if (PASSES == 3 && parts == 2) {
-            float lo[16];
-            tmem_ld16(tcol + (uint32_t)N, lo);
+        for (int c0 = 0; c0 < N; c0 += 32) {
+          const int gw = min(32, N - c0);          // columns of this group (16 or 32)
+          HCF_T(tr0);
+          // ---- row domain (thread = pixel): TMEM -> bias / scale / activation -> staging
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] += lo[j];
-          }
-          if (!inb || c0 >= cout || (p.debug & 8)) continue;
-          if (bias) {   // bias / scale are padded to >= N entries and 16-byte aligned
+          for (int h = 0; h < 2; ++h) {
+            if (h * 16 < gw) {
+              float v[16];
+              const int cc = c0 + h * 16;
+              const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (acc * MT + mt) * p.nb_max + (uint32_t)cc;
+              tmem_ld16(tcol, v);
+              if (PASSES == 3 && parts == 2) {
+                float lo[16];
+                tmem_ld16(tcol + (uint32_t)N, lo);
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const float4 t4 = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));
-              v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
-            }
-          }
-          if (scale) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const float4 t4 = __ldg(reinterpret_cast<const float4*>(scale + c0 + j));
-              v[j] *= t4.x; v[j + 1] *= t4.y; v[j + 2] *= t4.z; v[j + 3] *= t4.w;
-            }
-          }
-          if (act == HCF_ACT_RELU) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-          } else if (act == HCF_ACT_LRELU) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
-          }
-          // residuals may have been written by another SM earlier in this launch: L2-coherent loads
-          if (out_vec && c0 + 15 < cout) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              if (res1) {
-                const float4 rr = __ldcg(reinterpret_cast<const float4*>(res1 + pix * res1_ld + c0 + j));
-                o.x = o.x * alpha1 + rr.x; o.y = o.y * alpha1 + rr.y;
-                o.z = o.z * alpha1 + rr.z; o.w = o.w * alpha1 + rr.w;
+                for (int j = 0; j < 16; ++j) v[j] = F16 ? fmaf(lo[j], 1.0f / 2048.0f, v[j]) : v[j] + lo[j];
               }
-              if (res2) {
-                const float4 rr = __ldcg(reinterpret_cast<const float4*>(res2 + pix * res2_ld + c0 + j));
-                o.x = o.x * alpha2 + rr.x; o.y = o.y * alpha2 + rr.y;
-                o.z = o.z * alpha2 + rr.z; o.w = o.w * alpha2 + rr.w;
-              }
-              *reinterpret_cast<float4*>(out + pix * out_ld + c0 + j) = o;
-              if (out2) *reinterpret_cast<float4*>(out2 + pix * out2_ld + c0 + j) = o;
-            }
-          } else {
+              if (has_bias) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int c = c0 + j;
-              if (c < cout) {
-                float t = v[j];
-                if (res1) t = t * alpha1 + __ldcg(res1 + pix * res1_ld + c);
-                if (res2) t = t * alpha2 + __ldcg(res2 + pix * res2_ld + c);
-                out[pix * out_ld + c] = t;
-                if (out2) out2[pix * out2_ld + c] = t;
+                for (int j = 0; j < 16; j += 4) {
+                  const float4 t4 = *reinterpret_cast<const float4*>(s_bias + cc + j);
+                  v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
+                }
+              }
+              if (has_scale) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                  const float4 t4 = *reinterpret_cast<const float4*>(s_scale + cc + j);
+                  v[j] *= t4.x; v[j + 1] *= t4.y; v[j + 2] *= t4.z; v[j + 3] *= t4.w;
+                }
+              }
+              if (act == HCF_ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+              } else if (act == HCF_ACT_LRELU) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j)   // 16-byte chunk index XOR (pixel & 7): conflict-free both ways
+                stage[lane * 8 + ((h * 4 + j) ^ (lane & 7))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+          }
+          __syncwarp();
+          HCF_T(tr1);
+          HCF_ACC(PROF_E_ROW, tr0, tr1);
+          // ---- coalesced domain (8 lanes = the 32 channels of one pixel, 4 pixels per instruction):
+          //      residuals -> full-line global stores (fp32 and / or fp16 hi / lo planes)
+          if (!(p.debug & 8)) {
+            const int cidx = lane & 7;
+            const int ch = c0 + cidx * 4;
+#pragma unroll 4
+            for (int it = 0; it < 8; ++it) {
+              const int pl = it * 4 + (lane >> 3);
+              const int mm = q * 32 + pl;
+              const int gy = y0 + mt * TH + mm / TW, gx = x0 + mm % TW;
+              if (gy < p.H && gx < p.W && ch < cout && cidx * 4 < gw) {
+                const size_t pix = ((size_t)b * p.H + gy) * p.W + gx;
+                float4 o = stage[pl * 8 + (cidx ^ (pl & 7))];
+                if (out_vec && ch + 3 < cout) {
+                  // residuals may have been written by another SM earlier in this launch: L2-coherent loads
+                  if (res1) {
+                    const float4 rr = __ldcg(reinterpret_cast<const float4*>(res1 + pix * res1_ld + ch));
+                    o.x = o.x * alpha1 + rr.x; o.y = o.y * alpha1 + rr.y; o.z = o.z * alpha1 + rr.z; o.w = o.w * alpha1 + rr.w;
+                  }
+                  if (res2) {
+                    const float4 rr = __ldcg(reinterpret_cast<const float4*>(res2 + pix * res2_ld + ch));
+                    o.x = o.x * alpha2 + rr.x; o.y = o.y * alpha2 + rr.y; o.z = o.z * alpha2 + rr.z; o.w = o.w * alpha2 + rr.w;
+                  }
+                  if (out) *reinterpret_cast<float4*>(out + pix * out_ld + ch) = o;
+                  if (out2) *reinterpret_cast<float4*>(out2 + pix * out2_ld + ch) = o;
+                  if (F16) {
+                    if (o16.hi || o16.hi2) {
+                      const uint2 hi = split_hi(o);
+                      if (o16.hi) *reinterpret_cast<uint2*>(o16.hi + pix * out_ld + ch) = hi;
+                      if (o16.hi2) *reinterpret_cast<uint2*>(o16.hi2 + pix * out2_ld + ch) = hi;
+                      if (o16.lo || o16.lo2) {
+                        const uint2 lo = split_lo(o, hi);
+                        if (o16.lo) *reinterpret_cast<uint2*>(o16.lo + pix * out_ld + ch) = lo;
+                        if (o16.lo2) *reinterpret_cast<uint2*>(o16.lo2 + pix * out2_ld + ch) = lo;
+                      }
+                    }
+                  }
+                } else {
+                  const float e4[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const int c = ch + e;
+                    if (c < cout) {
+                      float t = e4[e];
+                      if (res1) t = t * alpha1 + __ldcg(res1 + pix * res1_ld + c);
+                      if (res2) t = t * alpha2 + __ldcg(res2 + pix * res2_ld + c);
+                      if (out) out[pix * out_ld + c] = t;
+                      if (out2) out2[pix * out2_ld + c] = t;
+                      if (F16) {
+                        const __half hh = __float2half_rn(t);
+                        const __half hl = __float2half_rn((t - __half2float(hh)) * 2048.0f);
+                        if (o16.hi) o16.hi[pix * out_ld + c] = hh;
+                        if (o16.hi2) o16.hi2[pix * out2_ld + c] = hh;
+                        if (o16.lo) o16.lo[pix * out_ld + c] = hl;
+                        if (o16.lo2) o16.lo2[pix * out2_ld + c] = hl;
+                      }
+                    }
+                  }
+                }
               }
             }
           }
+          __syncwarp();   // staging is reused by the next column group
+          HCF_T(tr2);
+          HCF_ACC(PROF_E_COAL, tr1, tr2);
         }
       }
       tc_fence_before();
       mbar_arrive(tmem_empty(acc));   // all TMEM reads of this item are complete (wait::ld above)
+      HCF_T(tl3);
+      HCF_ACC(PROF_E_BODY, tl2, tl3);
       if (chain) {
-        // publish: every epilogue thread's stores -> gpu-scope fence -> 128-thread barrier -> counter
-        __threadfence();
+        // publish: 128-thread barrier (the stores of every epilogue thread happen before it), then ONE thread
+        // makes them visible at gpu scope and bumps the tile's counter (release side of the producer's acquire)
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == 64) atomicAdd(p.done + tile, 1);
+        if (et == 0) red_release_add(p.done + tile, 1);
       }
+      HCF_T(tl4);
+      HCF_ACC(PROF_E_PUBLISH, tl3, tl4);
+    }
+    HCF_T(te1);
+    HCF_ACC(PROF_E_TOTAL, te0, te1);
+    if (prof_on && et == 0) {
+      for (int i = PROF_E_TOTAL; i <= PROF_E_COAL; ++i) atomicAdd((unsigned long long*)p.prof + i, (unsigned long long)pacc[i]);
+      if (blockIdx.x == 0) atomicAdd((unsigned long long*)p.prof + PROF_LAUNCHES, 1ull);
     }
   } else {
     // ===================== A_lo converters (PASSES == 3) =====================
-    if (PASSES == 3) {
+    if (PASSES == 3 && !F16) {
       const int et = threadIdx.x - 192;   // 0..127
       uint32_t a_it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -563,12 +772,12 @@ static int num_sms() {
 // ring depths and B slot granularity that fit in shared memory; false if nothing fits
 static bool pick_rings(int mt, int passes, int ks, int NB, int* sa, int* sb, int* slab_taps, size_t* smem) {
   const int a_stage = a_part(mt, ks) * (passes == 3 ? 2 : 1);
-  const int budget = SMEM_LIMIT - 1024 - 512;
+  const int budget = SMEM_LIMIT - 1024 - TAIL_BYTES;
   const int tap = NB * ROW_BYTES;
   const int taps = ks * ks;
   auto done = [&](int a, int b, int st) {
     *sa = a; *sb = b; *slab_taps = st;
-    *smem = 1024 + (size_t)a * a_stage + (size_t)b * st * tap + 512;
+    *smem = 1024 + (size_t)a * a_stage + (size_t)b * st * tap + TAIL_BYTES;
     return true;
   };
   // 1) whole-chunk slots (one barrier round trip per chunk): >= 2 of them beside >= 2 A stages
@@ -600,23 +809,28 @@ static bool pick_rings(int mt, int passes, int ks, int NB, int* sa, int* sb, int
   return false;
 }
 
-typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
-                         const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const Params);
+typedef void (*KernelFn)(const Maps, const Params);
 
-static KernelFn pick_kernel(int mt, int passes, int ks) {
-  if (ks == 1) return passes == 3 ? conv_tc_kernel<1, 3, 1> : conv_tc_kernel<1, 1, 1>;
-  if (passes == 3) return conv_tc_kernel<1, 3, 3>;
-  return mt == 2 ? conv_tc_kernel<2, 1, 3> : conv_tc_kernel<1, 1, 3>;
+static KernelFn pick_kernel(int mt, int passes, int ks, bool f16) {
+  if (f16) {
+    if (ks == 1) return passes == 3 ? conv_tc_kernel<1, 3, 1, true> : conv_tc_kernel<1, 1, 1, true>;
+    return passes == 3 ? conv_tc_kernel<1, 3, 3, true> : conv_tc_kernel<1, 1, 3, true>;
+  }
+  if (ks == 1) return passes == 3 ? conv_tc_kernel<1, 3, 1, false> : conv_tc_kernel<1, 1, 1, false>;
+  if (passes == 3) return conv_tc_kernel<1, 3, 3, false>;
+  return mt == 2 ? conv_tc_kernel<2, 1, 3, false> : conv_tc_kernel<1, 1, 3, false>;
 }
 
 }  // namespace tc
 }  // namespace hcf
 
 struct hcf_conv_tc_plan {
-  CUtensorMap maps[hcf::tc::MAX_MAPS];
+  hcf::tc::Maps maps;
   hcf::tc::Params p;
   hcf::tc::KernelFn fn;
   hcf::tc::LayerDesc* d_layers;
+  long long* d_prof;
+  mutable long runs;
   size_t smem_bytes;
   int threads;
   dim3 grid;
@@ -633,6 +847,15 @@ extern "C" int hcf_conv_tc_supported(const hcf_conv_args* a) {
     if (a->seg[i].ld % 4 != 0 || !hcf::aligned16(a->seg[i].ptr)) return 0;
   }
   if (a->cout < 1 || a->cout > 128) return 0;
+  return 1;
+}
+
+// fp16 operand variant: the same, with 16-byte alignment counted in fp16 elements (the hi / lo planes
+// mirror the fp32 buffer's geometry: same ld, same channel offset)
+extern "C" int hcf_conv_tc16_supported(const hcf_conv_args* a) {
+  if (!hcf_conv_tc_supported(a)) return 0;
+  for (int i = 0; i < a->nseg; ++i)
+    if (a->seg[i].ld % 8 != 0) return 0;
   return 1;
 }
 
@@ -670,42 +893,93 @@ extern "C" int hcf_conv_tc_pack_weights(const float* w, int32_t kin, int32_t cou
   return 0;
 }
 
-// A chain of n convolutions on the same [B,H,W] grid with the same kernel size, each TC-eligible,
-// executed by one persistent launch.  Conv i may read anything convs < i wrote (dependencies are
-// tracked per 3x3 tile neighbourhood, which also covers write-after-read).  `done_flags`
-// (device, B*ceil(H/16)*ceil(W/8) int32) must be zeroed before every run; NULL is allowed for n == 1.
-extern "C" int hcf_conv_chain_create(const hcf_conv_args* args, const float* const* wtc, const int32_t* layer_passes,
-                                     int32_t n, int32_t* done_flags, hcf_conv_tc_plan** out) {
+// fp16 weight image: kin padded per segment to multiples of 64
+extern "C" int64_t hcf_conv_tc16_weight_bytes(int32_t kin, int32_t cout, int32_t ks, int32_t passes) {
+  if (kin % 64 != 0 || cout < 1 || cout > 128 || (ks != 1 && ks != 3) || (passes != 1 && passes != 3)) return 0;
+  return (int64_t)(kin / 64) * ks * ks * hcf::tc::n_for(cout) * (passes == 3 ? 2 : 1) * 128;
+}
+
+// w: [cout][kin][ks][ks] fp32 (host) -> [kchunk][dy][dx][rows][64 fp16], rows = [hi N ; lo' N] for passes == 3
+// (hi = fp16(w), lo' = fp16((w - hi) * 2048)), 128-byte rows pre-swizzled like the activations TMA writes
+extern "C" int hcf_conv_tc16_pack_weights(const float* w, int32_t kin, int32_t cout, int32_t ks, int32_t passes,
+                                          void* image) {
   using namespace hcf;
+  HCF_REQUIRE(w && image && kin % 64 == 0 && cout >= 1 && cout <= 128 && (ks == 1 || ks == 3) &&
+                  (passes == 1 || passes == 3), "tc16_pack: bad args");
+  const int N = tc::n_for(cout), KC = kin / 64, parts = passes == 3 ? 2 : 1, NB = N * parts;
+  memset(image, 0, (size_t)hcf_conv_tc16_weight_bytes(kin, cout, ks, passes));
+  __half* img = reinterpret_cast<__half*>(image);
+  for (int kc = 0; kc < KC; ++kc)
+    for (int dy = 0; dy < ks; ++dy)
+      for (int dx = 0; dx < ks; ++dx)
+        for (int part = 0; part < parts; ++part)
+          for (int n = 0; n < cout; ++n)
+            for (int j = 0; j < 64; ++j) {
+              const float v = w[(((size_t)n * kin + kc * 64 + j) * ks + dy) * ks + dx];
+              const __half hi = __float2half_rn(v);
+              const __half val = part == 0 ? hi : __float2half_rn((v - __half2float(hi)) * 2048.0f);
+              const int row = part * N + n;
+              const int chunk = (j / 8) ^ (row & 7);   // 16-byte chunk = 8 fp16
+              img[((((size_t)kc * ks + dy) * ks + dx) * NB + row) * 64 + chunk * 8 + (j & 7)] = val;
+            }
+  return 0;
+}
+
+namespace hcf {
+namespace tc {
+
+// maps a view pointer of an fp32 buffer to the same element of its fp16 hi / lo plane
+static bool shadow_of(const hcf_shadow16* sh, int n_sh, const float* ptr, __half** hi, __half** lo) {
+  for (int i = 0; i < n_sh; ++i) {
+    const char* base = reinterpret_cast<const char*>(sh[i].f32);
+    const char* q = reinterpret_cast<const char*>(ptr);
+    if (q >= base && q < base + sh[i].bytes) {
+      const size_t el = (size_t)(q - base) / 4;
+      *hi = reinterpret_cast<__half*>(sh[i].hi) + el;
+      *lo = reinterpret_cast<__half*>(sh[i].lo) + el;
+      return true;
+    }
+  }
+  return false;
+}
+
+static int chain_create(const hcf_conv_args* args, const void* const* wtc, const int32_t* layer_passes,
+                        const int32_t* out_flags, int32_t n, int32_t* done_flags, bool f16, const hcf_shadow16* shadows,
+                        int32_t n_shadows, hcf_conv_tc_plan** out) {
   HCF_REQUIRE(out != nullptr, "tc_chain: null out");
   *out = nullptr;
   HCF_REQUIRE(args && wtc && layer_passes && n >= 1, "tc_chain: bad args");
   HCF_REQUIRE(n == 1 || done_flags != nullptr, "tc_chain: a chain needs the done-flag array");
-  int passes = 1;   // kernel variant: 3 as soon as one layer uses the 3xTF32 split
+  HCF_REQUIRE(!f16 || (shadows && n_shadows >= 1 && out_flags), "tc_chain: fp16 chain needs the hi/lo planes and output flags");
+  int passes = 1;   // kernel variant: 3 as soon as one layer uses the split
   for (int i = 0; i < n; ++i) {
     HCF_REQUIRE(layer_passes[i] == 1 || layer_passes[i] == 3, "tc_chain: conv %d: passes %d", i, layer_passes[i]);
     if (layer_passes[i] == 3) passes = 3;
   }
   const int ks = args[0].ks;
+  const int kch = f16 ? KCH16 : KCH;
   for (int i = 0; i < n; ++i) {
     int rc = validate_conv_args(&args[i]);
     if (rc) return rc;
-    HCF_REQUIRE(hcf_conv_tc_supported(&args[i]), "tc_chain: conv %d: unsupported shape", i);
+    if (!(f16 ? hcf_conv_tc16_supported(&args[i]) : hcf_conv_tc_supported(&args[i]))) {
+      set_error("tc_chain: conv %d: unsupported shape", i);
+      return HCF_ENOTSUP;
+    }
     HCF_REQUIRE(wtc[i] && aligned16(wtc[i]), "tc_chain: conv %d: weight image alignment", i);
     HCF_REQUIRE(args[i].ks == ks && args[i].B == args[0].B && args[i].H == args[0].H && args[i].W == args[0].W,
                 "tc_chain: conv %d: all convs of a chain share ks and [B,H,W]", i);
   }
-  tc::EncodeTiledFn enc = tc::get_encode();
+  EncodeTiledFn enc = get_encode();
   HCF_REQUIRE(enc != nullptr, "tc_chain: cuTensorMapEncodeTiled entry point not found");
   const hcf_conv_args* a0 = &args[0];
   hcf_conv_tc_plan* pl = new hcf_conv_tc_plan();
   memset(pl, 0, sizeof(*pl));
-  tc::Params& p = pl->p;
+  Params& p = pl->p;
   p.B = a0->B; p.H = a0->H; p.W = a0->W;
-  const int sms = tc::num_sms();
+  const int sms = num_sms();
   int nmax = 0, nbmax = 0;
   for (int i = 0; i < n; ++i) {
-    const int nn = tc::n_for(args[i].cout), nb = nn * (layer_passes[i] == 3 ? 2 : 1);
+    const int nn = n_for(args[i].cout), nb = nn * (layer_passes[i] == 3 ? 2 : 1);
     nmax = nmax > nn ? nmax : nn;
     nbmax = nbmax > nb ? nbmax : nb;
   }
@@ -713,11 +987,11 @@ extern "C" int hcf_conv_chain_create(const hcf_conv_args* args, const float* con
   // sub-tiles per work item: 2 halves the weight traffic per pixel but quantises worse on small images
   int mt = 1;
   const char* env = getenv("HCF_TC_MT");
-  if (passes == 1 && ks == 3 && n == 1) {
+  if (!f16 && passes == 1 && ks == 3 && n == 1) {
     const long items1 = (long)a0->B * ceil_div(a0->H, 16) * ceil_div(a0->W, 8);
     const long items2 = (long)a0->B * ceil_div(a0->H, 32) * ceil_div(a0->W, 8);
-    const double t1 = (double)ceil_div((int)items1, sms) * (tc::a_part(1, 3) + 9.0 * nmax * 128);
-    const double t2 = (double)ceil_div((int)items2, sms) * (tc::a_part(2, 3) + 9.0 * nmax * 128);
+    const double t1 = (double)ceil_div((int)items1, sms) * (a_part(1, 3) + 9.0 * nmax * 128);
+    const double t2 = (double)ceil_div((int)items2, sms) * (a_part(2, 3) + 9.0 * nmax * 128);
     mt = (t2 < 0.80 * t1) ? 2 : 1;
     if (env && (env[0] == '1' || env[0] == '2')) mt = env[0] - '0';
   }
@@ -726,7 +1000,7 @@ extern "C" int hcf_conv_chain_create(const hcf_conv_args* args, const float* con
     p.debug = dbg ? atoi(dbg) : 0;
   }
   int slot_taps = 0;
-  if (!tc::pick_rings(mt, passes, ks, p.nb_max, &p.sa, &p.sb, &slot_taps, &pl->smem_bytes)) {
+  if (!pick_rings(mt, passes, ks, p.nb_max, &p.sa, &p.sb, &slot_taps, &pl->smem_bytes)) {
     delete pl;
     set_error("tc_chain: tile does not fit in shared memory");
     return HCF_ENOTSUP;
@@ -735,62 +1009,86 @@ extern "C" int hcf_conv_chain_create(const hcf_conv_args* args, const float* con
     int ra = 0, rb = 0, rs = 0;
     if (sscanf(rings, "%d,%d,%d", &ra, &rb, &rs) == 3 && ra >= 1 && ra <= 4 && rb >= 2 && rb <= 18 &&
         (rs == 1 || rs == ks || rs == ks * ks)) {
-      const size_t need = 1024 + (size_t)ra * tc::a_part(mt, ks) * (passes == 3 ? 2 : 1) +
-                          (size_t)rb * rs * p.nb_max * tc::ROW_BYTES + 512;
-      if (need <= (size_t)tc::SMEM_LIMIT) {
+      const size_t need = 1024 + (size_t)ra * a_part(mt, ks) * (passes == 3 ? 2 : 1) +
+                          (size_t)rb * rs * p.nb_max * ROW_BYTES + TAIL_BYTES;
+      if (need <= (size_t)SMEM_LIMIT) {
         p.sa = ra; p.sb = rb; slot_taps = rs;
         pl->smem_bytes = need;
       }
     }
   }
-  p.slot_bytes = slot_taps * p.nb_max * tc::ROW_BYTES;
-  p.tiles_x = ceil_div(a0->W, tc::TW); p.tiles_y = ceil_div(a0->H, tc::TH * mt);
+  p.slot_bytes = slot_taps * p.nb_max * ROW_BYTES;
+  p.tiles_x = ceil_div(a0->W, TW); p.tiles_y = ceil_div(a0->H, TH * mt);
   p.n_tiles = p.tiles_x * p.tiles_y * a0->B;
   p.n_layers = n;
   p.n_items = p.n_tiles * n;
   p.done = n > 1 ? done_flags : nullptr;
+  if (n > 1 && getenv("HCF_TC_PROF")) {
+    if (cudaMalloc(&pl->d_prof, sizeof(long long) * PROF_N) == cudaSuccess) cudaMemset(pl->d_prof, 0, sizeof(long long) * PROF_N);
+    p.prof = pl->d_prof;
+  }
 
-  // ---- tensor maps, de-duplicated.  A segment whose channel count is a multiple of 32 never reads
-  // beyond its last chunk, so such segments of one buffer share a map of the widest extent seen.
-  struct MapKey { const float* ptr; int ld; int C; bool ragged; };
+  // ---- tensor maps, de-duplicated.  A segment whose channel count is a multiple of the chunk width never
+  // reads beyond its last chunk, so such segments of one buffer share a map of the widest extent seen.
+  // fp16 chains treat every multiple of 32 that way: the half-empty last chunk then reads finite stale values
+  // of the same buffer against zero weight rows (buffers are zero-initialised and only ever hold conv outputs).
+  struct MapKey { const void* ptr; int ld; int C; bool ragged; };
   std::vector<MapKey> keys;
-  std::vector<tc::LayerDesc> layers(n);
+  auto map_for = [&](const void* ptr, int ld, int C) {
+    const bool ragged = (C % (f16 ? 32 : kch)) != 0;
+    int found = -1;
+    for (size_t k = 0; k < keys.size(); ++k)
+      if (keys[k].ptr == ptr && keys[k].ld == ld && keys[k].ragged == ragged && (!ragged || keys[k].C == C)) found = (int)k;
+    if (found < 0) {
+      keys.push_back({ptr, ld, C, ragged});
+      found = (int)keys.size() - 1;
+    } else if (!ragged && keys[found].C < C) {
+      keys[found].C = C;
+    }
+    return found;
+  };
+  std::vector<LayerDesc> layers(n);
   for (int i = 0; i < n; ++i) {
     const hcf_conv_args& a = args[i];
-    tc::LayerDesc& L = layers[i];
+    LayerDesc& L = layers[i];
     memset(&L, 0, sizeof(L));
     L.nseg = a.nseg;
+    L.parts = layer_passes[i] == 3 ? 2 : 1;
     int kc = 0;
     for (int s = 0; s < 3; ++s) {
       if (s < a.nseg) {
         const hcf_seg& sg = a.seg[s];
-        const bool ragged = (sg.C % 32) != 0;
-        int found = -1;
-        for (size_t k = 0; k < keys.size(); ++k)
-          if (keys[k].ptr == sg.ptr && keys[k].ld == sg.ld && keys[k].ragged == ragged && (!ragged || keys[k].C == sg.C))
-            found = (int)k;
-        if (found < 0) {
-          keys.push_back({sg.ptr, sg.ld, sg.C, ragged});
-          found = (int)keys.size() - 1;
-        } else if (!ragged && keys[found].C < sg.C) {
-          keys[found].C = sg.C;
+        if (f16) {
+          __half *hi = nullptr, *lo = nullptr;
+          if (!shadow_of(shadows, n_shadows, sg.ptr, &hi, &lo)) {
+            delete pl;
+            set_error("tc_chain: conv %d segment %d: no fp16 planes registered for this buffer", i, s);
+            return HCF_EINVAL;
+          }
+          if (!aligned16(hi)) {
+            delete pl;
+            set_error("tc_chain: conv %d segment %d: fp16 view is not 16-byte aligned", i, s);
+            return HCF_ENOTSUP;
+          }
+          L.map_idx[s] = map_for(hi, sg.ld, sg.C);
+          L.map_lo[s] = L.parts == 2 ? map_for(lo, sg.ld, sg.C) : 0;
+        } else {
+          L.map_idx[s] = map_for(sg.ptr, sg.ld, sg.C);
         }
-        L.map_idx[s] = found;
-        kc += (sg.C + 31) / 32;
+        kc += (sg.C + kch - 1) / kch;
       }
       L.seg_end[s] = s < a.nseg ? kc : (1 << 30);
     }
     L.seg_end[a.nseg - 1] = 1 << 30;
     L.kchunks = kc;
-    L.N = tc::n_for(a.cout);
-    L.parts = layer_passes[i] == 3 ? 2 : 1;
+    L.N = n_for(a.cout);
     {   // largest tap count (whole chunk, one dy row, one tap) of this layer that fits a ring slot
-      const int tap = L.N * L.parts * tc::ROW_BYTES;
+      const int tap = L.N * L.parts * ROW_BYTES;
       L.slab_taps = (ks * ks * tap <= p.slot_bytes) ? ks * ks : ((ks * tap <= p.slot_bytes) ? ks : 1);
     }
     L.cout = a.cout;
     L.act = a.act;
-    L.wimg = wtc[i]; L.bias = a.bias; L.scale = a.scale;
+    L.wimg = reinterpret_cast<const float*>(wtc[i]); L.bias = a.bias; L.scale = a.scale;
     L.out = a.out; L.out_ld = a.out_ld; L.out2 = a.out2; L.out2_ld = a.out2_ld;
     L.res1 = a.res1; L.res1_ld = a.res1_ld; L.alpha1 = a.alpha1;
     L.res2 = a.res2; L.res2_ld = a.res2_ld; L.alpha2 = a.alpha2;
@@ -799,31 +1097,55 @@ extern "C" int hcf_conv_chain_create(const hcf_conv_args* args, const float* con
     if (a.res1) ov = ov && aligned16(a.res1) && a.res1_ld % 4 == 0;
     if (a.res2) ov = ov && aligned16(a.res2) && a.res2_ld % 4 == 0;
     L.out_vec = ov ? 1 : 0;
+    if (f16) {
+      const int fl = out_flags[i];
+      __half *hi = nullptr, *lo = nullptr;
+      if (fl & (HCF_OUT_HI | HCF_OUT_LO)) {
+        if (!shadow_of(shadows, n_shadows, a.out, &hi, &lo)) {
+          delete pl;
+          set_error("tc_chain: conv %d: no fp16 planes registered for the output buffer", i);
+          return HCF_EINVAL;
+        }
+        L.out_hi = hi;
+        L.out_lo = (fl & HCF_OUT_LO) ? lo : nullptr;
+        if (a.out2) {
+          if (!shadow_of(shadows, n_shadows, a.out2, &hi, &lo)) {
+            delete pl;
+            set_error("tc_chain: conv %d: no fp16 planes registered for the second output buffer", i);
+            return HCF_EINVAL;
+          }
+          L.out2_hi = hi;
+          L.out2_lo = (fl & HCF_OUT_LO) ? lo : nullptr;
+        }
+      }
+      if (!(fl & HCF_OUT_F32)) { L.out = nullptr; L.out2 = nullptr; }
+    }
   }
-  if ((int)keys.size() > tc::MAX_MAPS) {
+  if ((int)keys.size() > MAX_MAPS) {
     delete pl;
-    set_error("tc_chain: %d distinct input views (max %d)", (int)keys.size(), tc::MAX_MAPS);
+    set_error("tc_chain: %d distinct input views (max %d)", (int)keys.size(), MAX_MAPS);
     return HCF_ENOTSUP;
   }
-  const cuuint32_t box[4] = {(cuuint32_t)tc::KCH, (cuuint32_t)tc::halo_w(ks), (cuuint32_t)tc::halo_rows(mt, ks), 1};
+  const cuuint32_t box[4] = {(cuuint32_t)kch, (cuuint32_t)halo_w(ks), (cuuint32_t)halo_rows(mt, ks), 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
-  for (int i = 0; i < tc::MAX_MAPS; ++i) {
+  const cuuint64_t esz = f16 ? 2 : 4;
+  for (int i = 0; i < MAX_MAPS; ++i) {
     const MapKey& k = keys[i < (int)keys.size() ? i : 0];   // unused maps alias map 0 (never dereferenced)
     const cuuint64_t dims[4] = {(cuuint64_t)k.C, (cuuint64_t)a0->W, (cuuint64_t)a0->H, (cuuint64_t)a0->B};
-    const cuuint64_t ld_b = (cuuint64_t)k.ld * 4;
+    const cuuint64_t ld_b = (cuuint64_t)k.ld * esz;
     const cuuint64_t strides[3] = {ld_b, ld_b * a0->W, ld_b * a0->W * a0->H};
-    CUresult r = enc(&pl->maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(k.ptr), dims, strides,
-                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(&pl->maps.m[i], f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                     const_cast<void*>(k.ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       delete pl;
       set_error("tc_chain: cuTensorMapEncodeTiled failed with %d (view %d, C %d, ld %d)", (int)r, i, k.C, k.ld);
       return HCF_EINVAL;
     }
   }
-  cudaError_t e = cudaMalloc(&pl->d_layers, sizeof(tc::LayerDesc) * n);
+  cudaError_t e = cudaMalloc(&pl->d_layers, sizeof(LayerDesc) * n);
   if (e == cudaSuccess)
-    e = cudaMemcpy(pl->d_layers, layers.data(), sizeof(tc::LayerDesc) * n, cudaMemcpyHostToDevice);
+    e = cudaMemcpy(pl->d_layers, layers.data(), sizeof(LayerDesc) * n, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     if (pl->d_layers) cudaFree(pl->d_layers);
     delete pl;
@@ -832,10 +1154,10 @@ extern "C" int hcf_conv_chain_create(const hcf_conv_args* args, const float* con
   }
   p.layers = pl->d_layers;
   pl->grid = dim3((unsigned)(p.n_tiles < sms ? p.n_tiles : sms));
-  pl->threads = passes == 3 ? 320 : 192;
-  pl->fn = tc::pick_kernel(mt, passes, ks);
+  pl->threads = (passes == 3 && !f16) ? 320 : 192;
+  pl->fn = pick_kernel(mt, passes, ks, f16);
   e = cudaFuncSetAttribute(reinterpret_cast<const void*>(pl->fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           tc::SMEM_LIMIT);
+                           SMEM_LIMIT);
   if (e != cudaSuccess) {
     cudaFree(pl->d_layers);
     delete pl;
@@ -844,6 +1166,26 @@ extern "C" int hcf_conv_chain_create(const hcf_conv_args* args, const float* con
   }
   *out = pl;
   return 0;
+}
+
+}  // namespace tc
+}  // namespace hcf
+
+// A chain of n convolutions on the same [B,H,W] grid with the same kernel size, each TC-eligible,
+// executed by one persistent launch.  Conv i may read anything convs < i wrote (dependencies are
+// tracked per 3x3 tile neighbourhood, which also covers write-after-read).  `done_flags`
+// (device, B*ceil(H/16)*ceil(W/8) int32) must be zeroed before every run; NULL is allowed for n == 1.
+extern "C" int hcf_conv_chain_create(const hcf_conv_args* args, const float* const* wtc, const int32_t* layer_passes,
+                                     int32_t n, int32_t* done_flags, hcf_conv_tc_plan** out) {
+  return hcf::tc::chain_create(args, reinterpret_cast<const void* const*>(wtc), layer_passes, nullptr, n, done_flags,
+                               false, nullptr, 0, out);
+}
+
+// The same chain on fp16 operands (see include/hcflow_b200.h).
+extern "C" int hcf_conv_chain16_create(const hcf_conv_args* args, const void* const* w16, const int32_t* layer_passes,
+                                       const int32_t* out_flags, int32_t n, int32_t* done_flags,
+                                       const hcf_shadow16* shadows, int32_t n_shadows, hcf_conv_tc_plan** out) {
+  return hcf::tc::chain_create(args, w16, layer_passes, out_flags, n, done_flags, true, shadows, n_shadows, out);
 }
 
 extern "C" int hcf_conv_tc_plan_create(const hcf_conv_args* a, const float* wtc, int32_t passes,
@@ -856,13 +1198,30 @@ extern "C" int32_t hcf_conv_tc_plan_layers(const hcf_conv_tc_plan* pl) { return 
 extern "C" int hcf_conv_tc_run(const hcf_conv_tc_plan* pl, void* stream) {
   using namespace hcf;
   HCF_REQUIRE(pl != nullptr, "tc_run: null plan");
-  pl->fn<<<pl->grid, pl->threads, pl->smem_bytes, (cudaStream_t)stream>>>(
-      pl->maps[0], pl->maps[1], pl->maps[2], pl->maps[3], pl->maps[4], pl->maps[5], pl->maps[6], pl->maps[7], pl->p);
+  ++pl->runs;
+  pl->fn<<<pl->grid, pl->threads, pl->smem_bytes, (cudaStream_t)stream>>>(pl->maps, pl->p);
   return finish_launch("hcf_conv_tc_run");
 }
 
 extern "C" void hcf_conv_tc_plan_destroy(hcf_conv_tc_plan* p) {
   if (!p) return;
+  if (p->d_prof) {   // HCF_TC_PROF=1: average cycles per CTA and launch, by role and wait class
+    long long h[hcf::tc::PROF_N];
+    cudaDeviceSynchronize();
+    if (cudaMemcpy(h, p->d_prof, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      static const char* names[hcf::tc::PROF_N] = {"P.total", "P.deps", "P.emptyA", "P.emptyB", "M.total", "M.tmem_empty",
+                                                   "M.fullA", "M.fullB", "M.convA", "E.total", "E.tmem_full", "E.body",
+                                                   "E.publish", "E.layer", "E.row", "E.coal", "launches"};
+      const double items = (double)p->p.n_items / p->grid.x;
+      const double launches = h[hcf::tc::PROF_LAUNCHES] > 0 ? (double)h[hcf::tc::PROF_LAUNCHES] : 1.0;
+      fprintf(stderr, "[hcf prof] chain layers=%d tiles=%d items/CTA=%.1f launches=%.0f; cycles per item:", p->p.n_layers,
+              p->p.n_tiles, items, launches);
+      for (int i = 0; i < hcf::tc::PROF_LAUNCHES; ++i)
+        fprintf(stderr, " %s=%.0f", names[i], (double)h[i] / p->grid.x / launches / items);
+      fprintf(stderr, "\n");
+    }
+    cudaFree(p->d_prof);
+  }
   if (p->d_layers) cudaFree(p->d_layers);
   delete p;
 }

@@ -1,6 +1,8 @@
 // Layout plumbing: NCHW <-> NHWC at the module boundary (with the dequantisation noise /
 // clamp / 8-bit rounding of the arch wrappers folded in), squeeze2d / unsqueeze2d and the
 // Haar analysis / synthesis pair.  All memory-bound, one read + one write per element.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace hcf {
@@ -151,6 +153,29 @@ extern "C" int hcf_squeeze2d(const hcf_squeeze_args* a, void* s) { return squeez
 extern "C" int hcf_unsqueeze2d(const hcf_squeeze_args* a, void* s) { return squeeze_like(a, s, 1, 0, "hcf_unsqueeze2d"); }
 extern "C" int hcf_haar_forward(const hcf_squeeze_args* a, void* s) { return squeeze_like(a, s, 0, 1, "hcf_haar_forward"); }
 extern "C" int hcf_haar_inverse(const hcf_squeeze_args* a, void* s) { return squeeze_like(a, s, 1, 1, "hcf_haar_inverse"); }
+
+// fp32 view -> fp16 hi / lo planes of the same geometry (operand format of the fp16 conv chains:
+// a = hi + lo / 2048); used for chain inputs that were not produced by a chain epilogue
+__global__ void __launch_bounds__(hcf::LT) split16_kernel(const float* __restrict__ src, __half* __restrict__ hi,
+                                                          __half* __restrict__ lo, long long n, int C, int ld) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long pix = i / C;
+  const int c = (int)(i - pix * C);
+  const float v = src[pix * ld + c];
+  const __half h = __float2half_rn(v);
+  hi[pix * ld + c] = h;
+  if (lo) lo[pix * ld + c] = __float2half_rn((v - __half2float(h)) * 2048.0f);
+}
+
+extern "C" int hcf_split16(const float* src, int32_t ld, int32_t C, int64_t npix, void* hi, void* lo, void* stream) {
+  using namespace hcf;
+  HCF_REQUIRE(src && hi && ld >= C && C > 0 && npix > 0, "split16: bad args");
+  const long long n = (long long)npix * C;
+  split16_kernel<<<(unsigned)((n + LT - 1) / LT), LT, 0, (cudaStream_t)stream>>>(src, reinterpret_cast<__half*>(hi),
+                                                                                 reinterpret_cast<__half*>(lo), n, C, ld);
+  return finish_launch("hcf_split16");
+}
 
 extern "C" int hcf_copy_view(const hcf_squeeze_args* a, void* stream) {
   using namespace hcf;

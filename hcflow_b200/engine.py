@@ -38,6 +38,8 @@ class Engine:
         self.n_tc = 0
         self.n_fp32_conv = 0
         self.n_chains = 0
+        self.n_chains16 = 0
+        self.shadow16 = {}       # buffer name -> (hi, lo) fp16 planes (fp16 chains)
         self.call_info = []      # per call: {"cls", "tag", "flops", "convs"}
         self.use_chains = use_chains
         with torch.cuda.device(self.device):
@@ -241,11 +243,12 @@ class Engine:
         re-enters the trunk through conv5 * 0.2) and the FCN sub-nets.  Measured on the reference goldens
         (profiles/r01_precision_mixed*.jsonl): 7.7e-5 max-abs on HR, identical to 3 passes everywhere,
         whereas one pass on conv5 alone gives 2e-2."""
-        if self.precision == "tf32":
+        base = {"f16": "tf32", "f16x3": "tf32x3"}.get(self.precision, self.precision)
+        if base == "tf32":
             return 1
-        if self.precision == "tf32x3_all":
+        if base == "tf32x3_all":
             return 3
-        if self.precision == "tf32x3":
+        if base == "tf32x3":
             one_pass = op.tag.startswith("fcn.") or op.tag in ("enc.rdb.conv1", "enc.rdb.conv2", "enc.rdb.conv3",
                                                                "enc.rdb.conv4")
             return 1 if one_pass else 3
@@ -265,12 +268,131 @@ class Engine:
             self.weights[key] = img.to(self.device)
         return self.weights[key]
 
+    # ---- fp16 chains ("f16" / "f16x3"): hi / lo planes shadowing the fp32 buffers -----------------------
+    @staticmethod
+    def _reads(op):
+        if isinstance(op, P.ConvOp):
+            return [v for v, _ in op.segs] + [v for v in (op.res1, op.res2) if v is not None]
+        if isinstance(op, P.StepOp):
+            return [v for v in (op.z, op.h) if v is not None]
+        if isinstance(op, P.PriorOp):
+            return [op.h, op.z]
+        if isinstance(op, P.LayoutOp):
+            return [op.src] if isinstance(op.src, P.View) else []
+        return []
+
+    @staticmethod
+    def _overlap(a, b):
+        return a.buf.name == b.buf.name and a.off < b.off + b.C and b.off < a.off + a.C
+
+    def _shadow(self, buf):
+        if buf.name not in self.shadow16:
+            t = self.bufs[buf.name]
+            self.shadow16[buf.name] = (torch.zeros(t.shape, dtype=torch.float16, device=self.device),
+                                       torch.zeros(t.shape, dtype=torch.float16, device=self.device))
+        return self.shadow16[buf.name]
+
+    def _tc16_weights(self, op, passes):
+        key = self._wkey(op) + "#tc16_{}".format(passes)
+        if key not in self.weights:
+            w = prep.pad_weight_for_tc(self._sd_cpu[op.weight], [v.C for v, _ in op.segs], chunk=64)
+            cout, kin, ks = w.shape[0], w.shape[1], w.shape[2]
+            nbytes = self.lib.hcf_conv_tc16_weight_bytes(kin, cout, ks, passes)
+            img = torch.zeros(nbytes // 2, dtype=torch.float16)
+            L.check(self.lib.hcf_conv_tc16_pack_weights(w.data_ptr(), kin, cout, ks, passes, img.data_ptr()), "tc16_pack")
+            self.weights[key] = img.to(self.device)
+        return self.weights[key]
+
+    def _try_chain16(self, pending):
+        """One persistent chained launch on fp16 operands (include/hcflow_b200.h, hcf_conv_chain16_create).
+        Returns False (nothing emitted) when a conv of the run does not qualify."""
+        lib = self.lib
+        n = len(pending)
+        ops = [p[0] for p in pending]
+        if not all(lib.hcf_conv_tc16_supported(C.byref(p[1])) for p in pending):
+            return False
+        passes = [self._passes_for(op) for op in ops]
+        chain_ids = {id(op) for op in ops}
+        others = [o for o in self.plan.ops if id(o) not in chain_ids]
+        flags = []
+        for k, op in enumerate(ops):
+            outs = [v for v in (op.out, op.out2) if v is not None]
+            hi = lo = f32 = False
+            for j in range(k + 1, n):
+                if any(self._overlap(v, o) for v, _ in ops[j].segs for o in outs):
+                    hi = True
+                    lo = lo or passes[j] == 3
+            for j in range(n):   # residual sources stay fp32
+                if any(self._overlap(v, o) for v in (ops[j].res1, ops[j].res2) if v is not None for o in outs):
+                    f32 = True
+            if any(self._overlap(v, o) for other in others for v in self._reads(other) for o in outs):
+                f32 = True
+            if not (hi or f32):
+                f32 = True
+            flags.append((L.OUT_F32 if f32 else 0) | (L.OUT_HI if hi else 0) | (L.OUT_LO if lo else 0))
+        # inputs that no conv of the chain produced: converted to hi / lo right before the launch
+        external = {}
+        for k, op in enumerate(ops):
+            for v, _ in op.segs:
+                produced = any(self._overlap(v, o) for j in range(k) for o in (ops[j].out, ops[j].out2) if o is not None)
+                if not produced:
+                    # the lo plane is needed as soon as ANY split conv of the chain reads these channels (e.g. the
+                    # first RDB's conv5 reads x0 inside a wider view that is otherwise produced by the chain)
+                    need_lo = any(passes[j] == 3 and any(self._overlap(v, s) for s, _ in ops[j].segs) for j in range(n))
+                    external[(v.buf.name, v.off, v.C)] = (v, need_lo)
+        bufs = {}
+        for op in ops:
+            for v in [s for s, _ in op.segs] + [o for o in (op.out, op.out2) if o is not None]:
+                bufs[v.buf.name] = v.buf
+        sh = (L.Shadow16 * len(bufs))()
+        for i, b in enumerate(bufs.values()):
+            hi_t, lo_t = self._shadow(b)
+            t = self.bufs[b.name]
+            sh[i].f32, sh[i].bytes, sh[i].hi, sh[i].lo = t.data_ptr(), t.numel() * 4, hi_t.data_ptr(), lo_t.data_ptr()
+        arr = (L.ConvArgs * n)()
+        wptr = (C.c_void_p * n)()
+        lp = (C.c_int32 * n)()
+        of = (C.c_int32 * n)()
+        for i, (op, a, _, _) in enumerate(pending):
+            C.memmove(C.byref(arr[i]), C.byref(a), C.sizeof(L.ConvArgs))
+            lp[i] = passes[i]
+            of[i] = flags[i]
+            wptr[i] = self._tc16_weights(op, passes[i]).data_ptr()
+        op0 = ops[0]
+        tiles = self.B * ((op0.H + 15) // 16) * ((op0.W + 7) // 8)
+        done = torch.zeros(tiles, dtype=torch.int32, device=self.device)
+        handle = C.c_void_p()
+        rc = lib.hcf_conv_chain16_create(arr, wptr, lp, of, n, done.data_ptr(), sh, len(bufs), C.byref(handle))
+        if rc == -2:
+            return False
+        L.check(rc, "conv_chain16_create")
+        self._keep += [arr, wptr, lp, of, sh, done]
+        self._tc_plans.append(handle)
+        npix = self.B * op0.H * op0.W
+        for v, need_lo in external.values():
+            hi_t, lo_t = self._shadow(v.buf)
+            src = self.bufs[v.buf.name].data_ptr() + 4 * v.off
+            hi_p, lo_p = hi_t.data_ptr() + 2 * v.off, (lo_t.data_ptr() + 2 * v.off) if need_lo else None
+
+            def conv_in(_a, stream, src=src, ld=v.buf.C, c=v.C, hi_p=hi_p, lo_p=lo_p):
+                return lib.hcf_split16(src, ld, c, npix, hi_p, lo_p, stream)
+            self._add_call(conv_in, None, "layout_split16")
+        self._add_call(lambda _a, _s, f=done: (f.zero_(), 0)[1], None, "flags_zero")
+        self._add_call(lib.hcf_conv_tc_run, handle, "conv_tc_chain",
+                       "chain16[{}..{}]x{}".format(pending[0][3], pending[-1][3], n), sum(p[2] for p in pending), n)
+        self.n_tc += n
+        self.n_chains += 1
+        self.n_chains16 += 1
+        return True
+
     def _flush_tc(self, pending):
         """Lower a run of consecutive tensor-core convs: one persistent chained launch when the run
         has more than one conv (same grid, 3x3), otherwise a single-conv launch."""
         if not pending:
             return
         lib = self.lib
+        if len(pending) > 1 and self.precision in ("f16", "f16x3") and self._try_chain16(pending):
+            return
         if len(pending) > 1:
             n = len(pending)
             arr = (L.ConvArgs * n)()

@@ -93,15 +93,18 @@ def tc_pad(c):
     return (c + 31) // 32 * 32
 
 
-def pad_weight_for_tc(w, seg_channels):
-    """w [Cout, Cin, ks, ks] -> [Cout, sum(ceil32(C_seg)), ks, ks] with zero rows after each segment
-    (the tensor-core kernel walks K in 32-channel chunks per segment)."""
+def pad_weight_for_tc(w, seg_channels, chunk=32):
+    """w [Cout, Cin, ks, ks] -> [Cout, sum(ceil_chunk(C_seg)), ks, ks] with zero rows after each segment
+    (the tensor-core kernel walks K in 32-channel chunks per segment; 64 for the fp16 kernels)."""
     cout, cin, ks, _ = w.shape
     assert sum(seg_channels) == cin, (seg_channels, cin)
-    out = torch.zeros(cout, sum(tc_pad(c) for c in seg_channels), ks, ks, dtype=torch.float32)
+
+    def pad(c):
+        return (c + chunk - 1) // chunk * chunk
+    out = torch.zeros(cout, sum(pad(c) for c in seg_channels), ks, ks, dtype=torch.float32)
     src = dst = 0
     for c in seg_channels:
         out[:, dst:dst + c] = w[:, src:src + c].detach().float()
         src += c
-        dst += tc_pad(c)
+        dst += pad(c)
     return out.contiguous()

@@ -119,6 +119,34 @@ int hcf_conv_tc_plan_create(const hcf_conv_args* a, const float* wtc, int32_t pa
  * `layer_passes[i]` in {1,3} selects TF32 / 3xTF32 per conv; wtc[i] must be packed with the same value. */
 int hcf_conv_chain_create(const hcf_conv_args* args, const float* const* wtc, const int32_t* layer_passes,
                           int32_t n, int32_t* done_flags, hcf_conv_tc_plan** out);
+/* The same chained launch on FP16 operands (kind::f16, 64 channels per 128-byte row: half the shared-memory
+ * and L2 traffic per MAC of the TF32 path, and round-to-nearest instead of TF32 truncation).
+ * Every fp32 activation buffer a chain conv reads or writes is shadowed by two fp16 planes of the same
+ * geometry (same ld, same channel offsets): value = hi + lo / 2048, hi = fp16(value),
+ * lo = fp16((value - hi) * 2048).  `shadows` lists them; views are matched to buffers by address range.
+ * layer_passes[i] = 1: D = A_hi x W_hi (11-bit operands); 3: D = A_hi x W_hi + (A_hi x W_lo + A_lo x W_hi) / 2048
+ * (~fp32 accuracy, needs the lo plane of its inputs).  out_flags[i] says which representations conv i writes:
+ * the fp32 view (residual sources and anything read outside the chain), the hi plane, the lo plane.
+ * Inputs that no chain conv produced must be converted first (hcf_split16).  w16[i] comes from
+ * hcf_conv_tc16_pack_weights with the same `passes`; the input-channel axis is padded per segment to
+ * multiples of 64.  Returns HCF_ENOTSUP when a conv of the chain does not qualify (ld % 8, alignment). */
+typedef struct {
+  const float* f32;  /* base of the fp32 buffer */
+  int64_t bytes;     /* its size */
+  void* hi;          /* fp16 planes, same element count */
+  void* lo;
+} hcf_shadow16;
+#define HCF_OUT_F32 1
+#define HCF_OUT_HI 2
+#define HCF_OUT_LO 4
+int hcf_conv_tc16_supported(const hcf_conv_args* a);
+int64_t hcf_conv_tc16_weight_bytes(int32_t kin, int32_t cout, int32_t ks, int32_t passes);
+int hcf_conv_tc16_pack_weights(const float* w_oihw, int32_t kin, int32_t cout, int32_t ks, int32_t passes, void* image);
+int hcf_conv_chain16_create(const hcf_conv_args* args, const void* const* w16, const int32_t* layer_passes,
+                            const int32_t* out_flags, int32_t n, int32_t* done_flags, const hcf_shadow16* shadows,
+                            int32_t n_shadows, hcf_conv_tc_plan** out);
+/* fp32 NHWC view (ld, C, npix pixels) -> hi / lo planes at the same element offsets (lo may be NULL) */
+int hcf_split16(const float* src, int32_t ld, int32_t C, int64_t npix, void* hi, void* lo, void* stream);
 int32_t hcf_conv_tc_plan_layers(const hcf_conv_tc_plan* p);
 int hcf_conv_tc_run(const hcf_conv_tc_plan* p, void* stream);
 void hcf_conv_tc_plan_destroy(hcf_conv_tc_plan* p);

@@ -308,10 +308,13 @@ def test_conv_tcgen05_matches_fp64(case, precision, report):
 
 # End-to-end tolerances of the tensor-core modes against the reference goldens (un-clamped HR,
 # values in about +-6..+-11): measured tf32 1.3e-2 max / 9e-4 mean (x4), tf32x3 see report.
-E2E_TOL = {"tf32": 5e-2, "tf32x3": 2e-3, "tf32x3_all": 2e-3}
+# "f16" / "f16x3": the chained encoder convs on FP16 operands (round-to-nearest 11-bit operands instead of TF32's
+# truncated 10+1 bits; the split layers of f16x3 carry hi + lo = 22 bits).  CPU emulation of the same operand
+# rounding (oracle + patched conv2d) gives 1.6e-3 / 1.3e-5 max-abs on sr_x4.
+E2E_TOL = {"tf32": 5e-2, "tf32x3": 2e-3, "tf32x3_all": 2e-3, "f16": 2e-2, "f16x3": 2e-3}
 
 
-@pytest.mark.parametrize("precision", ["tf32", "tf32x3", "tf32x3_all"])
+@pytest.mark.parametrize("precision", ["tf32", "tf32x3", "tf32x3_all", "f16", "f16x3"])
 @pytest.mark.parametrize("cfg", ["sr_x4", "sr_x8", "rescaling_x4"])
 def test_tensor_core_modes_match_reference_golden(cfg, precision, report):
     g = load_golden(cfg)
@@ -325,7 +328,9 @@ def test_tensor_core_modes_match_reference_golden(cfg, precision, report):
     e = maxabs(raw, g["inv_raw"])
     mean = float((raw.double() - g["inv_raw"].double()).abs().mean())
     report["e2e_reverse_{}/{}".format(precision, cfg)] = {"hr_raw_max": e, "hr_raw_mean": mean, "tc_convs": eng.n_tc,
-                                                          "fp32_convs": eng.n_fp32_conv}
+                                                          "fp32_convs": eng.n_fp32_conv, "chains16": eng.n_chains16}
+    if precision in ("f16", "f16x3"):
+        assert eng.n_chains16 > 0, "fp16 chain kernel was not selected"
     assert e < E2E_TOL[precision], (cfg, precision, e)
 
 
@@ -353,3 +358,114 @@ def test_chained_launch_is_bit_identical_to_separate_launches(precision, report)
         assert e1.n_chains >= 2 and e1.launches_per_run < e0.launches_per_run
     report["chain/{}".format(precision)] = {"launches_chained": e1.launches_per_run,
                                             "launches_separate": e0.launches_per_run, "chains": e1.n_chains}
+
+
+# ------------------------------------------------------------------------------ fp16 chains
+def _rdb_chain16(B, H, W, passes, seed=0):
+    """One ResidualDenseBlock (Basic.py:360-383) as a 5-conv fp16 chain through the C ABI: dense concat inside a
+    192-channel buffer (fp16 hi / lo planes), x5 * 0.2 + x in the last epilogue.  Returns (got fp32 out, fp64 ref,
+    hi plane of x1..x4, fp64 x1..x4)."""
+    from hcflow_b200 import prep
+    lib = L.load()
+    st = torch.cuda.current_stream().cuda_stream
+    x0 = _rand(B, 64, H, W, seed=seed)
+    ws = [_rand(32 if k < 4 else 64, 64 + 32 * k, 3, 3, seed=seed + 10 + k, scale=1.0 / math.sqrt((64 + 32 * k) * 9))
+          for k in range(5)]
+    bs = [_rand(32 if k < 4 else 64, seed=seed + 20 + k, scale=0.1) for k in range(5)]
+    X = torch.zeros(B, H, W, 192, dtype=torch.float32, device="cuda")
+    X[..., :64] = x0.cuda().permute(0, 2, 3, 1)
+    Y = torch.zeros(B, H, W, 192, dtype=torch.float32, device="cuda")
+    planes = [torch.zeros(B, H, W, 192, dtype=torch.float16, device="cuda") for _ in range(4)]
+    sh = (L.Shadow16 * 2)()
+    for i, (t, hi, lo) in enumerate(((X, planes[0], planes[1]), (Y, planes[2], planes[3]))):
+        sh[i].f32, sh[i].bytes, sh[i].hi, sh[i].lo = t.data_ptr(), t.numel() * 4, hi.data_ptr(), lo.data_ptr()
+    n = 5
+    arr = (L.ConvArgs * n)()
+    wptr = (C.c_void_p * n)()
+    lp = (C.c_int32 * n)(*passes)
+    of = (C.c_int32 * n)()
+    keep = []
+    for k in range(n):
+        cin, cout = 64 + 32 * k, (32 if k < 4 else 64)
+        a = arr[k]
+        a.B, a.H, a.W, a.nseg = B, H, W, 1
+        a.seg[0].ptr, a.seg[0].ld, a.seg[0].C, a.seg[0].up_shift = X.data_ptr(), 192, cin, 0
+        npad = prep.npad_for(cout)
+        a.ks, a.kpad, a.cout, a.npad = 3, cin, cout, npad
+        wp = prep.pack_conv_weight(ws[k], [cin], npad).cuda()
+        bp = prep.pad_vec(bs[k], npad, 0.0).cuda()
+        a.w, a.bias = wp.data_ptr(), bp.data_ptr()
+        if k < 4:
+            a.act = 2
+            a.out, a.out_ld = X.data_ptr() + 4 * cin, 192
+            of[k] = L.OUT_HI | (L.OUT_LO if any(p == 3 for p in passes[k + 1:]) else 0)
+        else:
+            a.act = 0
+            a.out, a.out_ld = Y.data_ptr(), 192
+            a.res1, a.res1_ld, a.alpha1 = X.data_ptr(), 192, 0.2
+            of[k] = L.OUT_F32 | L.OUT_HI | L.OUT_LO
+        wt = prep.pad_weight_for_tc(ws[k], [cin], chunk=64)
+        img = torch.zeros(lib.hcf_conv_tc16_weight_bytes(wt.shape[1], cout, 3, passes[k]) // 2, dtype=torch.float16)
+        L.check(lib.hcf_conv_tc16_pack_weights(wt.data_ptr(), wt.shape[1], cout, 3, passes[k], img.data_ptr()), "pack16")
+        img = img.cuda()
+        wptr[k] = img.data_ptr()
+        keep += [wp, bp, img]
+    tiles = B * ((H + 15) // 16) * ((W + 7) // 8)
+    done = torch.zeros(tiles, dtype=torch.int32, device="cuda")
+    h = C.c_void_p()
+    L.check(lib.hcf_conv_chain16_create(arr, wptr, lp, of, n, done.data_ptr(), sh, 2, C.byref(h)), "chain16_create")
+    L.check(lib.hcf_split16(X.data_ptr(), 192, 64, B * H * W, planes[0].data_ptr(), planes[1].data_ptr(), st), "split16")
+    L.check(lib.hcf_conv_tc_run(h, st), "chain16_run")
+    torch.cuda.synchronize()
+    lib.hcf_conv_tc_plan_destroy(h)
+    cat = x0.double()
+    for k in range(4):
+        y = F.leaky_relu(F.conv2d(cat, ws[k].double(), bs[k].double(), padding=1), 0.2)
+        cat = torch.cat((cat, y), 1)
+    ref = F.conv2d(cat, ws[4].double(), bs[4].double(), padding=1) * 0.2 + x0.double()
+    got = Y[..., :64].permute(0, 3, 1, 2).cpu()
+    mid = planes[0][..., 64:192].float().permute(0, 3, 1, 2).cpu()
+    y_hi = planes[2][..., :64].float().permute(0, 3, 1, 2).cpu()
+    y_lo = planes[3][..., :64].float().permute(0, 3, 1, 2).cpu()
+    return got, ref, mid, cat[:, 64:], y_hi + y_lo / 2048.0
+
+
+# outputs of magnitude ~1..4.  1 pass: fp16 operands (11 bits, round-to-nearest); the split recovers fp32-level
+# accuracy for the layers that use it.  measured values are written to the parity report.
+@pytest.mark.parametrize("mode,passes,tol", [("one_pass", [1, 1, 1, 1, 1], 3e-3), ("conv5_split", [1, 1, 1, 1, 3], 3e-3),
+                                             ("all_split", [3, 3, 3, 3, 3], 2e-5)])
+@pytest.mark.parametrize("shape", [(2, 40, 40), (1, 21, 13)], ids=["40x40", "partial_tiles"])
+def test_conv_chain16_rdb_matches_fp64(shape, mode, passes, tol, report):
+    B, H, W = shape
+    got, ref, mid, mid_ref, y16 = _rdb_chain16(B, H, W, passes)
+    err = maxabs(got, ref)
+    err_mid = maxabs(mid, mid_ref)
+    err16 = maxabs(y16, got)          # hi + lo / 2048 planes reproduce the fp32 output to ~2^-22 relative
+    report["chain16_rdb/{}/{}x{}".format(mode, H, W)] = {"out": err, "x1_4_hi_plane": err_mid, "hi_lo_vs_f32": err16}
+    assert err < tol, (mode, err)
+    assert err_mid < 6e-3, err_mid     # hi plane alone: fp16 rounding of O(1..4) values
+    assert err16 < 4e-6, err16
+
+
+@pytest.mark.parametrize("precision", ["f16", "f16x3"])
+def test_chain16_full_size_is_deterministic_and_close_to_fp32_path(precision, report):
+    """Full BASELINE size (B=16, 40x40 -> 160x160): the fp16 chains (dependency counters across 148 CTAs) give the
+    same bits on every run and agree with the tf32x3 path within the mode's end-to-end tolerance."""
+    opt, net, sd = _net_cuda("sr_x4", "tf32x3")
+    B = 16
+    lr = synth.synthetic_lr(B, 40, 40, seed=5).cuda()
+    unit = synth.synthetic_noise(orc.noise_shapes(opt, B, 40, 40, True), seed=9)
+    with torch.no_grad():
+        net(lr=lr, eps_std=0.8, reverse=True, eps=unit)
+        want = net.last["hr_raw"].clone()
+        net.set_precision(precision)
+        outs = []
+        for rep in range(3):
+            net(lr=lr, eps_std=0.8, reverse=True, eps=unit)
+            outs.append(net.last["hr_raw"].clone())
+        eng = [e for e in net._engines.values()][-1]
+    assert eng.n_chains16 >= 2
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    err = float((outs[0] - want).abs().max())
+    report["chain16_full/{}".format(precision)] = {"max_vs_tf32x3": err, "chains16": eng.n_chains16}
+    assert err < E2E_TOL[precision], err
