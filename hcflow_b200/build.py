@@ -47,7 +47,8 @@ def build(force=False, verbose=False):
     procs = []
     for src in _sources():
         obj = os.path.join(odir, os.path.basename(src).replace(".cu", ".o"))
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        prof = ["-DHCF_TC_PROF_BUILD"] if os.environ.get("HCF_BUILD_PROF") else []   # in-kernel wait profiler
+        cmd = [_nvcc()] + NVCC_FLAGS + prof + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
         objs.append(obj)
     for cmd, p in procs:

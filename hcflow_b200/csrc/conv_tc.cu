@@ -50,7 +50,7 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int NUM_SMS_FALLBACK = 148;
 constexpr int BAR_BYTES = 512;               // mbarriers + TMEM slot
 constexpr int STAGE_BYTES = 4 * 32 * 32 * 4;  // epilogue staging: 4 warps x 32 pixels x 32 channels fp32
-constexpr int TAIL_BYTES = BAR_BYTES + 1024 + STAGE_BYTES;   // + per-layer bias / scale + staging
+constexpr int TAIL_BYTES = BAR_BYTES + 2 * (1024 + STAGE_BYTES);   // + (per-layer bias / scale + staging) x 2 epilogue groups
 
 // ks = 3: (16*mt+2) x 10 halo tile; ks = 1: plain 16*mt x 8 tile
 __host__ __device__ constexpr int halo_w(int ks) { return TW + (ks - 1); }
@@ -206,12 +206,56 @@ __device__ __forceinline__ uint2 split_lo(const float4 o, const uint2 hi) {
 }
 struct Out16 { __half* hi; __half* lo; __half* hi2; __half* lo2; };
 
+// Coalesced-domain store of one 32-column group when every chunk is a full float4 and the layer has a single
+// output view: which representations are written is a template parameter (one specialisation per layer kind of
+// a chain), so the per-pixel code is straight-line.  8 lanes cover the 32 channels of a pixel.
+template <bool W32, bool WHI, bool WLO>
+__device__ __forceinline__ void coal_store_fast(const float4* __restrict__ stage, const uint32_t (&pixv)[8], int lane,
+                                                int ch, int ld, float* __restrict__ out, __half* __restrict__ hi_p,
+                                                __half* __restrict__ lo_p, bool has_r1, bool has_r2,
+                                                const float4 (&r1v)[8], const float4 (&r2v)[8], float alpha1,
+                                                float alpha2) {
+  const int cidx = lane & 7;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int pl = it * 4 + (lane >> 3);
+    if (pixv[it] != 0xffffffffu) {
+      const uint32_t e1 = pixv[it] * (uint32_t)ld + ch;
+      float4 o = stage[pl * 8 + (cidx ^ (pl & 7))];
+      if (has_r1) {
+        const float4 rr = r1v[it];
+        o.x = fmaf(o.x, alpha1, rr.x); o.y = fmaf(o.y, alpha1, rr.y); o.z = fmaf(o.z, alpha1, rr.z); o.w = fmaf(o.w, alpha1, rr.w);
+      }
+      if (has_r2) {
+        const float4 rr = r2v[it];
+        o.x = fmaf(o.x, alpha2, rr.x); o.y = fmaf(o.y, alpha2, rr.y); o.z = fmaf(o.z, alpha2, rr.z); o.w = fmaf(o.w, alpha2, rr.w);
+      }
+      if (W32) *reinterpret_cast<float4*>(out + e1) = o;
+      if (WHI) {
+        const uint2 hi = split_hi(o);
+        *reinterpret_cast<uint2*>(hi_p + e1) = hi;
+        if (WLO) *reinterpret_cast<uint2*>(lo_p + e1) = split_lo(o, hi);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ kernel
 // profile slots (HCF_TC_PROF=1): cycles summed over CTAs, printed by hcf_conv_tc_plan_destroy
 enum { PROF_P_TOTAL = 0, PROF_P_DEPS, PROF_P_EMPTYA, PROF_P_EMPTYB, PROF_M_TOTAL, PROF_M_TMEM, PROF_M_FULLA, PROF_M_FULLB,
        PROF_M_CONVA, PROF_E_TOTAL, PROF_E_TMEMFULL, PROF_E_BODY, PROF_E_PUBLISH, PROF_E_LAYER, PROF_E_ROW, PROF_E_COAL, PROF_LAUNCHES, PROF_N };
+// compiled in only with -DHCF_TC_PROF_BUILD (HCF_BUILD_PROF=1 python -m hcflow_b200.build --force): the accumulators
+// cost ~30 registers per thread
+#ifdef HCF_TC_PROF_BUILD
 #define HCF_T(var) const long long var = prof_on ? clock64() : 0ll
 #define HCF_ACC(slot, a, b) do { if (prof_on) pacc[slot] += (b) - (a); } while (0)
+#define HCF_PROF_FLUSH(lo, hi) do { if (prof_on) for (int i_ = (lo); i_ <= (hi); ++i_) \
+    atomicAdd((unsigned long long*)p.prof + i_, (unsigned long long)pacc[i_]); } while (0)
+#else
+#define HCF_T(var) do { } while (0)
+#define HCF_ACC(slot, a, b) do { } while (0)
+#define HCF_PROF_FLUSH(lo, hi) do { } while (0)
+#endif
 template <typename T>
 __device__ __forceinline__ T* ldg_ptr(T* const* p) {
   return reinterpret_cast<T*>(__ldg(reinterpret_cast<const unsigned long long*>(p)));
@@ -251,7 +295,7 @@ __device__ __forceinline__ bool deps_ready(const Deps& d, int layer) {
 
 // F16: operands are fp16 (hi / lo planes, 64 channels per 128-byte row, kind::f16); otherwise fp32 words read as TF32.
 template <int MT, int PASSES, int KS, bool F16>
-__global__ void __launch_bounds__((PASSES == 3 && !F16) ? 320 : 192, 1)
+__global__ void __launch_bounds__((PASSES == 3 || F16) ? 320 : 192, 1)
 conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
   constexpr int HALO = KS / 2;
   constexpr int HALO_W = halo_w(KS);
@@ -313,10 +357,12 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
   const int per_img = p.tiles_x * p.tiles_y;
   const int n_items = (p.debug & 32) ? 0 : p.n_items;   // timing experiment: prologue + teardown only
   const bool chain = p.done != nullptr;
+#ifdef HCF_TC_PROF_BUILD
   const bool prof_on = p.prof != nullptr;
   long long pacc[PROF_N];
 #pragma unroll
   for (int i = 0; i < PROF_N; ++i) pacc[i] = 0;
+#endif
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -412,8 +458,7 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
       }
       HCF_T(tp1);
       HCF_ACC(PROF_P_TOTAL, tp0, tp1);
-      if (prof_on)
-        for (int i = PROF_P_TOTAL; i <= PROF_P_EMPTYB; ++i) atomicAdd((unsigned long long*)p.prof + i, (unsigned long long)pacc[i]);
+      HCF_PROF_FLUSH(PROF_P_TOTAL, PROF_P_EMPTYB);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -514,26 +559,30 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
     }
     HCF_T(tm1);
     HCF_ACC(PROF_M_TOTAL, tm0, tm1);
-    if (prof_on && lane == 0)
-      for (int i = PROF_M_TOTAL; i <= PROF_M_CONVA; ++i) atomicAdd((unsigned long long*)p.prof + i, (unsigned long long)pacc[i]);
-  } else if (warp < 6) {
+    if (lane == 0) HCF_PROF_FLUSH(PROF_M_TOTAL, PROF_M_CONVA);
+  } else if (warp < 6 || F16) {
     // ===================== epilogue =====================
+    // fp16 kernels run TWO epilogue groups of four warps (warps 2-5 and 6-9): group g drains accumulator buffer g,
+    // i.e. every other work item, so the single-warp-per-scheduler latency of the store code is halved.
+    constexpr int EG = F16 ? 2 : 1;
+    const int grp = (warp - 2) >> 2;              // epilogue group of this warp
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int et = threadIdx.x - 64;              // 0..127
-    float* s_bias = reinterpret_cast<float*>(gen_base + (bar_base + BAR_BYTES - smem_base));   // [128] bias | [128] scale
-    float* s_scale = s_bias + 128;
+    const int et = (threadIdx.x - 64) & 127;      // 0..127 within the group
+    float* s_bias = reinterpret_cast<float*>(gen_base + (bar_base + BAR_BYTES - smem_base)) + grp * (256 + STAGE_BYTES / 4);
+    float* s_scale = s_bias + 128;                // [128] bias | [128] scale | staging, per group
     float4* stage = reinterpret_cast<float4*>(s_bias + 256) + q * 256;   // this warp's [32 pixels][8 x 16 B]
     Out16 o16 = {nullptr, nullptr, nullptr, nullptr};
-    uint32_t t_it = 0;
+    uint32_t t_it = grp;
     // per-layer fields stay in registers, bias / scale in shared memory (every thread needs all N of them)
     int cur_layer = -1, N = 0, cout = 0, act = 0, out_vec = 0, parts = 1;
     int out_ld = 0, out2_ld = 0, res1_ld = 0, res2_ld = 0;
     bool has_bias = false, has_scale = false;
+    int fast = 0;   // straight-line store path: bit0 fp32, bit1 hi plane, bit2 lo plane (0 = generic path)
     float* out = nullptr; float* out2 = nullptr;
     const float* res1 = nullptr; const float* res2 = nullptr;
     float alpha1 = 0.f, alpha2 = 0.f;
     HCF_T(te0);
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++t_it) {
+    for (int item = blockIdx.x + grp * gridDim.x; item < n_items; item += EG * gridDim.x, t_it += EG) {
       const int layer = item / p.n_tiles, tile = item - layer * p.n_tiles;
       const int b = tile / per_img, r = tile % per_img;
       const int y0 = (r / p.tiles_x) * TH * MT, x0 = (r % p.tiles_x) * TW;
@@ -555,14 +604,45 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
         out_ld = __ldg(&L->out_ld); out2_ld = __ldg(&L->out2_ld);
         res1_ld = __ldg(&L->res1_ld); res2_ld = __ldg(&L->res2_ld);
         alpha1 = __ldg(&L->alpha1); alpha2 = __ldg(&L->alpha2);
-        asm volatile("bar.sync 1, 128;" ::: "memory");      // everyone is done with the previous layer's bias / scale
+        fast = 0;
+        if (out_vec && cout % 32 == 0 && out2 == nullptr && o16.hi2 == nullptr && o16.lo2 == nullptr &&
+            (o16.lo == nullptr || o16.hi != nullptr))
+          fast = (out ? 1 : 0) | (o16.hi ? 2 : 0) | (o16.lo ? 4 : 0);
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");   // everyone is done with the previous layer's bias / scale
         if (et < N) {                                       // bias / scale are padded to >= N entries
           s_bias[et] = has_bias ? __ldg(bias + et) : 0.f;
           s_scale[et] = has_scale ? __ldg(scale + et) : 1.f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
       }
       const uint32_t acc = t_it & 1u;
+      // residual tiles in the coalesced-domain mapping, prefetched one column group ahead (the first group before
+      // the accumulator wait): L2-coherent loads cost a full round trip each when they are issued one by one
+      const bool res_pf = out_vec && (res1 != nullptr || res2 != nullptr) && !(p.debug & 8);
+      float4 r1v[8], r2v[8];
+      uint32_t pixv[8];   // coalesced-domain pixel of iteration `it` (global pixel index, ~0 = outside the image)
+      auto pix_setup = [&](int mt_) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int mm = q * 32 + it * 4 + (lane >> 3);
+          const int gy = y0 + mt_ * TH + mm / TW, gx = x0 + mm % TW;
+          pixv[it] = (gy < p.H && gx < p.W) ? (uint32_t)((b * p.H + gy) * p.W + gx) : 0xffffffffu;
+        }
+      };
+      auto res_prefetch = [&](int c0_) {
+        const int ch_ = c0_ + (lane & 7) * 4;
+        if (ch_ + 3 < cout) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            if (pixv[it] != 0xffffffffu) {
+              if (res1) r1v[it] = __ldcg(reinterpret_cast<const float4*>(res1 + (pixv[it] * (uint32_t)res1_ld + ch_)));
+              if (res2) r2v[it] = __ldcg(reinterpret_cast<const float4*>(res2 + (pixv[it] * (uint32_t)res2_ld + ch_)));
+            }
+          }
+        }
+      };
+      pix_setup(0);
+      if (res_pf) res_prefetch(0);
       HCF_T(tl1);
       mbar_wait(tmem_full(acc), (t_it >> 1) & 1u);
       tc_fence_after();
@@ -623,61 +703,80 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
           if (!(p.debug & 8)) {
             const int cidx = lane & 7;
             const int ch = c0 + cidx * 4;
-#pragma unroll 4
-            for (int it = 0; it < 8; ++it) {
+            const bool ch_ok = ch < cout && cidx * 4 < gw;
+            const bool vec = out_vec && ch + 3 < cout;
+            const bool hr1 = res1 != nullptr, hr2 = res2 != nullptr;
+            switch (fast) {
+              case 1: coal_store_fast<true, false, false>(stage, pixv, lane, ch, out_ld, out, o16.hi, o16.lo, hr1, hr2, r1v, r2v, alpha1, alpha2); break;
+              case 2: coal_store_fast<false, true, false>(stage, pixv, lane, ch, out_ld, out, o16.hi, o16.lo, hr1, hr2, r1v, r2v, alpha1, alpha2); break;
+              case 3: coal_store_fast<true, true, false>(stage, pixv, lane, ch, out_ld, out, o16.hi, o16.lo, hr1, hr2, r1v, r2v, alpha1, alpha2); break;
+              case 6: coal_store_fast<false, true, true>(stage, pixv, lane, ch, out_ld, out, o16.hi, o16.lo, hr1, hr2, r1v, r2v, alpha1, alpha2); break;
+              case 7: coal_store_fast<true, true, true>(stage, pixv, lane, ch, out_ld, out, o16.hi, o16.lo, hr1, hr2, r1v, r2v, alpha1, alpha2); break;
+              default: break;
+            }
+#pragma unroll
+            for (int it = 0; it < (fast ? 0 : 8); ++it) {
               const int pl = it * 4 + (lane >> 3);
-              const int mm = q * 32 + pl;
-              const int gy = y0 + mt * TH + mm / TW, gx = x0 + mm % TW;
-              if (gy < p.H && gx < p.W && ch < cout && cidx * 4 < gw) {
-                const size_t pix = ((size_t)b * p.H + gy) * p.W + gx;
+              if (pixv[it] != 0xffffffffu && ch_ok) {
+                const uint32_t e1 = pixv[it] * (uint32_t)out_ld + ch;     // element offsets fit 32 bits (checked on the host)
+                const uint32_t e2 = pixv[it] * (uint32_t)out2_ld + ch;
                 float4 o = stage[pl * 8 + (cidx ^ (pl & 7))];
-                if (out_vec && ch + 3 < cout) {
-                  // residuals may have been written by another SM earlier in this launch: L2-coherent loads
+                if (vec) {
                   if (res1) {
-                    const float4 rr = __ldcg(reinterpret_cast<const float4*>(res1 + pix * res1_ld + ch));
+                    const float4 rr = r1v[it];
                     o.x = o.x * alpha1 + rr.x; o.y = o.y * alpha1 + rr.y; o.z = o.z * alpha1 + rr.z; o.w = o.w * alpha1 + rr.w;
                   }
                   if (res2) {
-                    const float4 rr = __ldcg(reinterpret_cast<const float4*>(res2 + pix * res2_ld + ch));
+                    const float4 rr = r2v[it];
                     o.x = o.x * alpha2 + rr.x; o.y = o.y * alpha2 + rr.y; o.z = o.z * alpha2 + rr.z; o.w = o.w * alpha2 + rr.w;
                   }
-                  if (out) *reinterpret_cast<float4*>(out + pix * out_ld + ch) = o;
-                  if (out2) *reinterpret_cast<float4*>(out2 + pix * out2_ld + ch) = o;
+                  if (out) *reinterpret_cast<float4*>(out + e1) = o;
+                  if (out2) *reinterpret_cast<float4*>(out2 + e2) = o;
                   if (F16) {
                     if (o16.hi || o16.hi2) {
                       const uint2 hi = split_hi(o);
-                      if (o16.hi) *reinterpret_cast<uint2*>(o16.hi + pix * out_ld + ch) = hi;
-                      if (o16.hi2) *reinterpret_cast<uint2*>(o16.hi2 + pix * out2_ld + ch) = hi;
+                      if (o16.hi) *reinterpret_cast<uint2*>(o16.hi + e1) = hi;
+                      if (o16.hi2) *reinterpret_cast<uint2*>(o16.hi2 + e2) = hi;
                       if (o16.lo || o16.lo2) {
                         const uint2 lo = split_lo(o, hi);
-                        if (o16.lo) *reinterpret_cast<uint2*>(o16.lo + pix * out_ld + ch) = lo;
-                        if (o16.lo2) *reinterpret_cast<uint2*>(o16.lo2 + pix * out2_ld + ch) = lo;
+                        if (o16.lo) *reinterpret_cast<uint2*>(o16.lo + e1) = lo;
+                        if (o16.lo2) *reinterpret_cast<uint2*>(o16.lo2 + e2) = lo;
                       }
                     }
                   }
                 } else {
+                  // residuals may have been written by another SM earlier in this launch: L2-coherent loads
                   const float e4[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
-                    const int c = ch + e;
-                    if (c < cout) {
+                    if (ch + e < cout) {
                       float t = e4[e];
-                      if (res1) t = t * alpha1 + __ldcg(res1 + pix * res1_ld + c);
-                      if (res2) t = t * alpha2 + __ldcg(res2 + pix * res2_ld + c);
-                      if (out) out[pix * out_ld + c] = t;
-                      if (out2) out2[pix * out2_ld + c] = t;
+                      if (res1) t = t * alpha1 + __ldcg(res1 + (pixv[it] * (uint32_t)res1_ld + ch + e));
+                      if (res2) t = t * alpha2 + __ldcg(res2 + (pixv[it] * (uint32_t)res2_ld + ch + e));
+                      if (out) out[e1 + e] = t;
+                      if (out2) out2[e2 + e] = t;
                       if (F16) {
                         const __half hh = __float2half_rn(t);
                         const __half hl = __float2half_rn((t - __half2float(hh)) * 2048.0f);
-                        if (o16.hi) o16.hi[pix * out_ld + c] = hh;
-                        if (o16.hi2) o16.hi2[pix * out2_ld + c] = hh;
-                        if (o16.lo) o16.lo[pix * out_ld + c] = hl;
-                        if (o16.lo2) o16.lo2[pix * out2_ld + c] = hl;
+                        if (o16.hi) o16.hi[e1 + e] = hh;
+                        if (o16.hi2) o16.hi2[e2 + e] = hh;
+                        if (o16.lo) o16.lo[e1 + e] = hl;
+                        if (o16.lo2) o16.lo2[e2 + e] = hl;
                       }
                     }
                   }
                 }
               }
+            }
+            if (res_pf) {   // next column group's residuals: in flight during its row phase
+              if (c0 + 32 < N) {
+                res_prefetch(c0 + 32);
+              } else if (mt + 1 < MT) {
+                pix_setup(mt + 1);
+                res_prefetch(0);
+              }
+            } else if (c0 + 32 >= N && mt + 1 < MT) {
+              pix_setup(mt + 1);
             }
           }
           __syncwarp();   // staging is reused by the next column group
@@ -692,7 +791,7 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
       if (chain) {
         // publish: 128-thread barrier (the stores of every epilogue thread happen before it), then ONE thread
         // makes them visible at gpu scope and bumps the tile's counter (release side of the producer's acquire)
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
         if (et == 0) red_release_add(p.done + tile, 1);
       }
       HCF_T(tl4);
@@ -700,9 +799,11 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
     }
     HCF_T(te1);
     HCF_ACC(PROF_E_TOTAL, te0, te1);
-    if (prof_on && et == 0) {
-      for (int i = PROF_E_TOTAL; i <= PROF_E_COAL; ++i) atomicAdd((unsigned long long*)p.prof + i, (unsigned long long)pacc[i]);
-      if (blockIdx.x == 0) atomicAdd((unsigned long long*)p.prof + PROF_LAUNCHES, 1ull);
+    if (et == 0 && grp == 0) {
+      HCF_PROF_FLUSH(PROF_E_TOTAL, PROF_E_COAL);
+#ifdef HCF_TC_PROF_BUILD
+      if (prof_on && blockIdx.x == 0) atomicAdd((unsigned long long*)p.prof + PROF_LAUNCHES, 1ull);
+#endif
     }
   } else {
     // ===================== A_lo converters (PASSES == 3) =====================
@@ -968,6 +1069,14 @@ static int chain_create(const hcf_conv_args* args, const void* const* wtc, const
     HCF_REQUIRE(wtc[i] && aligned16(wtc[i]), "tc_chain: conv %d: weight image alignment", i);
     HCF_REQUIRE(args[i].ks == ks && args[i].B == args[0].B && args[i].H == args[0].H && args[i].W == args[0].W,
                 "tc_chain: conv %d: all convs of a chain share ks and [B,H,W]", i);
+    {   // the epilogue addresses outputs and residuals with 32-bit element offsets
+      const uint64_t npix = (uint64_t)args[i].B * args[i].H * args[i].W;
+      int ldm = args[i].out_ld;
+      if (args[i].out2 && args[i].out2_ld > ldm) ldm = args[i].out2_ld;
+      if (args[i].res1 && args[i].res1_ld > ldm) ldm = args[i].res1_ld;
+      if (args[i].res2 && args[i].res2_ld > ldm) ldm = args[i].res2_ld;
+      HCF_REQUIRE(npix * (uint64_t)ldm < (1ull << 32), "tc_chain: conv %d: buffer too large for 32-bit element offsets", i);
+    }
   }
   EncodeTiledFn enc = get_encode();
   HCF_REQUIRE(enc != nullptr, "tc_chain: cuTensorMapEncodeTiled entry point not found");
@@ -1154,7 +1263,7 @@ static int chain_create(const hcf_conv_args* args, const void* const* wtc, const
   }
   p.layers = pl->d_layers;
   pl->grid = dim3((unsigned)(p.n_tiles < sms ? p.n_tiles : sms));
-  pl->threads = (passes == 3 && !f16) ? 320 : 192;
+  pl->threads = (passes == 3 || f16) ? 320 : 192;
   pl->fn = pick_kernel(mt, passes, ks, f16);
   e = cudaFuncSetAttribute(reinterpret_cast<const void*>(pl->fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
                            SMEM_LIMIT);
