@@ -17,6 +17,11 @@ class Seg(C.Structure):
                 ("_pad", C.c_int32)]
 
 
+class ConvStep(C.Structure):
+    _fields_ = [("z", C.c_void_p), ("z_ld", C.c_int32), ("C", C.c_int32), ("n_pass", C.c_int32), ("z16_ld", C.c_int32),
+                ("w", C.c_void_p), ("an_scale", C.c_void_p), ("an_bias", C.c_void_p), ("z16_hi", C.c_void_p)]
+
+
 class ConvArgs(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("nseg", C.c_int32),
@@ -27,7 +32,8 @@ class ConvArgs(C.Structure):
         ("out", C.c_void_p), ("out2", C.c_void_p),
         ("out2_ld", C.c_int32), ("res1_ld", C.c_int32),
         ("res1", C.c_void_p), ("res2", C.c_void_p),
-        ("res2_ld", C.c_int32), ("alpha1", C.c_float), ("alpha2", C.c_float), ("_pad", C.c_int32),
+        ("res2_ld", C.c_int32), ("alpha1", C.c_float), ("alpha2", C.c_float), ("pre_ld", C.c_int32),
+        ("pre", C.c_void_p), ("step", C.POINTER(ConvStep)),
     ]
 
 
@@ -68,6 +74,10 @@ class Shadow16(C.Structure):
     _fields_ = [("f32", C.c_void_p), ("bytes", C.c_int64), ("hi", C.c_void_p), ("lo", C.c_void_p)]
 
 
+class Seg16(C.Structure):
+    _fields_ = [("hi", C.c_void_p), ("lo", C.c_void_p), ("ld", C.c_int32), ("_pad", C.c_int32)]
+
+
 OUT_F32, OUT_HI, OUT_LO = 1, 2, 4
 
 # every symbol include/hcflow_b200.h declares: name -> (restype, argtypes)
@@ -88,8 +98,9 @@ SYMBOLS = {
     "hcf_conv_tc16_pack_weights": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "hcf_conv_chain16_create": (C.c_int, [C.POINTER(ConvArgs), C.POINTER(C.c_void_p), C.POINTER(C.c_int32),
                                           C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.POINTER(Shadow16), C.c_int32,
-                                          C.POINTER(C.c_void_p)]),
-    "hcf_split16": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                          C.POINTER(Seg16), C.POINTER(C.c_void_p)]),
+    "hcf_split16": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,
+                              C.c_void_p]),
     "hcf_conv_tc_plan_layers": (C.c_int32, [C.c_void_p]),
     "hcf_conv_tc_run": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hcf_conv_tc_plan_destroy": (None, [C.c_void_p]),

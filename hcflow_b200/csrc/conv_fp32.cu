@@ -225,12 +225,17 @@ int validate_conv_args(const hcf_conv_args* a) {
   HCF_REQUIRE(a->out && a->out_ld >= a->cout, "conv: out");
   HCF_REQUIRE(!a->bias || aligned16(a->bias), "conv: bias alignment");
   HCF_REQUIRE(!a->scale || aligned16(a->scale), "conv: scale alignment");
+  HCF_REQUIRE(!a->pre || (!a->res1 && !a->res2 && a->pre_ld >= a->cout), "conv: pre excludes res1 / res2");
   return 0;
 }
 
 }  // namespace hcf
 
 extern "C" int hcf_conv_fp32(const hcf_conv_args* a, void* stream) {
+  if (a && (a->pre || a->step)) {
+    hcf::set_error("conv_fp32: the pre-activation addend and the fused FlowStep are tensor-core kernel features");
+    return HCF_ENOTSUP;
+  }
   using namespace hcf;
   int rc = validate_conv_args(a);
   if (rc) return rc;

@@ -75,6 +75,7 @@ struct LayerDesc {
   int out_vec;
   int parts;          // 1: one TF32 pass (B rows = N);  2: 3xTF32 split (B rows = [raw N ; lo N], plus A_lo x B)
   int slab_taps;      // taps of this layer per B ring slot: KS*KS, KS or 1 (largest that fits the slot)
+  int taps, tap0;     // taps of this layer (KS*KS, or 1 for a 1x1 conv inside a 3x3 chain) and the first tap index
   const float* wimg;  // [kchunks][ks dy][ks dx][NB][32] pre-swizzled; NB = N * parts
   const float* bias;
   const float* scale;
@@ -84,6 +85,12 @@ struct LayerDesc {
   __half* out2_hi; __half* out2_lo;
   const float* res1; int res1_ld; float alpha1;
   const float* res2; int res2_ld; float alpha2;
+  const float* pre; int pre_ld;   // added to the accumulator before bias / scale / activation
+  // fused FlowStep inverse (FlowStep.py:55-64): this conv is the sub-net's last layer; its output h is not stored,
+  // the epilogue applies  z2 = z2 * exp(-ls(h)) - shift(h);  z = W^-1 z;  z = z * exp(-logs) - bias  in place
+  float* step_z; int step_z_ld, step_C, step_npass;
+  const float* step_w; const float* step_sc; const float* step_b;
+  __half* step_z16; int step_z16_ld;   // fp16 chains: hi plane of z[:, :n_pass] for the next step's first conv
 };
 
 struct Params {
@@ -100,6 +107,7 @@ struct Params {
                       // 64 no dependency waits
   const LayerDesc* layers;
   int* done;          // chain mode: per-tile count of completed layers (zeroed before the launch)
+  int step_tab;       // 1: the chain has fused FlowStep layers (shared memory carries their W^-1 / ActNorm tables)
   long long* prof;    // HCF_TC_PROF=1: cycles per role / wait class summed over CTAs (see PROF_* below)
 };
 
@@ -209,12 +217,26 @@ struct Out16 { __half* hi; __half* lo; __half* hi2; __half* lo2; };
 // Coalesced-domain store of one 32-column group when every chunk is a full float4 and the layer has a single
 // output view: which representations are written is a template parameter (one specialisation per layer kind of
 // a chain), so the per-pixel code is straight-line.  8 lanes cover the 32 channels of a pixel.
+// per-lane epilogue constants of one 32-column group (the lane's 4 channels)
+struct Chan4 { float4 bias, scale; int act; bool has_bias, has_scale; };
+__device__ __forceinline__ float4 chan_apply(float4 o, const Chan4& c) {
+  if (c.has_bias) { o.x += c.bias.x; o.y += c.bias.y; o.z += c.bias.z; o.w += c.bias.w; }
+  if (c.has_scale) { o.x *= c.scale.x; o.y *= c.scale.y; o.z *= c.scale.z; o.w *= c.scale.w; }
+  if (c.act == HCF_ACT_RELU) {
+    o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+  } else if (c.act == HCF_ACT_LRELU) {
+    o.x = o.x > 0.f ? o.x : 0.2f * o.x; o.y = o.y > 0.f ? o.y : 0.2f * o.y;
+    o.z = o.z > 0.f ? o.z : 0.2f * o.z; o.w = o.w > 0.f ? o.w : 0.2f * o.w;
+  }
+  return o;
+}
+
 template <bool W32, bool WHI, bool WLO>
 __device__ __forceinline__ void coal_store_fast(const float4* __restrict__ stage, const uint32_t (&pixv)[8], int lane,
                                                 int ch, int ld, float* __restrict__ out, __half* __restrict__ hi_p,
-                                                __half* __restrict__ lo_p, bool has_r1, bool has_r2,
-                                                const float4 (&r1v)[8], const float4 (&r2v)[8], float alpha1,
-                                                float alpha2) {
+                                                __half* __restrict__ lo_p, const Chan4& cc, bool has_pre, bool has_r1,
+                                                bool has_r2, const float4 (&r1v)[8], const float4 (&r2v)[8],
+                                                float alpha1, float alpha2) {
   const int cidx = lane & 7;
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
@@ -222,6 +244,11 @@ __device__ __forceinline__ void coal_store_fast(const float4* __restrict__ stage
     if (pixv[it] != 0xffffffffu) {
       const uint32_t e1 = pixv[it] * (uint32_t)ld + ch;
       float4 o = stage[pl * 8 + (cidx ^ (pl & 7))];
+      if (has_pre) {
+        const float4 rr = r1v[it];
+        o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+      }
+      o = chan_apply(o, cc);
       if (has_r1) {
         const float4 rr = r1v[it];
         o.x = fmaf(o.x, alpha1, rr.x); o.y = fmaf(o.y, alpha1, rr.y); o.z = fmaf(o.z, alpha1, rr.z); o.w = fmaf(o.w, alpha1, rr.w);
@@ -230,13 +257,57 @@ __device__ __forceinline__ void coal_store_fast(const float4* __restrict__ stage
         const float4 rr = r2v[it];
         o.x = fmaf(o.x, alpha2, rr.x); o.y = fmaf(o.y, alpha2, rr.y); o.z = fmaf(o.z, alpha2, rr.z); o.w = fmaf(o.w, alpha2, rr.w);
       }
-      if (W32) *reinterpret_cast<float4*>(out + e1) = o;
+      // st.global.cg: the consumers are other SMs (TMA / L2-coherent loads); a plain store through a pointer that was
+      // loaded from memory compiles to a generic ST
+      if (W32) __stcg(reinterpret_cast<float4*>(out + e1), o);
       if (WHI) {
         const uint2 hi = split_hi(o);
-        *reinterpret_cast<uint2*>(hi_p + e1) = hi;
-        if (WLO) *reinterpret_cast<uint2*>(lo_p + e1) = split_lo(o, hi);
+        __stcg(reinterpret_cast<uint2*>(hi_p + e1), hi);
+        if (WLO) __stcg(reinterpret_cast<uint2*>(lo_p + e1), split_lo(o, hi));
       }
     }
+  }
+}
+
+// Fused FlowStep inverse on one pixel (the thread's accumulator row): h (N <= 32 values, after bias / scale) is
+// parked in the warp's staging region as scratch[c * 32 + lane] (conflict-free), z lives in registers.
+// Arithmetic follows step_inverse_kernel (flow_ops.cu): AffineCouplings.py:73-87, Permutations.py:103-108,
+// ActNorms.py:66-69.
+constexpr int STEP_MAXC = 24;
+constexpr int STEP_TAB_BYTES = (STEP_MAXC * STEP_MAXC + 2 * STEP_MAXC) * 4 + 64;   // W^-1 | scale | bias, per epilogue group
+__device__ __forceinline__ void step_inverse_pixel(float* __restrict__ scratch, int lane, const float4 (&zq)[8],
+                                                   float* __restrict__ zp, int C, int n_pass, bool has_w,
+                                                   const float* __restrict__ s_w, const float* __restrict__ s_sc,
+                                                   const float* __restrict__ s_b, __half* __restrict__ z16p) {
+  float z[STEP_MAXC];   // z arrives in the (otherwise unused) residual prefetch registers: 6 x float4
+#pragma unroll
+  for (int i = 0; i < STEP_MAXC / 4; ++i) {
+    z[4 * i] = zq[i].x; z[4 * i + 1] = zq[i].y; z[4 * i + 2] = zq[i].z; z[4 * i + 3] = zq[i].w;
+  }
+#pragma unroll
+  for (int i = 0; i < STEP_MAXC; ++i) {
+    if (i >= n_pass && i < C) {
+      const int j = i - n_pass;
+      const float shift = scratch[(2 * j) * 32 + lane], scale = scratch[(2 * j + 1) * 32 + lane];
+      z[i] = z[i] * expf(-coupling_logscale(scale)) - shift;
+    }
+  }
+  for (int i = 0; i < C; ++i) {   // (scratch columns are private to the thread: no warp sync needed)
+    float acc = 0.f;
+    if (has_w) {
+#pragma unroll
+      for (int j = 0; j < STEP_MAXC; ++j)
+        if (j < C) acc = fmaf(s_w[i * C + j], z[j], acc);
+    } else {
+#pragma unroll
+      for (int j = 0; j < STEP_MAXC; ++j) acc = (j == i) ? z[j] : acc;
+    }
+    scratch[i * 32 + lane] = acc * s_sc[i] - s_b[i];
+  }
+  for (int i = 0; i < C; ++i) {
+    const float v = scratch[i * 32 + lane];
+    zp[i] = v;
+    if (z16p && i < n_pass) z16p[i] = __float2half_rn(v);
   }
 }
 
@@ -318,7 +389,10 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
   const uint32_t tbar = bar_base + 8u * (3 * p.sa + 2 * p.sb);
   auto tmem_full = [&](int a) { return tbar + 8u * a; };
   auto tmem_empty = [&](int a) { return tbar + 16u + 8u * a; };
-  const uint32_t tmem_slot = tbar + 32u;
+  // producer -> epilogue: number of this CTA's work items whose inputs have been acquired (monotonic counter; an
+  // mbarrier would need the producer to be at most one phase ahead)
+  const uint32_t dep_seq = tbar + 32u;
+  const uint32_t tmem_slot = tbar + 48u;
   auto map_ptr = [&](int i) -> const CUtensorMap* { return &maps.m[i]; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -341,6 +415,7 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
       mbar_init(tmem_full(a), 1);
       mbar_init(tmem_empty(a), 128);
     }
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(dep_seq), "r"(0u) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -367,10 +442,10 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      uint32_t a_it = 0, b_it = 0;
+      uint32_t a_it = 0, b_it = 0, p_it = 0;
       // per-layer fields stay in registers; a CTA sees the same layer for ~n_tiles/gridDim.x items in a row
       int cur_layer = -1, kchunks = 0, se0 = 0, se1 = 0, m0 = 0, m1 = 0, m2 = 0, slab_taps = 1, slabs = 1;
-      int l0 = 0, l1 = 0, l2 = 0, lparts = 1;
+      int l0 = 0, l1 = 0, l2 = 0, lparts = 1, ltaps = KS * KS;
       uint32_t tap_bytes = 0, b_slab = 0;
       const uint8_t* wimg = nullptr;
       Deps deps;
@@ -395,7 +470,8 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
           lparts = __ldg(&L->parts);
           tap_bytes = (uint32_t)(__ldg(&L->N) * __ldg(&L->parts)) * ROW_BYTES;
           slab_taps = __ldg(&L->slab_taps);
-          slabs = (KS * KS) / slab_taps;
+          ltaps = __ldg(&L->taps);
+          slabs = ltaps / slab_taps;
           b_slab = (uint32_t)slab_taps * tap_bytes;
           wimg = reinterpret_cast<const uint8_t*>(ldg_ptr(&L->wimg));
         }
@@ -412,13 +488,17 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
             HCF_T(td1);
             HCF_ACC(PROF_P_DEPS, td0, td1);
           }
+          asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"(dep_seq), "r"(p_it + 1u) : "memory");   // epilogue may prefetch
           const int nitem = item + gridDim.x;                  // counters of the next item: in flight during this item's loads
           if (nitem < n_items) {
             const int nt = nitem % p.n_tiles;
             const int nb = nt / per_img, nr = nt % per_img;
             load_deps(deps, p.done, nb * per_img, nr / p.tiles_x, nr % p.tiles_x, p.tiles_y, p.tiles_x);
           }
+        } else {
+          asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"(dep_seq), "r"(p_it + 1u) : "memory");
         }
+        ++p_it;
         for (int kc = 0; kc < kchunks; ++kc) {
           const int sA = a_it % p.sa;
           HCF_T(ta0);
@@ -450,7 +530,7 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
             } else {
               mbar_expect_tx(fullB(sB), b_slab);
               bulk_load(b_base + sB * slot_bytes,
-                        wimg + (size_t)kc * ((uint32_t)(KS * KS) * tap_bytes) + (size_t)sl * b_slab, b_slab, fullB(sB));
+                        wimg + (size_t)kc * ((uint32_t)ltaps * tap_bytes) + (size_t)sl * b_slab, b_slab, fullB(sB));
             }
             ++b_it;
           }
@@ -471,7 +551,7 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
     const uint64_t a_tmpl = make_desc(0, HALO_W * ROW_BYTES);
     const uint64_t b_tmpl = make_desc(0, 8u * ROW_BYTES);
     uint32_t a_it = 0, b_it = 0, t_it = 0;
-    int cur_layer = -1, kchunks = 0, slab_taps = 1, slabs = 1;
+    int cur_layer = -1, kchunks = 0, slab_taps = 1, slabs = 1, tap0 = 0;
     uint32_t parts = 1, nb = 0, idesc_n = 0, idesc = 0, n_cols = 0;
     HCF_T(tm0);
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++t_it) {
@@ -484,7 +564,8 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
         parts = (uint32_t)__ldg(&L->parts);
         const uint32_t NB = N * parts;
         slab_taps = __ldg(&L->slab_taps);
-        slabs = (KS * KS) / slab_taps;
+        slabs = __ldg(&L->taps) / slab_taps;
+        tap0 = __ldg(&L->tap0);
         nb = NB * (ROW_BYTES >> 4);      // one tap of B in 16-byte units
         const uint32_t fmt = F16 ? 0u : 2u;   // A / B format: F16 = 0, TF32 = 2; D = F32
         idesc_n = (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((128u >> 4) << 24);
@@ -520,7 +601,7 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
           if (elect_one()) {
             const uint64_t b0 = b_tmpl + ((b_base + sB * slot_bytes) >> 4);
             for (int t = 0; t < ((p.debug & 2) ? 0 : slab_taps); ++t) {
-              const int tap = sl * slab_taps + t;
+              const int tap = tap0 + sl * slab_taps + t;
               const int dy = tap / KS, dx = tap - dy * KS;
               uint64_t a_tap = a0 + (uint32_t)((dy * HALO_W + dx) * (ROW_BYTES >> 4));
               if (p.debug & 1) a_tap = make_desc(0, 8u * ROW_BYTES) + ((smem_base + sA * A_STAGE) >> 4);
@@ -571,6 +652,9 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
     float* s_bias = reinterpret_cast<float*>(gen_base + (bar_base + BAR_BYTES - smem_base)) + grp * (256 + STAGE_BYTES / 4);
     float* s_scale = s_bias + 128;                // [128] bias | [128] scale | staging, per group
     float4* stage = reinterpret_cast<float4*>(s_bias + 256) + q * 256;   // this warp's [32 pixels][8 x 16 B]
+    float* st_w = reinterpret_cast<float*>(gen_base + (bar_base + TAIL_BYTES - smem_base) + grp * STEP_TAB_BYTES);
+    float* st_sc = st_w + STEP_MAXC * STEP_MAXC;   // (only present when p.step_tab)
+    float* st_b = st_sc + STEP_MAXC;
     Out16 o16 = {nullptr, nullptr, nullptr, nullptr};
     uint32_t t_it = grp;
     // per-layer fields stay in registers, bias / scale in shared memory (every thread needs all N of them)
@@ -581,6 +665,10 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
     float* out = nullptr; float* out2 = nullptr;
     const float* res1 = nullptr; const float* res2 = nullptr;
     float alpha1 = 0.f, alpha2 = 0.f;
+    bool is_pre = false;   // res1 holds the pre-activation addend (prefetched through the same registers)
+    float* step_z = nullptr; int step_z_ld = 0, step_C = 0, step_npass = 0, step_z16_ld = 0;
+    const float* step_w = nullptr; const float* step_sc = nullptr; const float* step_b = nullptr;
+    __half* step_z16 = nullptr;
     HCF_T(te0);
     for (int item = blockIdx.x + grp * gridDim.x; item < n_items; item += EG * gridDim.x, t_it += EG) {
       const int layer = item / p.n_tiles, tile = item - layer * p.n_tiles;
@@ -604,6 +692,16 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
         out_ld = __ldg(&L->out_ld); out2_ld = __ldg(&L->out2_ld);
         res1_ld = __ldg(&L->res1_ld); res2_ld = __ldg(&L->res2_ld);
         alpha1 = __ldg(&L->alpha1); alpha2 = __ldg(&L->alpha2);
+        step_z = ldg_ptr(&L->step_z);
+        if (step_z) {
+          step_z_ld = __ldg(&L->step_z_ld); step_C = __ldg(&L->step_C); step_npass = __ldg(&L->step_npass);
+          step_w = ldg_ptr(&L->step_w); step_sc = ldg_ptr(&L->step_sc); step_b = ldg_ptr(&L->step_b);
+          step_z16 = ldg_ptr(&L->step_z16); step_z16_ld = __ldg(&L->step_z16_ld);
+        }
+        is_pre = false;
+        if (const float* pre = ldg_ptr(&L->pre)) {   // host guarantees: no res1 / res2 on such a layer
+          res1 = pre; res1_ld = __ldg(&L->pre_ld); is_pre = true;
+        }
         fast = 0;
         if (out_vec && cout % 32 == 0 && out2 == nullptr && o16.hi2 == nullptr && o16.lo2 == nullptr &&
             (o16.lo == nullptr || o16.hi != nullptr))
@@ -612,6 +710,11 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
         if (et < N) {                                       // bias / scale are padded to >= N entries
           s_bias[et] = has_bias ? __ldg(bias + et) : 0.f;
           s_scale[et] = has_scale ? __ldg(scale + et) : 1.f;
+        }
+        if (step_z) {
+          if (step_w)
+            for (int i = et; i < step_C * step_C; i += 128) st_w[i] = __ldg(step_w + i);
+          if (et < step_C) { st_sc[et] = __ldg(step_sc + et); st_b[et] = __ldg(step_b + et); }
         }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
       }
@@ -642,7 +745,28 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
         }
       };
       pix_setup(0);
-      if (res_pf) res_prefetch(0);
+      if (res_pf || step_z) {
+        // the producer has acquired this item's inputs (dependency counters + fence): from here on residuals, the
+        // pre-activation addend and z may be read -- long before the accumulator is ready, so the latency hides
+        uint32_t seen;
+        do {
+          asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(seen) : "r"(dep_seq) : "memory");
+        } while (seen <= t_it);
+        if (res_pf) res_prefetch(0);
+        if (step_z) {
+          const int mm = q * 32 + lane;
+          const int gy = y0 + mm / TW, gx = x0 + mm % TW;    // (fused steps run with MT == 1)
+          const bool in = gy < p.H && gx < p.W;
+          const float* zp = step_z + (size_t)((b * p.H + (in ? gy : 0)) * p.W + (in ? gx : 0)) * step_z_ld;
+#pragma unroll
+          for (int i = 0; i < STEP_MAXC / 4; ++i) {   // a fused-step layer has no residuals: z rides in r1v
+            r1v[i].x = (in && 4 * i < step_C) ? __ldcg(zp + 4 * i) : 0.f;
+            r1v[i].y = (in && 4 * i + 1 < step_C) ? __ldcg(zp + 4 * i + 1) : 0.f;
+            r1v[i].z = (in && 4 * i + 2 < step_C) ? __ldcg(zp + 4 * i + 2) : 0.f;
+            r1v[i].w = (in && 4 * i + 3 < step_C) ? __ldcg(zp + 4 * i + 3) : 0.f;
+          }
+        }
+      }
       HCF_T(tl1);
       mbar_wait(tmem_full(acc), (t_it >> 1) & 1u);
       tc_fence_after();
@@ -655,7 +779,35 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
         for (int c0 = 0; c0 < N; c0 += 32) {
           const int gw = min(32, N - c0);          // columns of this group (16 or 32)
           HCF_T(tr0);
-          // ---- row domain (thread = pixel): TMEM -> bias / scale / activation -> staging
+          if (step_z) {
+            // ---- fused FlowStep inverse (N <= 32, single group): h never leaves the SM
+            float* scratch = reinterpret_cast<float*>(stage);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              if (h * 16 < gw) {
+                float v[16];
+                const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (acc * MT + mt) * p.nb_max + (uint32_t)(h * 16);
+                tmem_ld16(tcol, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  float t = v[j];
+                  if (has_bias) t += s_bias[h * 16 + j];
+                  if (has_scale) t *= s_scale[h * 16 + j];
+                  scratch[(h * 16 + j) * 32 + lane] = t;
+                }
+              }
+            }
+            const int mm = q * 32 + lane;
+            const int gy = y0 + mt * TH + mm / TW, gx = x0 + mm % TW;
+            if (gy < p.H && gx < p.W && !(p.debug & 8)) {
+              const uint32_t pix = (uint32_t)((b * p.H + gy) * p.W + gx);
+              step_inverse_pixel(scratch, lane, r1v, step_z + (size_t)pix * step_z_ld, step_C, step_npass,
+                                 step_w != nullptr, st_w, st_sc, st_b, step_z16 ? step_z16 + (size_t)pix * step_z16_ld : nullptr);
+            }
+            __syncwarp();
+            continue;
+          }
+          // ---- row domain (thread = pixel): TMEM accumulator -> staging (transpose through shared memory)
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             if (h * 16 < gw) {
@@ -668,27 +820,6 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                 tmem_ld16(tcol + (uint32_t)N, lo);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = F16 ? fmaf(lo[j], 1.0f / 2048.0f, v[j]) : v[j] + lo[j];
-              }
-              if (has_bias) {
-#pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                  const float4 t4 = *reinterpret_cast<const float4*>(s_bias + cc + j);
-                  v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
-                }
-              }
-              if (has_scale) {
-#pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                  const float4 t4 = *reinterpret_cast<const float4*>(s_scale + cc + j);
-                  v[j] *= t4.x; v[j + 1] *= t4.y; v[j + 2] *= t4.z; v[j + 3] *= t4.w;
-                }
-              }
-              if (act == HCF_ACT_RELU) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-              } else if (act == HCF_ACT_LRELU) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
               }
 #pragma unroll
               for (int j = 0; j < 4; ++j)   // 16-byte chunk index XOR (pixel & 7): conflict-free both ways
@@ -705,15 +836,22 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
             const int ch = c0 + cidx * 4;
             const bool ch_ok = ch < cout && cidx * 4 < gw;
             const bool vec = out_vec && ch + 3 < cout;
-            const bool hr1 = res1 != nullptr, hr2 = res2 != nullptr;
+            const bool hr1 = res1 != nullptr && !is_pre, hr2 = res2 != nullptr;
+            Chan4 cc;   // bias / scale are padded to N entries; ch < N always
+            cc.bias = *reinterpret_cast<const float4*>(s_bias + ch);
+            cc.scale = *reinterpret_cast<const float4*>(s_scale + ch);
+            cc.act = act; cc.has_bias = has_bias; cc.has_scale = has_scale;
+#define HCF_COAL(A, B_, C_) coal_store_fast<A, B_, C_>(stage, pixv, lane, ch, out_ld, out, o16.hi, o16.lo, cc, is_pre, hr1, hr2, \
+                                                     r1v, r2v, alpha1, alpha2)
             switch (fast) {
-              case 1: coal_store_fast<true, false, false>(stage, pixv, lane, ch, out_ld, out, o16.hi, o16.lo, hr1, hr2, r1v, r2v, alpha1, alpha2); break;
-              case 2: coal_store_fast<false, true, false>(stage, pixv, lane, ch, out_ld, out, o16.hi, o16.lo, hr1, hr2, r1v, r2v, alpha1, alpha2); break;
-              case 3: coal_store_fast<true, true, false>(stage, pixv, lane, ch, out_ld, out, o16.hi, o16.lo, hr1, hr2, r1v, r2v, alpha1, alpha2); break;
-              case 6: coal_store_fast<false, true, true>(stage, pixv, lane, ch, out_ld, out, o16.hi, o16.lo, hr1, hr2, r1v, r2v, alpha1, alpha2); break;
-              case 7: coal_store_fast<true, true, true>(stage, pixv, lane, ch, out_ld, out, o16.hi, o16.lo, hr1, hr2, r1v, r2v, alpha1, alpha2); break;
+              case 1: HCF_COAL(true, false, false); break;
+              case 2: HCF_COAL(false, true, false); break;
+              case 3: HCF_COAL(true, true, false); break;
+              case 6: HCF_COAL(false, true, true); break;
+              case 7: HCF_COAL(true, true, true); break;
               default: break;
             }
+#undef HCF_COAL
 #pragma unroll
             for (int it = 0; it < (fast ? 0 : 8); ++it) {
               const int pl = it * 4 + (lane >> 3);
@@ -722,7 +860,12 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                 const uint32_t e2 = pixv[it] * (uint32_t)out2_ld + ch;
                 float4 o = stage[pl * 8 + (cidx ^ (pl & 7))];
                 if (vec) {
-                  if (res1) {
+                  if (is_pre) {
+                    const float4 rr = r1v[it];
+                    o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+                  }
+                  o = chan_apply(o, cc);
+                  if (hr1) {
                     const float4 rr = r1v[it];
                     o.x = o.x * alpha1 + rr.x; o.y = o.y * alpha1 + rr.y; o.z = o.z * alpha1 + rr.z; o.w = o.w * alpha1 + rr.w;
                   }
@@ -751,7 +894,11 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                   for (int e = 0; e < 4; ++e) {
                     if (ch + e < cout) {
                       float t = e4[e];
-                      if (res1) t = t * alpha1 + __ldcg(res1 + (pixv[it] * (uint32_t)res1_ld + ch + e));
+                      if (is_pre) t += __ldcg(res1 + (pixv[it] * (uint32_t)res1_ld + ch + e));
+                      if (has_bias) t += s_bias[ch + e];
+                      if (has_scale) t *= s_scale[ch + e];
+                      t = act == HCF_ACT_RELU ? fmaxf(t, 0.f) : (act == HCF_ACT_LRELU ? (t > 0.f ? t : 0.2f * t) : t);
+                      if (hr1) t = t * alpha1 + __ldcg(res1 + (pixv[it] * (uint32_t)res1_ld + ch + e));
                       if (res2) t = t * alpha2 + __ldcg(res2 + (pixv[it] * (uint32_t)res2_ld + ch + e));
                       if (out) out[e1 + e] = t;
                       if (out2) out2[e2 + e] = t;
@@ -871,14 +1018,14 @@ static int num_sms() {
 }
 
 // ring depths and B slot granularity that fit in shared memory; false if nothing fits
-static bool pick_rings(int mt, int passes, int ks, int NB, int* sa, int* sb, int* slab_taps, size_t* smem) {
+static bool pick_rings(int mt, int passes, int ks, int NB, int extra, int* sa, int* sb, int* slab_taps, size_t* smem) {
   const int a_stage = a_part(mt, ks) * (passes == 3 ? 2 : 1);
-  const int budget = SMEM_LIMIT - 1024 - TAIL_BYTES;
+  const int budget = SMEM_LIMIT - 1024 - TAIL_BYTES - extra;
   const int tap = NB * ROW_BYTES;
   const int taps = ks * ks;
   auto done = [&](int a, int b, int st) {
     *sa = a; *sb = b; *slab_taps = st;
-    *smem = 1024 + (size_t)a * a_stage + (size_t)b * st * tap + TAIL_BYTES;
+    *smem = 1024 + (size_t)a * a_stage + (size_t)b * st * tap + TAIL_BYTES + extra;
     return true;
   };
   // 1) whole-chunk slots (one barrier round trip per chunk): >= 2 of them beside >= 2 A stages
@@ -1046,7 +1193,7 @@ static bool shadow_of(const hcf_shadow16* sh, int n_sh, const float* ptr, __half
 
 static int chain_create(const hcf_conv_args* args, const void* const* wtc, const int32_t* layer_passes,
                         const int32_t* out_flags, int32_t n, int32_t* done_flags, bool f16, const hcf_shadow16* shadows,
-                        int32_t n_shadows, hcf_conv_tc_plan** out) {
+                        int32_t n_shadows, const hcf_seg16* seg16, hcf_conv_tc_plan** out) {
   HCF_REQUIRE(out != nullptr, "tc_chain: null out");
   *out = nullptr;
   HCF_REQUIRE(args && wtc && layer_passes && n >= 1, "tc_chain: bad args");
@@ -1057,24 +1204,29 @@ static int chain_create(const hcf_conv_args* args, const void* const* wtc, const
     HCF_REQUIRE(layer_passes[i] == 1 || layer_passes[i] == 3, "tc_chain: conv %d: passes %d", i, layer_passes[i]);
     if (layer_passes[i] == 3) passes = 3;
   }
-  const int ks = args[0].ks;
+  int ks = 1;   // kernel variant: 3 as soon as one conv is 3x3; 1x1 convs of such a chain use the centre tap only
+  for (int i = 0; i < n; ++i) ks = args[i].ks > ks ? args[i].ks : ks;
   const int kch = f16 ? KCH16 : KCH;
   for (int i = 0; i < n; ++i) {
     int rc = validate_conv_args(&args[i]);
     if (rc) return rc;
-    if (!(f16 ? hcf_conv_tc16_supported(&args[i]) : hcf_conv_tc_supported(&args[i]))) {
+    if (!(f16 ? (seg16 ? hcf_conv_tc_supported(&args[i]) : hcf_conv_tc16_supported(&args[i]))
+              : hcf_conv_tc_supported(&args[i]))) {
       set_error("tc_chain: conv %d: unsupported shape", i);
       return HCF_ENOTSUP;
     }
     HCF_REQUIRE(wtc[i] && aligned16(wtc[i]), "tc_chain: conv %d: weight image alignment", i);
-    HCF_REQUIRE(args[i].ks == ks && args[i].B == args[0].B && args[i].H == args[0].H && args[i].W == args[0].W,
-                "tc_chain: conv %d: all convs of a chain share ks and [B,H,W]", i);
+    HCF_REQUIRE((args[i].ks == ks || args[i].ks == 1) && args[i].B == args[0].B && args[i].H == args[0].H &&
+                    args[i].W == args[0].W, "tc_chain: conv %d: all convs of a chain share [B,H,W]; ks is 1 or the chain's", i);
+    HCF_REQUIRE(!args[i].pre || (!args[i].res1 && !args[i].res2 && args[i].pre_ld >= args[i].cout),
+                "tc_chain: conv %d: pre excludes res1 / res2", i);
     {   // the epilogue addresses outputs and residuals with 32-bit element offsets
       const uint64_t npix = (uint64_t)args[i].B * args[i].H * args[i].W;
       int ldm = args[i].out_ld;
       if (args[i].out2 && args[i].out2_ld > ldm) ldm = args[i].out2_ld;
       if (args[i].res1 && args[i].res1_ld > ldm) ldm = args[i].res1_ld;
       if (args[i].res2 && args[i].res2_ld > ldm) ldm = args[i].res2_ld;
+      if (args[i].pre && args[i].pre_ld > ldm) ldm = args[i].pre_ld;
       HCF_REQUIRE(npix * (uint64_t)ldm < (1ull << 32), "tc_chain: conv %d: buffer too large for 32-bit element offsets", i);
     }
   }
@@ -1109,7 +1261,12 @@ static int chain_create(const hcf_conv_args* args, const void* const* wtc, const
     p.debug = dbg ? atoi(dbg) : 0;
   }
   int slot_taps = 0;
-  if (!pick_rings(mt, passes, ks, p.nb_max, &p.sa, &p.sb, &slot_taps, &pl->smem_bytes)) {
+  int tail_extra = 0;
+  for (int i = 0; i < n; ++i)
+    if (args[i].step) tail_extra = 2 * STEP_TAB_BYTES;
+  p.step_tab = tail_extra ? 1 : 0;
+  if (tail_extra && mt != 1) mt = 1;
+  if (!pick_rings(mt, passes, ks, p.nb_max, tail_extra, &p.sa, &p.sb, &slot_taps, &pl->smem_bytes)) {
     delete pl;
     set_error("tc_chain: tile does not fit in shared memory");
     return HCF_ENOTSUP;
@@ -1119,7 +1276,7 @@ static int chain_create(const hcf_conv_args* args, const void* const* wtc, const
     if (sscanf(rings, "%d,%d,%d", &ra, &rb, &rs) == 3 && ra >= 1 && ra <= 4 && rb >= 2 && rb <= 18 &&
         (rs == 1 || rs == ks || rs == ks * ks)) {
       const size_t need = 1024 + (size_t)ra * a_part(mt, ks) * (passes == 3 ? 2 : 1) +
-                          (size_t)rb * rs * p.nb_max * ROW_BYTES + TAIL_BYTES;
+                          (size_t)rb * rs * p.nb_max * ROW_BYTES + TAIL_BYTES + tail_extra;
       if (need <= (size_t)SMEM_LIMIT) {
         p.sa = ra; p.sb = rb; slot_taps = rs;
         pl->smem_bytes = need;
@@ -1169,18 +1326,24 @@ static int chain_create(const hcf_conv_args* args, const void* const* wtc, const
         const hcf_seg& sg = a.seg[s];
         if (f16) {
           __half *hi = nullptr, *lo = nullptr;
-          if (!shadow_of(shadows, n_shadows, sg.ptr, &hi, &lo)) {
+          int ld16 = sg.ld;
+          const hcf_seg16* ov = seg16 ? &seg16[i * 3 + s] : nullptr;
+          if (ov && ov->hi) {
+            hi = reinterpret_cast<__half*>(const_cast<void*>(ov->hi));
+            lo = reinterpret_cast<__half*>(const_cast<void*>(ov->lo));
+            ld16 = ov->ld;
+          } else if (!shadow_of(shadows, n_shadows, sg.ptr, &hi, &lo)) {
             delete pl;
             set_error("tc_chain: conv %d segment %d: no fp16 planes registered for this buffer", i, s);
             return HCF_EINVAL;
           }
-          if (!aligned16(hi)) {
+          if (!aligned16(hi) || ld16 % 8 != 0 || (L.parts == 2 && (!lo || !aligned16(lo)))) {
             delete pl;
-            set_error("tc_chain: conv %d segment %d: fp16 view is not 16-byte aligned", i, s);
+            set_error("tc_chain: conv %d segment %d: fp16 view breaks TMA's 16-byte rules", i, s);
             return HCF_ENOTSUP;
           }
-          L.map_idx[s] = map_for(hi, sg.ld, sg.C);
-          L.map_lo[s] = L.parts == 2 ? map_for(lo, sg.ld, sg.C) : 0;
+          L.map_idx[s] = map_for(hi, ld16, sg.C);
+          L.map_lo[s] = L.parts == 2 ? map_for(lo, ld16, sg.C) : 0;
         } else {
           L.map_idx[s] = map_for(sg.ptr, sg.ld, sg.C);
         }
@@ -1191,9 +1354,15 @@ static int chain_create(const hcf_conv_args* args, const void* const* wtc, const
     L.seg_end[a.nseg - 1] = 1 << 30;
     L.kchunks = kc;
     L.N = n_for(a.cout);
-    {   // largest tap count (whole chunk, one dy row, one tap) of this layer that fits a ring slot
+    if (a.ks == ks) {   // largest tap count (whole chunk, one dy row, one tap) of this layer that fits a ring slot
       const int tap = L.N * L.parts * ROW_BYTES;
       L.slab_taps = (ks * ks * tap <= p.slot_bytes) ? ks * ks : ((ks * tap <= p.slot_bytes) ? ks : 1);
+      L.taps = ks * ks;
+      L.tap0 = 0;
+    } else {            // 1x1 conv inside a 3x3 chain: same halo tile, centre tap
+      L.slab_taps = 1;
+      L.taps = 1;
+      L.tap0 = (ks * ks) / 2;
     }
     L.cout = a.cout;
     L.act = a.act;
@@ -1201,15 +1370,31 @@ static int chain_create(const hcf_conv_args* args, const void* const* wtc, const
     L.out = a.out; L.out_ld = a.out_ld; L.out2 = a.out2; L.out2_ld = a.out2_ld;
     L.res1 = a.res1; L.res1_ld = a.res1_ld; L.alpha1 = a.alpha1;
     L.res2 = a.res2; L.res2_ld = a.res2_ld; L.alpha2 = a.alpha2;
+    L.pre = a.pre; L.pre_ld = a.pre_ld;
+    if (a.step) {
+      const hcf_conv_step& st = *a.step;
+      if (!(st.z && st.C >= 2 && st.C <= STEP_MAXC && st.n_pass >= 1 && st.n_pass < st.C && st.z_ld >= st.C &&
+            a.cout == 2 * (st.C - st.n_pass) && L.N <= 32 && st.an_scale && st.an_bias && !a.res1 && !a.res2 && !a.pre &&
+            !a.out2 && (!st.z16_hi || st.z16_ld >= st.n_pass))) {
+        delete pl;
+        set_error("tc_chain: conv %d: fused FlowStep needs cout == 2 * (C - n_pass) <= 32, C <= %d, no residuals", i, STEP_MAXC);
+        return HCF_EINVAL;
+      }
+      L.step_z = st.z; L.step_z_ld = st.z_ld; L.step_C = st.C; L.step_npass = st.n_pass;
+      L.step_w = st.w; L.step_sc = st.an_scale; L.step_b = st.an_bias;
+      L.step_z16 = reinterpret_cast<__half*>(st.z16_hi); L.step_z16_ld = st.z16_ld;
+      L.out = nullptr; L.out2 = nullptr;
+    }
     bool ov = aligned16(a.out) && a.out_ld % 4 == 0;
     if (a.out2) ov = ov && aligned16(a.out2) && a.out2_ld % 4 == 0;
     if (a.res1) ov = ov && aligned16(a.res1) && a.res1_ld % 4 == 0;
     if (a.res2) ov = ov && aligned16(a.res2) && a.res2_ld % 4 == 0;
+    if (a.pre) ov = ov && aligned16(a.pre) && a.pre_ld % 4 == 0;
     L.out_vec = ov ? 1 : 0;
     if (f16) {
       const int fl = out_flags[i];
       __half *hi = nullptr, *lo = nullptr;
-      if (fl & (HCF_OUT_HI | HCF_OUT_LO)) {
+      if ((fl & (HCF_OUT_HI | HCF_OUT_LO)) && !a.step) {
         if (!shadow_of(shadows, n_shadows, a.out, &hi, &lo)) {
           delete pl;
           set_error("tc_chain: conv %d: no fp16 planes registered for the output buffer", i);
@@ -1227,7 +1412,7 @@ static int chain_create(const hcf_conv_args* args, const void* const* wtc, const
           L.out2_lo = (fl & HCF_OUT_LO) ? lo : nullptr;
         }
       }
-      if (!(fl & HCF_OUT_F32)) { L.out = nullptr; L.out2 = nullptr; }
+      if (!(fl & HCF_OUT_F32) || a.step) { L.out = nullptr; L.out2 = nullptr; }
     }
   }
   if ((int)keys.size() > MAX_MAPS) {
@@ -1287,14 +1472,15 @@ static int chain_create(const hcf_conv_args* args, const void* const* wtc, const
 extern "C" int hcf_conv_chain_create(const hcf_conv_args* args, const float* const* wtc, const int32_t* layer_passes,
                                      int32_t n, int32_t* done_flags, hcf_conv_tc_plan** out) {
   return hcf::tc::chain_create(args, reinterpret_cast<const void* const*>(wtc), layer_passes, nullptr, n, done_flags,
-                               false, nullptr, 0, out);
+                               false, nullptr, 0, nullptr, out);
 }
 
 // The same chain on fp16 operands (see include/hcflow_b200.h).
 extern "C" int hcf_conv_chain16_create(const hcf_conv_args* args, const void* const* w16, const int32_t* layer_passes,
                                        const int32_t* out_flags, int32_t n, int32_t* done_flags,
-                                       const hcf_shadow16* shadows, int32_t n_shadows, hcf_conv_tc_plan** out) {
-  return hcf::tc::chain_create(args, w16, layer_passes, out_flags, n, done_flags, true, shadows, n_shadows, out);
+                                       const hcf_shadow16* shadows, int32_t n_shadows, const hcf_seg16* seg16,
+                                       hcf_conv_tc_plan** out) {
+  return hcf::tc::chain_create(args, w16, layer_passes, out_flags, n, done_flags, true, shadows, n_shadows, seg16, out);
 }
 
 extern "C" int hcf_conv_tc_plan_create(const hcf_conv_args* a, const float* wtc, int32_t passes,

@@ -157,23 +157,25 @@ extern "C" int hcf_haar_inverse(const hcf_squeeze_args* a, void* s) { return squ
 // fp32 view -> fp16 hi / lo planes of the same geometry (operand format of the fp16 conv chains:
 // a = hi + lo / 2048); used for chain inputs that were not produced by a chain epilogue
 __global__ void __launch_bounds__(hcf::LT) split16_kernel(const float* __restrict__ src, __half* __restrict__ hi,
-                                                          __half* __restrict__ lo, long long n, int C, int ld) {
+                                                          __half* __restrict__ lo, long long n, int C, int ld,
+                                                          int dst_ld) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const long long pix = i / C;
   const int c = (int)(i - pix * C);
   const float v = src[pix * ld + c];
   const __half h = __float2half_rn(v);
-  hi[pix * ld + c] = h;
-  if (lo) lo[pix * ld + c] = __float2half_rn((v - __half2float(h)) * 2048.0f);
+  hi[pix * dst_ld + c] = h;
+  if (lo) lo[pix * dst_ld + c] = __float2half_rn((v - __half2float(h)) * 2048.0f);
 }
 
-extern "C" int hcf_split16(const float* src, int32_t ld, int32_t C, int64_t npix, void* hi, void* lo, void* stream) {
+extern "C" int hcf_split16(const float* src, int32_t ld, int32_t C, int64_t npix, void* hi, void* lo, int32_t dst_ld,
+                           void* stream) {
   using namespace hcf;
-  HCF_REQUIRE(src && hi && ld >= C && C > 0 && npix > 0, "split16: bad args");
+  HCF_REQUIRE(src && hi && ld >= C && dst_ld >= C && C > 0 && npix > 0, "split16: bad args");
   const long long n = (long long)npix * C;
   split16_kernel<<<(unsigned)((n + LT - 1) / LT), LT, 0, (cudaStream_t)stream>>>(src, reinterpret_cast<__half*>(hi),
-                                                                                 reinterpret_cast<__half*>(lo), n, C, ld);
+                                                                                 reinterpret_cast<__half*>(lo), n, C, ld, dst_ld);
   return finish_launch("hcf_split16");
 }
 

@@ -42,8 +42,14 @@ class Engine:
         self.shadow16 = {}       # buffer name -> (hi, lo) fp16 planes (fp16 chains)
         self.call_info = []      # per call: {"cls", "tag", "flops", "convs"}
         self.use_chains = use_chains
+        self.share_cond = True   # compute the coupling sub-nets' shared conditioning part once per level (TC modes)
+        self.fuse_steps = True   # FlowStep tail in the last sub-net conv's epilogue (TC modes, inverse pass)
+        self._step_structs = {}  # id(conv op) -> L.ConvStep
+        self._flag_pool = None   # dependency counters of all chained launches: one buffer, zeroed once per pass
+        self._flag_used = 0
         with torch.cuda.device(self.device):
             self._alloc()
+            self.ops = self._rewrite_ops()
             self.load_weights()
             self._lower()
 
@@ -89,20 +95,21 @@ class Engine:
             else:
                 self.weights[key] = t.to(dev)
 
-        for op in self.plan.ops:
+        self._sd_cpu = sd
+        for op in self.ops:
             if isinstance(op, P.ConvOp):
                 npad = prep.npad_for(op.cout)
                 segc = [v.C for v, _ in op.segs]
-                put(self._wkey(op), prep.pack_conv_weight(sd[op.weight], segc, npad))
+                put(self._wkey(op), prep.pack_conv_weight(self._raw_weight(op), segc, npad))
                 if op.bias:
                     put(op.bias + "@{}".format(npad), prep.pad_vec(prep.derive(sd, op.bias), npad, 0.0))
                 if op.scale:
                     put(op.scale + "@{}".format(npad), prep.pad_vec(prep.derive(sd, op.scale), npad, 1.0))
-            elif isinstance(op, P.StepOp):
-                for key in (op.w, op.an_scale, op.an_bias):
+            st = op if isinstance(op, P.StepOp) else (op.step if isinstance(op, P.ConvOp) else None)
+            if st is not None:
+                for key in (st.w, st.an_scale, st.an_bias):
                     if key:
                         put(key, prep.derive(sd, key))
-        self._sd_cpu = sd
         self.logdet_const = prep.logdet_constant(sd, self.plan.logdet_terms)
         if self.plan.direction == "forward" and self.plan.sr:
             s = 2 ** self.net.flow.L
@@ -112,14 +119,81 @@ class Engine:
 
     @staticmethod
     def _wkey(op):
-        return "{}|{}".format(op.weight, ",".join(str(v.C) for v, _ in op.segs))
+        return "{}{}|{}".format(op.weight, op.w_in or "", ",".join(str(v.C) for v, _ in op.segs))
+
+    def _raw_weight(self, op):
+        """[Cout, Cin, ks, ks] fp32 CPU weight of a conv op; engine-level rewrites may slice the input-channel
+        axis (w_in) or concatenate several parameters along Cout (weight = tuple of (key, lo, hi))."""
+        sd = self._sd_cpu
+        if isinstance(op.weight, str):
+            w = sd[op.weight].detach().float()
+            return w[:, op.w_in[0]:op.w_in[1]].contiguous() if op.w_in else w
+        return torch.cat([sd[k].detach().float()[:, lo:hi] for k, lo, hi in op.weight], 0).contiguous()
+
+    def _rewrite_ops(self):
+        """Engine-level rewrite of the plan for the tensor-core modes.  The conditional FlowSteps of a level all run
+        their sub-net's first conv on cat(z1, u) with the SAME encoder feature u (ConditionalFlow.py:62-66,
+        AffineCouplings.py:31): W * cat(z1, u) = W_z * z1 + W_u * u, and the W_u * u parts of all steps are one wide
+        conv over u (Cout = steps x 64, UMMA N = 128) computed once per level; each step then convolves only its few
+        z1 channels and adds its slice before ActNorm + ReLU (hcf_conv_args.pre)."""
+        ops = list(self.plan.ops)
+        if self.precision == "fp32" or not self.share_cond:
+            return ops
+        groups = {}
+        for i, op in enumerate(ops):
+            if isinstance(op, P.ConvOp) and op.tag == "fcn.conv1" and len(op.segs) == 2 and op.segs[1][1] == 0:
+                v = op.segs[1][0]
+                groups.setdefault((v.buf.name, v.off, v.C, op.H, op.W, op.cout, op.segs[0][0].C), []).append(i)
+        inserts = {}
+        for (bname, off, cc, H, W, cout, zc), idxs in groups.items():
+            if len(idxs) < 2 or cout > 128 or cout % 4 != 0:
+                continue
+            n = len(idxs)
+            per = max(1, 128 // cout)
+            ubuf = P.Buf("ucond_{}_{}".format(bname, off), H, W, n * cout)
+            self.bufs[ubuf.name] = torch.zeros(self.B, H, W, ubuf.C, dtype=torch.float32, device=self.device)
+            cond = ops[idxs[0]].segs[1][0]
+            uops = []
+            for g in range(0, n, per):
+                mem = idxs[g:g + per]
+                uops.append(P.ConvOp(H, W, [(cond, 0)], 3, cout * len(mem),
+                                     tuple((ops[m].weight, zc, zc + cc) for m in mem), None, None, P.ACT_NONE,
+                                     P.View(ubuf, g * cout, cout * len(mem)), tag="fcn.ucond"))
+            inserts[idxs[0]] = uops
+            for j, m in enumerate(idxs):
+                o = ops[m]
+                ops[m] = P.ConvOp(o.H, o.W, [o.segs[0]], o.ks, o.cout, o.weight, o.bias, o.scale, o.act, o.out, tag=o.tag,
+                                  w_in=(0, zc), pre=P.View(ubuf, j * cout, cout))
+        out = []
+        for i, op in enumerate(ops):
+            out.extend(inserts.get(i, []))
+            out.append(op)
+        if not self.fuse_steps:
+            return out
+        # FlowStep tail fused into the sub-net's last conv (hcf_conv_step): removes one launch per step and lets the
+        # convs of consecutive steps of a level run as ONE chained launch
+        fused = []
+        for op in out:
+            prev = fused[-1] if fused else None
+            if (isinstance(op, P.StepOp) and op.variant == "inverse" and op.mode == "affine" and op.h is not None
+                    and isinstance(prev, P.ConvOp) and prev.tag == "fcn.conv3" and prev.step is None
+                    and prev.out == op.h and prev.out2 is None and prev.res1 is None and prev.res2 is None
+                    and prev.cout == 2 * (op.z.C - op.n_pass) and prev.cout <= 32 and op.z.C <= 24
+                    and (prev.H, prev.W) == (op.H, op.W)):
+                prev.step = op
+                continue
+            if isinstance(op, P.ConvOp) and op.tag == "fcn.conv3":
+                op = P.ConvOp(op.H, op.W, op.segs, op.ks, op.cout, op.weight, op.bias, op.scale, op.act, op.out,
+                              tag=op.tag, w_in=op.w_in, pre=op.pre)   # private copy: the plan's op stays untouched
+            fused.append(op)
+        return fused
 
     # ------------------------------------------------------------------ lowering
     def _lower(self):
         lib = self.lib
         B = self.B
         pending = []
-        for idx, op in enumerate(self.plan.ops):
+        for idx, op in enumerate(self.ops):
             if isinstance(op, P.ConvOp):
                 a = L.ConvArgs()
                 a.B, a.H, a.W, a.nseg = B, op.H, op.W, len(op.segs)
@@ -143,15 +217,26 @@ class Engine:
                 if op.res2 is not None:
                     a.res2, a.res2_ld = self._vptr(op.res2)
                     a.alpha2 = op.alpha2
+                if op.pre is not None:
+                    a.pre, a.pre_ld = self._vptr(op.pre)
+                if op.step is not None:
+                    stp = L.ConvStep()
+                    stp.z, stp.z_ld = self._vptr(op.step.z)
+                    stp.C, stp.n_pass = op.step.z.C, op.step.n_pass
+                    stp.w = self.weights[op.step.w].data_ptr() if op.step.w else None
+                    stp.an_scale = self.weights[op.step.an_scale].data_ptr()
+                    stp.an_bias = self.weights[op.step.an_bias].data_ptr()
+                    self._step_structs[id(op)] = stp
+                    self._keep.append(stp)
+                    a.step = C.pointer(stp)
                 self._keep.append(a)
                 cin = sum(v.C for v, _ in op.segs)
                 flops = 2.0 * B * op.H * op.W * op.ks * op.ks * cin * op.cout
                 tag = "{}@{}x{}".format(op.tag, op.H, op.W)
                 if self._tc_eligible(a):
                     pending.append((op, a, flops, tag))
-                    nxt = self.plan.ops[idx + 1] if idx + 1 < len(self.plan.ops) else None
-                    same = (isinstance(nxt, P.ConvOp) and self.use_chains and nxt.ks == 3 and op.ks == 3
-                            and (nxt.H, nxt.W) == (op.H, op.W))
+                    nxt = self.ops[idx + 1] if idx + 1 < len(self.ops) else None
+                    same = (isinstance(nxt, P.ConvOp) and self.use_chains and (nxt.H, nxt.W) == (op.H, op.W))
                     if not same:
                         self._flush_tc(pending)
                         pending = []
@@ -230,6 +315,19 @@ class Engine:
             else:
                 raise TypeError(op)
         self._flush_tc(pending)
+        if self._flag_used:
+            pool, used = self._flag_pool, self._flag_used
+            self.calls.insert(0, (lambda _a, _s: (pool[:used].zero_(), 0)[1], None, "flags_zero"))
+            self.call_info.insert(0, {"cls": "flags_zero", "tag": "flags_zero", "flops": 0.0, "convs": 0})
+
+    def _alloc_flags(self, n):
+        if self._flag_pool is None:
+            self._flag_pool = torch.zeros(1 << 20, dtype=torch.int32, device=self.device)
+        n = (n + 31) // 32 * 32
+        assert self._flag_used + n <= self._flag_pool.numel(), "dependency-counter pool exhausted"
+        t = self._flag_pool[self._flag_used:self._flag_used + n]
+        self._flag_used += n
+        return t
 
     def _add_call(self, fn, arg, cls, tag="", flops=0.0, convs=0):
         self.calls.append((fn, arg, cls))
@@ -260,7 +358,7 @@ class Engine:
     def _tc_weights(self, op, passes):
         key = self._wkey(op) + "#tc{}".format(passes)
         if key not in self.weights:
-            w = prep.pad_weight_for_tc(self._sd_cpu[op.weight], [v.C for v, _ in op.segs])
+            w = prep.pad_weight_for_tc(self._raw_weight(op), [v.C for v, _ in op.segs])
             cout, kin, ks = w.shape[0], w.shape[1], w.shape[2]
             nbytes = self.lib.hcf_conv_tc_weight_bytes(kin, cout, ks, passes)
             img = torch.zeros(nbytes // 4, dtype=torch.float32)
@@ -272,7 +370,8 @@ class Engine:
     @staticmethod
     def _reads(op):
         if isinstance(op, P.ConvOp):
-            return [v for v, _ in op.segs] + [v for v in (op.res1, op.res2) if v is not None]
+            return ([v for v, _ in op.segs] + [v for v in (op.res1, op.res2) if v is not None]
+                    + ([op.step.z] if op.step is not None else []))
         if isinstance(op, P.StepOp):
             return [v for v in (op.z, op.h) if v is not None]
         if isinstance(op, P.PriorOp):
@@ -295,7 +394,7 @@ class Engine:
     def _tc16_weights(self, op, passes):
         key = self._wkey(op) + "#tc16_{}".format(passes)
         if key not in self.weights:
-            w = prep.pad_weight_for_tc(self._sd_cpu[op.weight], [v.C for v, _ in op.segs], chunk=64)
+            w = prep.pad_weight_for_tc(self._raw_weight(op), [v.C for v, _ in op.segs], chunk=64)
             cout, kin, ks = w.shape[0], w.shape[1], w.shape[2]
             nbytes = self.lib.hcf_conv_tc16_weight_bytes(kin, cout, ks, passes)
             img = torch.zeros(nbytes // 2, dtype=torch.float16)
@@ -303,17 +402,42 @@ class Engine:
             self.weights[key] = img.to(self.device)
         return self.weights[key]
 
+    @staticmethod
+    def _writes(op):
+        if isinstance(op, P.ConvOp):
+            if op.step is not None:    # h is consumed in the epilogue, z is updated in place
+                return [op.step.z]
+            return [v for v in (op.out, op.out2) if v is not None]
+        if isinstance(op, P.StepOp):
+            return [op.z]
+        if isinstance(op, P.PriorOp):
+            return [op.z] if op.variant == "sample" else []
+        if isinstance(op, P.LayoutOp):
+            return [op.dst] if isinstance(op.dst, P.View) else []
+        return []
+
+    def _read_later(self, view, after_idx):
+        """Is `view` (written by a chain conv) read by an op after position `after_idx` before it is fully
+        overwritten?  (buffers are reused by later steps, so a plain overlap test would be too conservative)"""
+        for o in self.ops[after_idx + 1:]:
+            rd = self._reads(o) + ([o.pre] if isinstance(o, P.ConvOp) and o.pre is not None else [])
+            if any(self._overlap(v, view) for v in rd):
+                return True
+            if any(w.buf.name == view.buf.name and w.off <= view.off and w.off + w.C >= view.off + view.C
+                   for w in self._writes(o)):
+                return False
+        return False
+
     def _try_chain16(self, pending):
         """One persistent chained launch on fp16 operands (include/hcflow_b200.h, hcf_conv_chain16_create).
         Returns False (nothing emitted) when a conv of the run does not qualify."""
         lib = self.lib
         n = len(pending)
         ops = [p[0] for p in pending]
-        if not all(lib.hcf_conv_tc16_supported(C.byref(p[1])) for p in pending):
+        if not all(lib.hcf_conv_tc_supported(C.byref(p[1])) for p in pending):
             return False
         passes = [self._passes_for(op) for op in ops]
-        chain_ids = {id(op) for op in ops}
-        others = [o for o in self.plan.ops if id(o) not in chain_ids]
+        last_idx = max(i for i, o in enumerate(self.ops) if o is ops[-1])
         flags = []
         for k, op in enumerate(ops):
             outs = [v for v in (op.out, op.out2) if v is not None]
@@ -322,28 +446,66 @@ class Engine:
                 if any(self._overlap(v, o) for v, _ in ops[j].segs for o in outs):
                     hi = True
                     lo = lo or passes[j] == 3
-            for j in range(n):   # residual sources stay fp32
-                if any(self._overlap(v, o) for v in (ops[j].res1, ops[j].res2) if v is not None for o in outs):
+            for j in range(n):   # residual sources and pre-activation addends stay fp32
+                if any(self._overlap(v, o) for v in (ops[j].res1, ops[j].res2, ops[j].pre) if v is not None for o in outs):
                     f32 = True
-            if any(self._overlap(v, o) for other in others for v in self._reads(other) for o in outs):
+            if any(self._read_later(o, last_idx) for o in outs):
                 f32 = True
             if not (hi or f32):
                 f32 = True
             flags.append((L.OUT_F32 if f32 else 0) | (L.OUT_HI if hi else 0) | (L.OUT_LO if lo else 0))
-        # inputs that no conv of the chain produced: converted to hi / lo right before the launch
+        # inputs that no conv of the chain produced: converted to hi / lo right before the launch.  Views whose
+        # geometry breaks TMA's 16-byte rules in fp16 (ld % 8, offset % 8) go through a private padded staging pair.
         external = {}
+        seg16 = (L.Seg16 * (3 * n))()
+        staged = {}
+        loc16 = {}     # (buffer, offset, C) -> (hi pointer, row pitch) of the fp16 copy the convs read
         for k, op in enumerate(ops):
-            for v, _ in op.segs:
-                produced = any(self._overlap(v, o) for j in range(k) for o in (ops[j].out, ops[j].out2) if o is not None)
-                if not produced:
-                    # the lo plane is needed as soon as ANY split conv of the chain reads these channels (e.g. the
-                    # first RDB's conv5 reads x0 inside a wider view that is otherwise produced by the chain)
-                    need_lo = any(passes[j] == 3 and any(self._overlap(v, s) for s, _ in ops[j].segs) for j in range(n))
-                    external[(v.buf.name, v.off, v.C)] = (v, need_lo)
+            for si, (v, _) in enumerate(op.segs):
+                by_conv = any(self._overlap(v, o) for j in range(k) if ops[j].step is None
+                              for o in (ops[j].out, ops[j].out2) if o is not None)
+                by_step = any(ops[j].step is not None and self._overlap(v, ops[j].step.z) for j in range(k))
+                aligned = v.buf.C % 8 == 0 and v.off % 8 == 0
+                key = (v.buf.name, v.off, v.C)
+                if by_conv and not aligned:
+                    return False
+                if not aligned:
+                    if key not in staged:
+                        ldp = (v.C + 7) // 8 * 8
+                        name = "stage16_{}_{}_{}".format(*key)
+                        if name not in self.shadow16:
+                            self.shadow16[name] = tuple(torch.zeros(self.B, op.H, op.W, ldp, dtype=torch.float16,
+                                                                    device=self.device) for _ in range(2))
+                        staged[key] = (self.shadow16[name], ldp)
+                    (hi_t, lo_t), ldp = staged[key]
+                    e = seg16[3 * k + si]
+                    e.hi, e.lo, e.ld = hi_t.data_ptr(), lo_t.data_ptr(), ldp
+                    loc16[key] = (hi_t.data_ptr(), ldp)
+                else:
+                    loc16[key] = (self._shadow(v.buf)[0].data_ptr() + 2 * v.off, v.buf.C)
+                # the lo plane is needed as soon as ANY split conv of the chain reads these channels (e.g. the
+                # first RDB's conv5 reads x0 inside a wider view that is otherwise produced by the chain)
+                need_lo = any(passes[j] == 3 and any(self._overlap(v, s) for s, _ in ops[j].segs) for j in range(n))
+                if by_step and need_lo:
+                    return False           # fused steps write the hi plane only
+                if not (by_conv or by_step) and key not in external:
+                    external[key] = (v, need_lo, staged.get(key))
+        for op in ops:   # where each fused FlowStep leaves the fp16 copy of z[:, :n_pass] for the next step's first conv
+            if op.step is not None:
+                stp = self._step_structs[id(op)]
+                z = op.step.z
+                tgt = loc16.get((z.buf.name, z.off, op.step.n_pass))
+                stp.z16_hi, stp.z16_ld = (tgt[0], tgt[1]) if tgt else (None, 0)
         bufs = {}
-        for op in ops:
-            for v in [s for s, _ in op.segs] + [o for o in (op.out, op.out2) if o is not None]:
-                bufs[v.buf.name] = v.buf
+        for k, op in enumerate(ops):
+            for si, (v, _) in enumerate(op.segs):
+                if not seg16[3 * k + si].hi:
+                    bufs[v.buf.name] = v.buf
+            for v in (op.out, op.out2):
+                if v is not None and flags[k] & (L.OUT_HI | L.OUT_LO):
+                    bufs[v.buf.name] = v.buf
+        if not bufs:   # the API wants at least one registered buffer
+            bufs[ops[0].out.buf.name] = ops[0].out.buf
         sh = (L.Shadow16 * len(bufs))()
         for i, b in enumerate(bufs.values()):
             hi_t, lo_t = self._shadow(b)
@@ -360,28 +522,35 @@ class Engine:
             wptr[i] = self._tc16_weights(op, passes[i]).data_ptr()
         op0 = ops[0]
         tiles = self.B * ((op0.H + 15) // 16) * ((op0.W + 7) // 8)
-        done = torch.zeros(tiles, dtype=torch.int32, device=self.device)
+        done = self._alloc_flags(tiles)
         handle = C.c_void_p()
-        rc = lib.hcf_conv_chain16_create(arr, wptr, lp, of, n, done.data_ptr(), sh, len(bufs), C.byref(handle))
+        rc = lib.hcf_conv_chain16_create(arr, wptr, lp, of, n, done.data_ptr(), sh, len(bufs), seg16, C.byref(handle))
         if rc == -2:
             return False
         L.check(rc, "conv_chain16_create")
-        self._keep += [arr, wptr, lp, of, sh, done]
+        self._keep += [arr, wptr, lp, of, sh, seg16, done]
         self._tc_plans.append(handle)
         npix = self.B * op0.H * op0.W
-        for v, need_lo in external.values():
-            hi_t, lo_t = self._shadow(v.buf)
+        for v, need_lo, st in external.values():
             src = self.bufs[v.buf.name].data_ptr() + 4 * v.off
-            hi_p, lo_p = hi_t.data_ptr() + 2 * v.off, (lo_t.data_ptr() + 2 * v.off) if need_lo else None
+            if st is None:
+                hi_t, lo_t = self._shadow(v.buf)
+                hi_p, lo_p, dld = hi_t.data_ptr() + 2 * v.off, lo_t.data_ptr() + 2 * v.off, v.buf.C
+            else:
+                (hi_t, lo_t), dld = st
+                hi_p, lo_p = hi_t.data_ptr(), lo_t.data_ptr()
+            if not need_lo:
+                lo_p = None
 
-            def conv_in(_a, stream, src=src, ld=v.buf.C, c=v.C, hi_p=hi_p, lo_p=lo_p):
-                return lib.hcf_split16(src, ld, c, npix, hi_p, lo_p, stream)
+            def conv_in(_a, stream, src=src, ld=v.buf.C, c=v.C, hi_p=hi_p, lo_p=lo_p, dld=dld):
+                return lib.hcf_split16(src, ld, c, npix, hi_p, lo_p, dld, stream)
             self._add_call(conv_in, None, "layout_split16")
-        self._add_call(lambda _a, _s, f=done: (f.zero_(), 0)[1], None, "flags_zero")
-        self._add_call(lib.hcf_conv_tc_run, handle, "conv_tc_chain",
-                       "chain16[{}..{}]x{}".format(pending[0][3], pending[-1][3], n), sum(p[2] for p in pending), n)
+        self._add_call(lib.hcf_conv_tc_run, handle, "conv_tc_chain" if n > 1 else "conv_tc",
+                       "chain16[{}..{}]x{}".format(pending[0][3], pending[-1][3], n) if n > 1 else pending[0][3] + "#16",
+                       sum(p[2] for p in pending), n)
         self.n_tc += n
-        self.n_chains += 1
+        if n > 1:
+            self.n_chains += 1
         self.n_chains16 += 1
         return True
 
@@ -391,8 +560,11 @@ class Engine:
         if not pending:
             return
         lib = self.lib
-        if len(pending) > 1 and self.precision in ("f16", "f16x3") and self._try_chain16(pending):
+        if self.precision in ("f16", "f16x3") and self._try_chain16(pending):
             return
+        for op, _, _, _ in pending:   # fp32-operand kernels read z itself
+            if op.step is not None:
+                self._step_structs[id(op)].z16_hi = None
         if len(pending) > 1:
             n = len(pending)
             arr = (L.ConvArgs * n)()
@@ -404,13 +576,12 @@ class Engine:
                 wptr[i] = self._tc_weights(op, lp[i]).data_ptr()
             op0 = pending[0][0]
             tiles = self.B * ((op0.H + 15) // 16) * ((op0.W + 7) // 8)
-            flags = torch.zeros(tiles, dtype=torch.int32, device=self.device)
+            flags = self._alloc_flags(tiles)
             handle = C.c_void_p()
             rc = lib.hcf_conv_chain_create(arr, wptr, lp, n, flags.data_ptr(), C.byref(handle))
             if rc == 0:
                 self._keep += [arr, wptr, lp, flags]
                 self._tc_plans.append(handle)
-                self._add_call(lambda _a, _s, f=flags: (f.zero_(), 0)[1], None, "flags_zero")
                 flops = sum(p[2] for p in pending)
                 self._add_call(lib.hcf_conv_tc_run, handle, "conv_tc_chain",
                                "chain[{}..{}]x{}".format(pending[0][3], pending[-1][3], n), flops, n)

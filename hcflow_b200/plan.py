@@ -56,6 +56,12 @@ class ConvOp:
     res2: Optional[View] = None
     alpha2: float = 1.0
     tag: str = ""
+    # engine-level rewrites only (engine.py, shared conditioning of the coupling sub-nets): `weight` may be a
+    # tuple of keys (concatenated along Cout), `w_in` an input-channel slice of it, `pre` an fp32 view added to
+    # the accumulator before bias / scale / activation
+    w_in: Optional[Tuple[int, int]] = None
+    pre: Optional[View] = None
+    step: Optional[object] = None   # a StepOp("inverse") executed by this conv's epilogue (fused FlowStep tail)
 
 
 @dataclass

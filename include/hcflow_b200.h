@@ -58,7 +58,7 @@ typedef struct {
 
 /* Stride-1 "same" convolution, ks in {1,3}, over the channel-concatenation of up to three
  * segments, with a fused epilogue:
- *     v = acc; v = (v + bias[c]) * scale[c]; v = act(v);
+ *     v = acc (+ pre); v = (v + bias[c]) * scale[c]; v = act(v);
  *     if (res1) v = v*alpha1 + res1;  if (res2) v = v*alpha2 + res2;
  *     out = v; if (out2) out2 = v;
  * Replaces nn.Conv2d / F.conv2d + the elementwise ops around it:
@@ -69,6 +69,25 @@ typedef struct {
  * Weights are pre-packed as w[tap][k][n]: tap = ky*ks+kx, k runs over the segments with
  * each segment zero-padded to a multiple of 8 channels (kpad = total), n < npad where
  * npad is 16, 32 or a multiple of 64 and >= cout.  bias / scale have npad entries. */
+/* Optional FlowStep tail of a conv (tensor-core chains only): the conv is the last layer of a coupling sub-net
+ * and its output h is consumed in the epilogue instead of being stored (FlowStep.py:55-64, reverse):
+ *     z[n_pass + j] = z[n_pass + j] * exp(-0.318 * atan(2 * h[2j+1])) - h[2j]     (AffineCouplings.py:73-87)
+ *     z = W^-1 z                                                                  (Permutations.py:103-108)
+ *     z = z * an_scale - an_bias                                                  (ActNorms.py:66-69)
+ * in place on the NHWC view z (C <= 24 channels, cout == 2 * (C - n_pass) <= 32).  Replaces a separate
+ * hcf_step_inverse launch; lets the convs of consecutive FlowSteps run as one chain. */
+typedef struct {
+  float* z;
+  int32_t z_ld;
+  int32_t C;
+  int32_t n_pass;
+  int32_t z16_ld;
+  const float* w;        /* W^-1 [C][C] row-major, or NULL (no permutation) */
+  const float* an_scale; /* exp(-logs) [C] */
+  const float* an_bias;  /* [C] */
+  void* z16_hi;          /* optional: fp16 copy of the new z[:, :n_pass], row pitch z16_ld (fp16 chains) */
+} hcf_conv_step;
+
 typedef struct {
   int32_t B, H, W;
   int32_t nseg;
@@ -91,7 +110,11 @@ typedef struct {
   int32_t res2_ld;
   float alpha1;
   float alpha2;
-  int32_t _pad;
+  int32_t pre_ld;
+  const float* pre; /* may be NULL; tensor-core kernels only: fp32 NHWC view [B,H,W,>=cout] added to the
+                       accumulator BEFORE bias / scale / activation (the part of a conv over an input that is
+                       shared by several convs, computed once by another conv); excludes res1 / res2 */
+  const hcf_conv_step* step; /* may be NULL; host pointer, read when the plan is created */
 } hcf_conv_args;
 
 /* fp32 CUDA-core (FFMA) implementation: exact-fp32 parity mode and odd shapes. */
@@ -142,11 +165,19 @@ typedef struct {
 int hcf_conv_tc16_supported(const hcf_conv_args* a);
 int64_t hcf_conv_tc16_weight_bytes(int32_t kin, int32_t cout, int32_t ks, int32_t passes);
 int hcf_conv_tc16_pack_weights(const float* w_oihw, int32_t kin, int32_t cout, int32_t ks, int32_t passes, void* image);
+/* seg16 (may be NULL): n x 3 explicit fp16 views for input segments whose fp32 geometry does not satisfy TMA's
+ * 16-byte rules in fp16 (ld % 8, channel offset % 8): entries with hi != NULL replace the shadow lookup. */
+typedef struct {
+  const void* hi;
+  const void* lo;
+  int32_t ld;
+  int32_t _pad;
+} hcf_seg16;
 int hcf_conv_chain16_create(const hcf_conv_args* args, const void* const* w16, const int32_t* layer_passes,
                             const int32_t* out_flags, int32_t n, int32_t* done_flags, const hcf_shadow16* shadows,
-                            int32_t n_shadows, hcf_conv_tc_plan** out);
-/* fp32 NHWC view (ld, C, npix pixels) -> hi / lo planes at the same element offsets (lo may be NULL) */
-int hcf_split16(const float* src, int32_t ld, int32_t C, int64_t npix, void* hi, void* lo, void* stream);
+                            int32_t n_shadows, const hcf_seg16* seg16, hcf_conv_tc_plan** out);
+/* fp32 NHWC view (ld, C, npix pixels) -> hi / lo planes with row pitch dst_ld (lo may be NULL) */
+int hcf_split16(const float* src, int32_t ld, int32_t C, int64_t npix, void* hi, void* lo, int32_t dst_ld, void* stream);
 int32_t hcf_conv_tc_plan_layers(const hcf_conv_tc_plan* p);
 int hcf_conv_tc_run(const hcf_conv_tc_plan* p, void* stream);
 void hcf_conv_tc_plan_destroy(hcf_conv_tc_plan* p);

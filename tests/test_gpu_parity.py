@@ -413,8 +413,8 @@ def _rdb_chain16(B, H, W, passes, seed=0):
     tiles = B * ((H + 15) // 16) * ((W + 7) // 8)
     done = torch.zeros(tiles, dtype=torch.int32, device="cuda")
     h = C.c_void_p()
-    L.check(lib.hcf_conv_chain16_create(arr, wptr, lp, of, n, done.data_ptr(), sh, 2, C.byref(h)), "chain16_create")
-    L.check(lib.hcf_split16(X.data_ptr(), 192, 64, B * H * W, planes[0].data_ptr(), planes[1].data_ptr(), st), "split16")
+    L.check(lib.hcf_conv_chain16_create(arr, wptr, lp, of, n, done.data_ptr(), sh, 2, None, C.byref(h)), "chain16_create")
+    L.check(lib.hcf_split16(X.data_ptr(), 192, 64, B * H * W, planes[0].data_ptr(), planes[1].data_ptr(), 192, st), "split16")
     L.check(lib.hcf_conv_tc_run(h, st), "chain16_run")
     torch.cuda.synchronize()
     lib.hcf_conv_tc_plan_destroy(h)
@@ -469,3 +469,123 @@ def test_chain16_full_size_is_deterministic_and_close_to_fp32_path(precision, re
     err = float((outs[0] - want).abs().max())
     report["chain16_full/{}".format(precision)] = {"max_vs_tf32x3": err, "chains16": eng.n_chains16}
     assert err < E2E_TOL[precision], err
+
+
+# ------------------------------------------------------------------------------ coupling sub-net as one chain
+def _fcn_chain(kind, B, H, W, zc=6, cond=128, hidden=64, cout=12, seed=0):
+    """FCN(cat(z1, u)) (Basic.py:426-447) the way the engine lowers it in the tensor-core modes: the W_u * u part of
+    conv1 by a separate conv (`pre` of the z-only conv1), then ONE chained launch conv3x3 -> conv1x1 -> conv3x3
+    (mixed kernel sizes; fp16 variant: z1 through a padded fp16 staging pair).  Returns (got, fp64 reference)."""
+    from hcflow_b200 import prep
+    lib = L.load()
+    st = torch.cuda.current_stream().cuda_stream
+    f16 = kind == "f16"
+    z1 = _rand(B, zc, H, W, seed=seed)
+    u = _rand(B, cond, H, W, seed=seed + 1, scale=0.5)
+    w1 = _rand(hidden, zc + cond, 3, 3, seed=seed + 2, scale=1.0 / math.sqrt((zc + cond) * 9))
+    w2 = _rand(hidden, hidden, 1, 1, seed=seed + 3, scale=1.0 / math.sqrt(hidden))
+    w3 = _rand(cout, hidden, 3, 3, seed=seed + 4, scale=1.0 / math.sqrt(hidden * 9))
+    bs = [_rand(c, seed=seed + 5 + i, scale=0.1) for i, c in enumerate((hidden, hidden, cout))]
+    sc = [torch.exp(_rand(c, seed=seed + 8 + i, scale=0.2)) for i, c in enumerate((hidden, hidden, cout))]
+    zld = (zc + 3) // 4 * 4
+    Z = torch.zeros(B, H, W, zld, dtype=torch.float32, device="cuda")
+    Z[..., :zc] = z1.cuda().permute(0, 2, 3, 1)
+    U = u.cuda().permute(0, 2, 3, 1).contiguous()
+    UB = torch.zeros(B, H, W, hidden, dtype=torch.float32, device="cuda")    # W_u * u
+    H1 = torch.zeros(B, H, W, hidden, dtype=torch.float32, device="cuda")
+    H2 = torch.zeros(B, H, W, hidden, dtype=torch.float32, device="cuda")
+    old = (cout + 3) // 4 * 4
+    OUT = torch.zeros(B, H, W, old, dtype=torch.float32, device="cuda")
+    keep = []
+
+    def args(src, ld, cin, w, ks, co, bias, scale, act, out, out_ld, pre=None):
+        a = L.ConvArgs()
+        a.B, a.H, a.W, a.nseg = B, H, W, 1
+        a.seg[0].ptr, a.seg[0].ld, a.seg[0].C, a.seg[0].up_shift = src.data_ptr(), ld, cin, 0
+        npad = prep.npad_for(co)
+        a.ks, a.kpad, a.cout, a.npad = ks, prep.seg_pad(cin), co, npad
+        wp = prep.pack_conv_weight(w, [cin], npad).cuda()
+        a.w = wp.data_ptr()
+        keep.append(wp)
+        if bias is not None:
+            bp, sp = prep.pad_vec(bias, npad, 0.0).cuda(), prep.pad_vec(scale, npad, 1.0).cuda()
+            keep.extend([bp, sp])
+            a.bias, a.scale = bp.data_ptr(), sp.data_ptr()
+        a.act = act
+        a.out, a.out_ld = out.data_ptr(), out_ld
+        if pre is not None:
+            a.pre, a.pre_ld = pre.data_ptr(), pre.shape[3]
+        return a
+
+    def wimg(w, cin, passes=1):
+        co, ks = w.shape[0], w.shape[2]
+        if f16:
+            wt = prep.pad_weight_for_tc(w, [cin], chunk=64)
+            img = torch.zeros(lib.hcf_conv_tc16_weight_bytes(wt.shape[1], co, ks, passes) // 2, dtype=torch.float16)
+            L.check(lib.hcf_conv_tc16_pack_weights(wt.data_ptr(), wt.shape[1], co, ks, passes, img.data_ptr()), "pack16")
+        else:
+            wt = prep.pad_weight_for_tc(w, [cin])
+            img = torch.zeros(lib.hcf_conv_tc_weight_bytes(wt.shape[1], co, ks, passes) // 4, dtype=torch.float32)
+            L.check(lib.hcf_conv_tc_pack_weights(wt.data_ptr(), wt.shape[1], co, ks, passes, img.data_ptr()), "pack")
+        img = img.cuda()
+        keep.append(img)
+        return img.data_ptr()
+
+    def run_chain(alist, wlist, oflags, planes, seg16):
+        n = len(alist)
+        arr = (L.ConvArgs * n)(*alist)
+        wptr = (C.c_void_p * n)(*wlist)
+        lp = (C.c_int32 * n)(*([1] * n))
+        tiles = B * ((H + 15) // 16) * ((W + 7) // 8)
+        done = torch.zeros(tiles, dtype=torch.int32, device="cuda")
+        h = C.c_void_p()
+        if f16:
+            of = (C.c_int32 * n)(*oflags)
+            sh = (L.Shadow16 * len(planes))()
+            for i, (t, hi, lo) in enumerate(planes):
+                sh[i].f32, sh[i].bytes, sh[i].hi, sh[i].lo = t.data_ptr(), t.numel() * 4, hi.data_ptr(), lo.data_ptr()
+            L.check(lib.hcf_conv_chain16_create(arr, wptr, lp, of, n, done.data_ptr(), sh, len(planes), seg16,
+                                                C.byref(h)), "chain16_create")
+        else:
+            L.check(lib.hcf_conv_chain_create(arr, wptr, lp, n, done.data_ptr(), C.byref(h)), "chain_create")
+        L.check(lib.hcf_conv_tc_run(h, st), "chain_run")
+        torch.cuda.synchronize()
+        lib.hcf_conv_tc_plan_destroy(h)
+
+    def pl(t):
+        return (t, torch.zeros(t.shape, dtype=torch.float16, device="cuda"), torch.zeros(t.shape, dtype=torch.float16, device="cuda"))
+
+    pU, pH1, pH2 = pl(U), pl(H1), pl(H2)
+    # 1) W_u * u (no bias / activation) -> UB
+    if f16:
+        L.check(lib.hcf_split16(U.data_ptr(), cond, cond, B * H * W, pU[1].data_ptr(), None, cond, st), "split16")
+    run_chain([args(U, cond, cond, w1[:, zc:].contiguous(), 3, hidden, None, None, 0, UB, hidden)],
+              [wimg(w1[:, zc:].contiguous(), cond)], [L.OUT_F32], [pU], None)
+    # 2) conv1(z1) + UB -> ActNorm, ReLU -> conv2 1x1 -> ActNorm, ReLU -> conv3 (bias, scale)
+    seg16 = None
+    if f16:
+        zhi = torch.zeros(B, H, W, 8, dtype=torch.float16, device="cuda")
+        L.check(lib.hcf_split16(Z.data_ptr(), zld, zc, B * H * W, zhi.data_ptr(), None, 8, st), "split16")
+        seg16 = (L.Seg16 * 9)()
+        seg16[0].hi, seg16[0].lo, seg16[0].ld = zhi.data_ptr(), None, 8
+        keep.append(zhi)
+    a1 = args(Z, zld, zc, w1[:, :zc].contiguous(), 3, hidden, bs[0], sc[0], 1, H1, hidden, pre=UB)
+    a2 = args(H1, hidden, hidden, w2, 1, hidden, bs[1], sc[1], 1, H2, hidden)
+    a3 = args(H2, hidden, hidden, w3, 3, cout, bs[2], sc[2], 0, OUT, old)
+    run_chain([a1, a2, a3], [wimg(w1[:, :zc].contiguous(), zc), wimg(w2, hidden), wimg(w3, hidden)],
+              [L.OUT_HI, L.OUT_HI, L.OUT_F32], [pH1, pH2], seg16)
+    x = torch.cat((z1, u), 1).double()
+    y = F.relu((F.conv2d(x, w1.double(), None, padding=1) + bs[0].double().view(1, -1, 1, 1)) * sc[0].double().view(1, -1, 1, 1))
+    y = F.relu((F.conv2d(y, w2.double()) + bs[1].double().view(1, -1, 1, 1)) * sc[1].double().view(1, -1, 1, 1))
+    y = (F.conv2d(y, w3.double(), None, padding=1) + bs[2].double().view(1, -1, 1, 1)) * sc[2].double().view(1, -1, 1, 1)
+    return OUT[..., :cout].permute(0, 3, 1, 2).cpu(), y
+
+
+@pytest.mark.parametrize("kind", ["tf32", "f16"])
+@pytest.mark.parametrize("shape", [(2, 40, 40), (1, 19, 11)], ids=["40x40", "partial_tiles"])
+def test_fcn_as_one_chain_with_shared_conditioning(kind, shape, report):
+    B, H, W = shape
+    got, ref = _fcn_chain(kind, B, H, W)
+    err = maxabs(got, ref)
+    report["fcn_chain/{}/{}x{}".format(kind, H, W)] = err
+    assert err < (1e-2 if kind == "tf32" else 4e-3), (kind, err)
