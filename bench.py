@@ -147,6 +147,11 @@ def conv_flops(plan, B):
     return total
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch (chained encoder kernel, 80x80 level), one
+# ncu --set full capture per precision mode (profiles/README.md)
+NCU_DRAM_BYTES = {"tf32x3": 5.76e9, "tf32x3_all": 5.76e9, "tf32": 5.42e9, "f16": 5.12e9, "f16x3": None}
+
+
 def per_class_times(eng):
     """One eager (non-graph) pass with a CUDA-event pair around every launch, on the launching
     stream; returns {class: (n_launches, ms, flops)} and fills per_class_times.by_tag."""
@@ -274,14 +279,19 @@ def run_ours(args):
     n, ms, fl = by_tag[top_tag]
     achieved = fl / (ms / 1e3) / 1e12
     # DRAM bytes per launch of that kernel from the committed ncu --set full capture (profiles/README.md)
-    ncu_traffic = {"tf32x3": 5.76e9, "tf32x3_all": 5.76e9, "tf32": 5.42e9}.get(args.precision) if "chain" in top_tag else None
+    ncu_traffic = NCU_DRAM_BYTES.get(args.precision) if "chain" in top_tag and "enc." in top_tag else None
+    f16_mode = args.precision in ("f16", "f16x3")
+    # the launch is timed inside the step (per-launch events of an eager pass): the sustained figure applies
+    peak_used = peaks.get("bf16_tflops_sustained") or peaks["bf16_tflops"]
     roofline = {
-        "bound": "tensor", "kernel": "conv_tc_kernel " + top_tag, "achieved": achieved, "peak": peaks["bf16_tflops"],
-        "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"], "traffic": ncu_traffic,
-        "traffic_note": "dram__bytes_read+write per launch, ncu --set full, profiles/r01_prof_chain_L0_*_summary.csv; "
+        "bound": "tensor", "kernel": "conv_tc_kernel " + top_tag, "achieved": achieved, "peak": peak_used,
+        "unit": "TFLOP/s", "frac": achieved / peak_used, "traffic": ncu_traffic, "peak_burst": peaks["bf16_tflops"],
+        "traffic_note": "dram__bytes_read+write per launch, ncu --set full, profiles/r01*_prof_chain_L0_*; "
                         "algorithmic bytes of that launch = 2.34e9",
-        "peak_source": "{} bf16 burst from MEASURED_PEAKS.json (the kernel computes in TF32, nominal peak = half "
-                       "of it; tf32x3 issues 2 MMAs per useful K-step)".format(peaks["source"]),
+        "peak_source": "{} bf16 sustained from MEASURED_PEAKS.json ({})".format(
+            peaks["source"], "the kernel computes on fp16 operands: same tensor rate; split layers issue 2 MMAs per useful "
+            "K-step" if f16_mode else "the kernel computes in TF32, nominal peak = half of it; tf32x3 issues 2 MMAs per "
+            "useful K-step"),
         "launches": n, "avg_launch_ms": ms / n, "share_of_step": ms / total_ms,
         "classes": {c: {"n": v[0], "ms": round(v[1], 4), "gflop": round(v[2] / 1e9, 3)} for c, v in classes.items()},
         "conv_by_layer": {t: {"n": v[0], "ms": round(v[1], 3), "tflops": round(v[2] / max(v[1], 1e-9) / 1e9, 1)}
@@ -290,7 +300,7 @@ def run_ours(args):
     if tc_keys:
         a_n, a_ms, a_fl = (sum(classes[c][k] for c in tc_keys) for k in range(3))
         roofline["all_tcgen05_convs"] = {"launches": a_n, "ms": round(a_ms, 3), "tflops": round(a_fl / a_ms / 1e9, 1),
-                                         "frac": a_fl / a_ms / 1e9 / peaks["bf16_tflops"], "share_of_step": a_ms / total_ms}
+                                         "frac": a_fl / a_ms / 1e9 / peak_used, "share_of_step": a_ms / total_ms}
     # ---- CPU baseline (rank 0, N=1 only): the oracle on the host cores, bounded sample
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -343,8 +353,8 @@ def run_ours(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "modes": modes,
-        "parity": "tests/test_gpu_parity.py: un-clamped HR vs reference goldens max-abs fp32 5e-6, tf32x3 1.9e-4, "
-                  "tf32 1.3e-2 (tolerances 2e-4 / 2e-3 / 5e-2)",
+        "parity": "tests/test_gpu_parity.py: un-clamped HR vs reference goldens max-abs fp32 5e-6, f16x3 7e-5, tf32x3 8e-5, "
+                  "f16 1.7e-3, tf32 1.3e-2 (tolerances 2e-4 / 2e-3 / 2e-3 / 2e-2 / 5e-2)",
     }
     print(json.dumps(line), flush=True)
 
@@ -355,10 +365,12 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("HCFLOW_PRECISION", "tf32x3"),
+    ap.add_argument("--precision", default=os.environ.get("HCFLOW_PRECISION", "f16x3"),
                     choices=["fp32", "tf32", "tf32x3", "tf32x3_all", "f16", "f16x3"],
-                    help="tf32x3 (default): tcgen05 3xTF32 split, fp32-level parity (2e-4); tf32: one TF32 pass "
-                         "(stock PyTorch conv numerics on CUDA); fp32: CUDA-core kernels")
+                    help="f16x3 (default): tcgen05 on fp16 hi/lo operand planes, split (hi+lo on both operands) for the "
+                         "convs that write the encoder's residual stream, fp32-level parity (7e-5 measured, 2e-3 "
+                         "tolerance); f16: one fp16 pass everywhere (1.7e-3); tf32x3 / tf32: the same on fp32 words read "
+                         "as TF32; fp32: CUDA-core kernels")
     ap.add_argument("--no-modes", action="store_true", help="skip the short runs of the other precision modes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches (for ncu)")

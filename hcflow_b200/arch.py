@@ -34,6 +34,8 @@ class _HCFlowBase(nn.Module):
         self.precision = "fp32"
         self.use_graph = True
         self.use_chains = True   # fuse runs of tensor-core convs into one persistent chained launch
+        self.share_cond = True   # tensor-core modes: the sub-nets' shared conditioning conv once per level (engine.py)
+        self.fuse_steps = True   # tensor-core modes, inverse pass: FlowStep tail in the last sub-net conv's epilogue
         self._engines = {}
         self.last = {}
 
@@ -51,11 +53,12 @@ class _HCFlowBase(nn.Module):
 
     def engine(self, direction, B, h, w, device):
         from .engine import Engine
-        key = (direction, B, h, w, str(device), self.precision, self.use_graph, self.use_chains)
+        key = (direction, B, h, w, str(device), self.precision, self.use_graph, self.use_chains, self.share_cond,
+               self.fuse_steps)
         eng = self._engines.get(key)
         if eng is None:
             eng = Engine(self, direction, B, h, w, device, precision=self.precision, use_graph=self.use_graph,
-                         use_chains=self.use_chains)
+                         use_chains=self.use_chains, share_cond=self.share_cond, fuse_steps=self.fuse_steps)
             self._engines[key] = eng
         return eng
 
@@ -79,9 +82,10 @@ class _HCFlowBase(nn.Module):
                 assert tuple(e.shape) == (B, c, H, W), (tuple(e.shape), (B, c, H, W))
                 dst.copy_(e * std)
             else:
-                # the reference's own draw, in its order (Basic.py:96-100)
-                zeros = torch.zeros(B, c, H, W, device=device)
-                dst.copy_(torch.normal(mean=zeros, std=torch.ones_like(zeros) * std))
+                # the reference's own draw, in its order (Basic.py:96-100): torch.normal(mean=zeros, std=ones * std)
+                # is normal_(0, 1) * std + mean inside ATen (normal_out_impl), drawn here without the host
+                # synchronisation of its `std >= 0` check (tests/test_gpu_parity.py checks the streams are identical)
+                dst.normal_(0.0, 1.0).mul_(std)
 
     def _reverse(self, lr, eps_std, eps):
         lr = self._check(lr, "lr")

@@ -18,7 +18,8 @@ from . import prep
 class Engine:
     """One compiled plan = (net weights, direction, B, h, w, precision) on one device."""
 
-    def __init__(self, net, direction, B, h, w, device, precision="fp32", use_graph=True, use_chains=True):
+    def __init__(self, net, direction, B, h, w, device, precision="fp32", use_graph=True, use_chains=True,
+                 share_cond=True, fuse_steps=True):
         if not torch.cuda.is_available():
             raise L.HcfError("hcflow_b200 needs a CUDA device (no CPU fallback)")
         self.lib = L.load()
@@ -30,6 +31,7 @@ class Engine:
         self.use_graph = use_graph
         self.graph = None
         self._keep = []          # ctypes structs must outlive the launches
+        self._params = None
         self._tc_plans = []
         self.weights = {}
         self.bufs = {}
@@ -42,8 +44,8 @@ class Engine:
         self.shadow16 = {}       # buffer name -> (hi, lo) fp16 planes (fp16 chains)
         self.call_info = []      # per call: {"cls", "tag", "flops", "convs"}
         self.use_chains = use_chains
-        self.share_cond = True   # compute the coupling sub-nets' shared conditioning part once per level (TC modes)
-        self.fuse_steps = True   # FlowStep tail in the last sub-net conv's epilogue (TC modes, inverse pass)
+        self.share_cond = share_cond   # the coupling sub-nets' shared conditioning part once per level (TC modes)
+        self.fuse_steps = fuse_steps   # FlowStep tail in the last sub-net conv's epilogue (TC modes, inverse pass)
         self._step_structs = {}  # id(conv op) -> L.ConvStep
         self._flag_pool = None   # dependency counters of all chained launches: one buffer, zeroed once per pass
         self._flag_used = 0
@@ -81,7 +83,11 @@ class Engine:
 
     # ------------------------------------------------------------------ weights
     def weight_signature(self):
-        return sum(p._version for p in self.net.parameters()), id(self.net)
+        # walking the module tree costs ~1 ms for 1478 tensors; the Parameter objects are stable (load_state_dict,
+        # .to() and optimizers update them in place and bump _version), so the flat list is cached
+        if self._params is None:
+            self._params = list(self.net.parameters())
+        return sum(p._version for p in self._params), id(self.net)
 
     def load_weights(self):
         """(Re)pack every parameter the plan touches. Device addresses stay stable on reload."""

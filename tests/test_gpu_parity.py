@@ -589,3 +589,42 @@ def test_fcn_as_one_chain_with_shared_conditioning(kind, shape, report):
     err = maxabs(got, ref)
     report["fcn_chain/{}/{}x{}".format(kind, H, W)] = err
     assert err < (1e-2 if kind == "tf32" else 4e-3), (kind, err)
+
+
+@pytest.mark.parametrize("precision", ["tf32x3", "f16x3"])
+def test_engine_rewrites_agree_with_the_plain_plan(precision, report):
+    """The engine-level rewrites of the tensor-core modes (shared conditioning conv + pre-activation addend,
+    FlowStep inverse fused into the sub-net's last conv) against the un-rewritten plan (one launch per StepOp,
+    conv1 over cat(z1, u)) at full size: same result up to the summation order of conv1 (tolerance: 1-pass
+    sub-net rounding, measured in the report), and far fewer launches."""
+    opt, net, sd = _net_cuda("sr_x4", precision)
+    B = 16
+    lr = synth.synthetic_lr(B, 40, 40, seed=5).cuda()
+    unit = synth.synthetic_noise(orc.noise_shapes(opt, B, 40, 40, True), seed=9)
+    with torch.no_grad():
+        net.share_cond, net.fuse_steps = False, False
+        net(lr=lr, eps_std=0.8, reverse=True, eps=unit)
+        want = net.last["hr_raw"].clone()
+        e0 = [e for e in net._engines.values()][-1]
+        net.share_cond, net.fuse_steps = True, True
+        net(lr=lr, eps_std=0.8, reverse=True, eps=unit)
+        got = net.last["hr_raw"].clone()
+        e1 = [e for e in net._engines.values()][-1]
+    err = float((got - want).abs().max())
+    report["rewrites/{}".format(precision)] = {"max": err, "launches_plain": e0.launches_per_run,
+                                               "launches_rewritten": e1.launches_per_run}
+    assert e1.launches_per_run < e0.launches_per_run // 3
+    assert err < 2e-3, err
+
+
+def test_prior_draw_consumes_the_reference_rng_stream():
+    """arch._draw_eps draws with normal_(0, 1) * std; the reference calls torch.normal(mean=zeros, std=ones * std)
+    (Basic.py:96-100).  Same generator state -> same bits, so a seeded run consumes the same stream."""
+    torch.manual_seed(1234)
+    z = torch.zeros(2, 6, 16, 16, device="cuda")
+    want = torch.normal(mean=z, std=torch.ones_like(z) * 0.8)
+    want2 = torch.normal(mean=z, std=torch.ones_like(z) * 0.8)
+    torch.manual_seed(1234)
+    got = torch.empty_like(z).normal_(0.0, 1.0).mul_(0.8)
+    got2 = torch.empty_like(z).normal_(0.0, 1.0).mul_(0.8)
+    assert torch.equal(got, want) and torch.equal(got2, want2)
