@@ -475,6 +475,24 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
           b_slab = (uint32_t)slab_taps * tap_bytes;
           wimg = reinterpret_cast<const uint8_t*>(ldg_ptr(&L->wimg));
         }
+        auto issue_b = [&](int kc, int sl) {
+          const int sB = b_it % p.sb;
+          HCF_T(tb0);
+          mbar_wait(emptyB(sB), ((b_it / p.sb) & 1u) ^ 1u);
+          HCF_T(tb1);
+          HCF_ACC(PROF_P_EMPTYB, tb0, tb1);
+          if (p.debug & 4) {
+            mbar_arrive(fullB(sB));
+          } else {
+            mbar_expect_tx(fullB(sB), b_slab);
+            bulk_load(b_base + sB * slot_bytes,
+                      wimg + (size_t)kc * ((uint32_t)ltaps * tap_bytes) + (size_t)sl * b_slab, b_slab, fullB(sB));
+          }
+          ++b_it;
+        };
+        // (issuing the first chunk's weight slabs BEFORE the dependency wait was measured slower: with a two-slot B
+        //  ring the activation tile then queues behind the wait for a free slot)
+        constexpr int n_pre = 0;
         if (chain) {
           if (layer > 0 && !(p.debug & 64)) {
             // wait until layer-1 is complete on the 3x3 tile neighbourhood (halo + WAR safety)
@@ -519,21 +537,7 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
             }
           }
           ++a_it;
-          for (int sl = 0; sl < slabs; ++sl) {
-            const int sB = b_it % p.sb;
-            HCF_T(tb0);
-            mbar_wait(emptyB(sB), ((b_it / p.sb) & 1u) ^ 1u);
-            HCF_T(tb1);
-            HCF_ACC(PROF_P_EMPTYB, tb0, tb1);
-            if (p.debug & 4) {
-              mbar_arrive(fullB(sB));
-            } else {
-              mbar_expect_tx(fullB(sB), b_slab);
-              bulk_load(b_base + sB * slot_bytes,
-                        wimg + (size_t)kc * ((uint32_t)ltaps * tap_bytes) + (size_t)sl * b_slab, b_slab, fullB(sB));
-            }
-            ++b_it;
-          }
+          for (int sl = (kc == 0 ? n_pre : 0); sl < slabs; ++sl) issue_b(kc, sl);
         }
       }
       HCF_T(tp1);
