@@ -117,6 +117,7 @@ SYMBOLS = {
     "hcf_haar_forward": (C.c_int, [C.POINTER(SqueezeArgs), C.c_void_p]),
     "hcf_haar_inverse": (C.c_int, [C.POINTER(SqueezeArgs), C.c_void_p]),
     "hcf_copy_view": (C.c_int, [C.POINTER(SqueezeArgs), C.c_void_p]),
+    "hcf_upsample_nearest": (C.c_int, [C.POINTER(SqueezeArgs), C.c_int32, C.c_void_p]),
     "hcf_gauss_logp_const": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_int32, C.c_void_p,
                                        C.c_void_p]),
 }

@@ -58,7 +58,7 @@ __host__ __device__ constexpr int halo_rows(int mt, int ks) { return TH * mt + (
 __host__ __device__ constexpr int a_bytes(int mt, int ks) { return halo_rows(mt, ks) * halo_w(ks) * ROW_BYTES; }
 __host__ __device__ constexpr int a_part(int mt, int ks) { return (a_bytes(mt, ks) + 1023) / 1024 * 1024; }
 
-constexpr int MAX_MAPS = 16;
+constexpr int MAX_MAPS = 20;
 struct Maps { CUtensorMap m[MAX_MAPS]; };
 
 // One convolution of a chain.  Lives in global memory; every warp role reads the fields it needs

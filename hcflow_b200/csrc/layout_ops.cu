@@ -179,6 +179,34 @@ extern "C" int hcf_split16(const float* src, int32_t ld, int32_t C, int64_t npix
   return finish_launch("hcf_split16");
 }
 
+// nearest-neighbour upsampling by 2^shift between NHWC views (F.interpolate(..., mode='nearest'),
+// FlowNet_SR_x4.py:98,117): materialises a conv input segment so that the conv can run on the tensor cores
+__global__ void __launch_bounds__(hcf::LT) upsample_kernel(const float4* __restrict__ src, float4* __restrict__ dst,
+                                                           int B, int C4, int H, int W, int src_ld4, int dst_ld4,
+                                                           int shift) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * H * W * C4) return;
+  const int c = (int)(i % C4);
+  const long long pix = i / C4;
+  const int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
+  const long long sp = ((long long)b * (H >> shift) + (y >> shift)) * (W >> shift) + (x >> shift);
+  dst[pix * dst_ld4 + c] = __ldg(src + sp * src_ld4 + c);
+}
+
+// a->H, a->W: the DESTINATION (high-res) size; a->C channels, multiples of 4, 16-byte aligned views
+extern "C" int hcf_upsample_nearest(const hcf_squeeze_args* a, int32_t shift, void* stream) {
+  using namespace hcf;
+  HCF_REQUIRE(a && a->src && a->dst && shift >= 1 && shift <= 3, "upsample: bad args");
+  HCF_REQUIRE(a->B > 0 && a->C > 0 && a->C % 4 == 0 && a->src_ld % 4 == 0 && a->dst_ld % 4 == 0 && a->src_ld >= a->C &&
+                  a->dst_ld >= a->C && a->H % (1 << shift) == 0 && a->W % (1 << shift) == 0 && aligned16(a->src) &&
+                  aligned16(a->dst), "upsample: shape / alignment");
+  const long long n = (long long)a->B * a->H * a->W * (a->C / 4);
+  upsample_kernel<<<(unsigned)((n + LT - 1) / LT), LT, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(a->src), reinterpret_cast<float4*>(a->dst), a->B, a->C / 4, a->H, a->W,
+      a->src_ld / 4, a->dst_ld / 4, shift);
+  return finish_launch("hcf_upsample_nearest");
+}
+
 extern "C" int hcf_copy_view(const hcf_squeeze_args* a, void* stream) {
   using namespace hcf;
   HCF_REQUIRE(a && a->src && a->dst, "copy_view: null args");

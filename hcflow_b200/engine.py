@@ -143,8 +143,31 @@ class Engine:
         conv over u (Cout = steps x 64, UMMA N = 128) computed once per level; each step then convolves only its few
         z1 channels and adds its slice before ActNorm + ReLU (hcf_conv_args.pre)."""
         ops = list(self.plan.ops)
-        if self.precision == "fp32" or not self.share_cond:
+        if self.precision == "fp32":
             return ops
+        # up-sampled conv segments (cat[z, up2(cf2), up4(cf3)] of the encoders' first conv) are materialised once, so
+        # that conv joins the level's chained tensor-core launch instead of running on the CUDA cores
+        mat = []
+        for op in ops:
+            if isinstance(op, P.ConvOp) and any(up > 0 for _, up in op.segs) and all(
+                    v.C % 4 == 0 and v.off % 4 == 0 and v.buf.C % 4 == 0 for v, up in op.segs if up > 0):
+                segs = []
+                for v, up in op.segs:
+                    if up > 0:
+                        ub = P.Buf("up{}_{}_{}".format(up, v.buf.name, v.off), op.H, op.W, v.C)
+                        if ub.name not in self.bufs:
+                            self.bufs[ub.name] = torch.zeros(self.B, op.H, op.W, v.C, dtype=torch.float32, device=self.device)
+                        dst = P.View(ub, 0, v.C)
+                        mat.append(P.LayoutOp("upsample", op.H, op.W, v.C, v, dst, post=up))
+                        segs.append((dst, 0))
+                    else:
+                        segs.append((v, 0))
+                op = P.ConvOp(op.H, op.W, segs, op.ks, op.cout, op.weight, op.bias, op.scale, op.act, op.out, op.out2,
+                              op.res1, op.alpha1, op.res2, op.alpha2, op.tag)
+            mat.append(op)
+        ops = mat
+        if not self.share_cond:
+            return self._fuse_steps_pass(ops)
         groups = {}
         for i, op in enumerate(ops):
             if isinstance(op, P.ConvOp) and op.tag == "fcn.conv1" and len(op.segs) == 2 and op.segs[1][1] == 0:
@@ -174,6 +197,9 @@ class Engine:
         for i, op in enumerate(ops):
             out.extend(inserts.get(i, []))
             out.append(op)
+        return self._fuse_steps_pass(out)
+
+    def _fuse_steps_pass(self, out):
         if not self.fuse_steps:
             return out
         # FlowStep tail fused into the sub-net's last conv (hcf_conv_step): removes one launch per step and lets the
@@ -301,6 +327,14 @@ class Engine:
                         a.dst = self.ext[op.dst].data_ptr()
                         a.post = op.post
                         fn = lib.hcf_nhwc_to_nchw
+                elif op.variant == "upsample":
+                    a = L.SqueezeArgs()
+                    a.B, a.C, a.H, a.W = B, op.C, op.H, op.W
+                    a.src, a.src_ld = self._vptr(op.src)
+                    a.dst, a.dst_ld = self._vptr(op.dst)
+
+                    def fn(arg, stream, shift=op.post):
+                        return lib.hcf_upsample_nearest(arg, shift, stream)
                 else:
                     a = L.SqueezeArgs()
                     a.B, a.C, a.H, a.W = B, op.C, op.H, op.W

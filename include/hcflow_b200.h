@@ -266,6 +266,10 @@ int hcf_haar_inverse(const hcf_squeeze_args* a, void* stream);
 /* dst[..., :C] = src[..., :C] for two NHWC views of size [B,H,W] (Basic.py:489-499 Split / cat when a view
  * would break TMA alignment). */
 int hcf_copy_view(const hcf_squeeze_args* a, void* stream);
+/* nearest-neighbour upsampling by 2^shift (1..3) from the low-res view src to the high-res view dst (a->H, a->W =
+ * high-res size; C % 4 == 0, 16-byte aligned views): materialises an up-sampled conv segment
+ * (F.interpolate(mode='nearest'), FlowNet_SR_x4.py:98,117) so that the conv runs on the tensor cores. */
+int hcf_upsample_nearest(const hcf_squeeze_args* a, int32_t shift, void* stream);
 
 /* logdet[b] += sum_{c,h,w} log N(x; mean, exp(logs)) with a constant logs, all NCHW
  * (HCFlowNet_SR_arch.py:63 with logs = -6). n = C*H*W elements per image. */
