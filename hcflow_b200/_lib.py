@@ -97,7 +97,7 @@ SYMBOLS = {
     "hcf_conv_tc16_weight_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "hcf_conv_tc16_pack_weights": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "hcf_conv_chain16_create": (C.c_int, [C.POINTER(ConvArgs), C.POINTER(C.c_void_p), C.POINTER(C.c_int32),
-                                          C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.POINTER(Shadow16), C.c_int32,
+                                          C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.POINTER(Shadow16), C.c_int32,
                                           C.POINTER(Seg16), C.POINTER(C.c_void_p)]),
     "hcf_split16": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,
                               C.c_void_p]),

@@ -74,6 +74,8 @@ struct LayerDesc {
   int act;
   int out_vec;
   int parts;          // 1: one TF32 pass (B rows = N);  2: 3xTF32 split (B rows = [raw N ; lo N], plus A_lo x B)
+  int split_kc;       // parts == 2: the split covers K chunks [0, split_kc) only (fp16 chains: the residual-stream
+                      // channels of an RDB's conv5); the remaining chunks run one pass into the main columns
   int slab_taps;      // taps of this layer per B ring slot: KS*KS, KS or 1 (largest that fits the slot)
   int taps, tap0;     // taps of this layer (KS*KS, or 1 for a 1x1 conv inside a 3x3 chain) and the first tap index
   const float* wimg;  // [kchunks][ks dy][ks dx][NB][32] pre-swizzled; NB = N * parts
@@ -445,8 +447,8 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
       uint32_t a_it = 0, b_it = 0, p_it = 0;
       // per-layer fields stay in registers; a CTA sees the same layer for ~n_tiles/gridDim.x items in a row
       int cur_layer = -1, kchunks = 0, se0 = 0, se1 = 0, m0 = 0, m1 = 0, m2 = 0, slab_taps = 1, slabs = 1;
-      int l0 = 0, l1 = 0, l2 = 0, lparts = 1, ltaps = KS * KS;
-      uint32_t tap_bytes = 0, b_slab = 0;
+      int l0 = 0, l1 = 0, l2 = 0, lparts = 1, ltaps = KS * KS, lsplit = 0;
+      uint32_t tap_n = 0;   // bytes of one tap of B at one row block (N rows)
       const uint8_t* wimg = nullptr;
       Deps deps;
       HCF_T(tp0);
@@ -468,11 +470,11 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
           m0 = __ldg(&L->map_idx[0]); m1 = __ldg(&L->map_idx[1]); m2 = __ldg(&L->map_idx[2]);
           l0 = __ldg(&L->map_lo[0]); l1 = __ldg(&L->map_lo[1]); l2 = __ldg(&L->map_lo[2]);
           lparts = __ldg(&L->parts);
-          tap_bytes = (uint32_t)(__ldg(&L->N) * __ldg(&L->parts)) * ROW_BYTES;
+          lsplit = lparts == 2 ? __ldg(&L->split_kc) : 0;
+          tap_n = (uint32_t)__ldg(&L->N) * ROW_BYTES;
           slab_taps = __ldg(&L->slab_taps);
           ltaps = __ldg(&L->taps);
           slabs = ltaps / slab_taps;
-          b_slab = (uint32_t)slab_taps * tap_bytes;
           wimg = reinterpret_cast<const uint8_t*>(ldg_ptr(&L->wimg));
         }
         auto issue_b = [&](int kc, int sl) {
@@ -484,9 +486,12 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
           if (p.debug & 4) {
             mbar_arrive(fullB(sB));
           } else {
+            // weight image: chunks [0, lsplit) carry [hi ; lo] row blocks (2N rows per tap), the rest N rows
+            const uint32_t tap_bytes = kc < lsplit ? 2u * tap_n : tap_n;
+            const uint32_t b_slab = (uint32_t)slab_taps * tap_bytes;
+            const size_t chunk_off = ((size_t)min(kc, lsplit) * 2u + (size_t)max(kc - lsplit, 0)) * (uint32_t)ltaps * tap_n;
             mbar_expect_tx(fullB(sB), b_slab);
-            bulk_load(b_base + sB * slot_bytes,
-                      wimg + (size_t)kc * ((uint32_t)ltaps * tap_bytes) + (size_t)sl * b_slab, b_slab, fullB(sB));
+            bulk_load(b_base + sB * slot_bytes, wimg + chunk_off + (size_t)sl * b_slab, b_slab, fullB(sB));
           }
           ++b_it;
         };
@@ -526,7 +531,7 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
           if (p.debug & 4) {
             mbar_arrive(fullA(sA));
           } else {
-            const bool two = F16 && PASSES == 3 && lparts == 2;   // split layer of an fp16 chain: hi and lo planes
+            const bool two = F16 && PASSES == 3 && kc < lsplit;   // split chunk of an fp16 chain: hi and lo planes
             mbar_expect_tx(fullA(sA), two ? 2 * A_BYTES : A_BYTES);
             const int mi = kc < se0 ? m0 : (kc < se1 ? m1 : m2);
             const int kl = kc < se0 ? kc : (kc < se1 ? kc - se0 : kc - se1);
@@ -556,7 +561,8 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
     const uint64_t b_tmpl = make_desc(0, 8u * ROW_BYTES);
     uint32_t a_it = 0, b_it = 0, t_it = 0;
     int cur_layer = -1, kchunks = 0, slab_taps = 1, slabs = 1, tap0 = 0;
-    uint32_t parts = 1, nb = 0, idesc_n = 0, idesc = 0, n_cols = 0;
+    uint32_t parts = 1, nb = 0, nb_n = 0, idesc_n = 0, idesc = 0, n_cols = 0;
+    int split_kc = 0;
     HCF_T(tm0);
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++t_it) {
       const int layer = item / p.n_tiles;
@@ -570,7 +576,9 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
         slab_taps = __ldg(&L->slab_taps);
         slabs = __ldg(&L->taps) / slab_taps;
         tap0 = __ldg(&L->tap0);
-        nb = NB * (ROW_BYTES >> 4);      // one tap of B in 16-byte units
+        nb = NB * (ROW_BYTES >> 4);      // one tap of B in 16-byte units (split chunk)
+        nb_n = N * (ROW_BYTES >> 4);     // ... of a one-pass chunk
+        split_kc = parts == 2 ? __ldg(&L->split_kc) : 0;
         const uint32_t fmt = F16 ? 0u : 2u;   // A / B format: F16 = 0, TF32 = 2; D = F32
         idesc_n = (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((128u >> 4) << 24);
         idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((NB >> 3) << 17) | ((128u >> 4) << 24);
@@ -595,6 +603,9 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
         HCF_ACC(PROF_M_FULLA, tfa0, tfa1);
         HCF_ACC(PROF_M_CONVA, tfa1, tfa2);
         const uint64_t a0 = a_tmpl + ((smem_base + sA * A_STAGE) >> 4);
+        const bool split = PASSES == 3 && parts == 2 && kc < split_kc;   // this chunk: hi + lo on both operands
+        const uint32_t nb_kc = split ? nb : nb_n;
+        const uint32_t idesc_kc = split ? idesc : idesc_n;
         for (int sl = 0; sl < slabs; ++sl) {
           const int sB = b_it % p.sb;
           HCF_T(tfb0);
@@ -609,7 +620,7 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
               const int dy = tap / KS, dx = tap - dy * KS;
               uint64_t a_tap = a0 + (uint32_t)((dy * HALO_W + dx) * (ROW_BYTES >> 4));
               if (p.debug & 1) a_tap = make_desc(0, 8u * ROW_BYTES) + ((smem_base + sA * A_STAGE) >> 4);
-              const uint64_t b_tap = b0 + (uint32_t)t * nb;
+              const uint64_t b_tap = b0 + (uint32_t)t * nb_kc;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const uint64_t bd = b_tap + 2u * k;
@@ -619,11 +630,11 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                   const uint64_t ad = a_tap + (uint32_t)((mt * TH * HALO_W * ROW_BYTES + k * 32) >> 4);
                   if (F16) {
                     // cols [0,N) += A_hi x B_hi, cols [N,2N) += A_hi x B_lo' + A_lo' x B_hi (lo' = lo * 2048)
-                    umma_f16(d, ad, bd, idesc, accum);
-                    if (PASSES == 3 && parts == 2) umma_f16(d + n_cols, ad + (A_PART >> 4), bd, idesc_n, 1u);
+                    umma_f16(d, ad, bd, idesc_kc, accum);
+                    if (split) umma_f16(d + n_cols, ad + (A_PART >> 4), bd, idesc_n, 1u);
                   } else {
-                    umma_tf32(d, ad, bd, idesc, accum);                                  // A x [B ; B_lo]
-                    if (PASSES == 3 && parts == 2) umma_tf32(d, ad + (A_PART >> 4), bd, idesc_n, 1u);  // A_lo x B
+                    umma_tf32(d, ad, bd, idesc_kc, accum);                               // A x [B ; B_lo]
+                    if (split) umma_tf32(d, ad + (A_PART >> 4), bd, idesc_n, 1u);        // A_lo x B
                   }
                 }
                 accum = 1u;
@@ -1145,23 +1156,28 @@ extern "C" int hcf_conv_tc_pack_weights(const float* w, int32_t kin, int32_t cou
   return 0;
 }
 
-// fp16 weight image: kin padded per segment to multiples of 64
-extern "C" int64_t hcf_conv_tc16_weight_bytes(int32_t kin, int32_t cout, int32_t ks, int32_t passes) {
-  if (kin % 64 != 0 || cout < 1 || cout > 128 || (ks != 1 && ks != 3) || (passes != 1 && passes != 3)) return 0;
-  return (int64_t)(kin / 64) * ks * ks * hcf::tc::n_for(cout) * (passes == 3 ? 2 : 1) * 128;
+// fp16 weight image: kin padded per segment to multiples of 64.  split_kin = number of LEADING input channels
+// (multiple of 64) packed as [hi ; lo] row blocks for the split; 0 = one pass everywhere, kin = split everywhere
+extern "C" int64_t hcf_conv_tc16_weight_bytes(int32_t kin, int32_t cout, int32_t ks, int32_t split_kin) {
+  if (kin % 64 != 0 || cout < 1 || cout > 128 || (ks != 1 && ks != 3) || split_kin < 0 || split_kin > kin ||
+      split_kin % 64 != 0)
+    return 0;
+  return (int64_t)((kin + split_kin) / 64) * ks * ks * hcf::tc::n_for(cout) * 128;
 }
 
-// w: [cout][kin][ks][ks] fp32 (host) -> [kchunk][dy][dx][rows][64 fp16], rows = [hi N ; lo' N] for passes == 3
-// (hi = fp16(w), lo' = fp16((w - hi) * 2048)), 128-byte rows pre-swizzled like the activations TMA writes
-extern "C" int hcf_conv_tc16_pack_weights(const float* w, int32_t kin, int32_t cout, int32_t ks, int32_t passes,
+// w: [cout][kin][ks][ks] fp32 (host) -> per 64-channel chunk [dy][dx][rows][64 fp16]; rows = [hi N ; lo' N] for the
+// chunks below split_kin (hi = fp16(w), lo' = fp16((w - hi) * 2048)), hi N otherwise; 128-byte rows pre-swizzled
+// like the activations TMA writes
+extern "C" int hcf_conv_tc16_pack_weights(const float* w, int32_t kin, int32_t cout, int32_t ks, int32_t split_kin,
                                           void* image) {
   using namespace hcf;
-  HCF_REQUIRE(w && image && kin % 64 == 0 && cout >= 1 && cout <= 128 && (ks == 1 || ks == 3) &&
-                  (passes == 1 || passes == 3), "tc16_pack: bad args");
-  const int N = tc::n_for(cout), KC = kin / 64, parts = passes == 3 ? 2 : 1, NB = N * parts;
-  memset(image, 0, (size_t)hcf_conv_tc16_weight_bytes(kin, cout, ks, passes));
+  HCF_REQUIRE(w && image && hcf_conv_tc16_weight_bytes(kin, cout, ks, split_kin) > 0, "tc16_pack: bad args");
+  const int N = tc::n_for(cout), KC = kin / 64, SKC = split_kin / 64;
+  memset(image, 0, (size_t)hcf_conv_tc16_weight_bytes(kin, cout, ks, split_kin));
   __half* img = reinterpret_cast<__half*>(image);
-  for (int kc = 0; kc < KC; ++kc)
+  size_t base = 0;   // in fp16 elements
+  for (int kc = 0; kc < KC; ++kc) {
+    const int parts = kc < SKC ? 2 : 1, NB = N * parts;
     for (int dy = 0; dy < ks; ++dy)
       for (int dx = 0; dx < ks; ++dx)
         for (int part = 0; part < parts; ++part)
@@ -1172,8 +1188,10 @@ extern "C" int hcf_conv_tc16_pack_weights(const float* w, int32_t kin, int32_t c
               const __half val = part == 0 ? hi : __float2half_rn((v - __half2float(hi)) * 2048.0f);
               const int row = part * N + n;
               const int chunk = (j / 8) ^ (row & 7);   // 16-byte chunk = 8 fp16
-              img[((((size_t)kc * ks + dy) * ks + dx) * NB + row) * 64 + chunk * 8 + (j & 7)] = val;
+              img[base + ((size_t)(dy * ks + dx) * NB + row) * 64 + chunk * 8 + (j & 7)] = val;
             }
+    base += (size_t)ks * ks * NB * 64;
+  }
   return 0;
 }
 
@@ -1196,7 +1214,7 @@ static bool shadow_of(const hcf_shadow16* sh, int n_sh, const float* ptr, __half
 }
 
 static int chain_create(const hcf_conv_args* args, const void* const* wtc, const int32_t* layer_passes,
-                        const int32_t* out_flags, int32_t n, int32_t* done_flags, bool f16, const hcf_shadow16* shadows,
+                        const int32_t* layer_split, const int32_t* out_flags, int32_t n, int32_t* done_flags, bool f16, const hcf_shadow16* shadows,
                         int32_t n_shadows, const hcf_seg16* seg16, hcf_conv_tc_plan** out) {
   HCF_REQUIRE(out != nullptr, "tc_chain: null out");
   *out = nullptr;
@@ -1357,6 +1375,15 @@ static int chain_create(const hcf_conv_args* args, const void* const* wtc, const
     }
     L.seg_end[a.nseg - 1] = 1 << 30;
     L.kchunks = kc;
+    L.split_kc = L.parts == 2 ? kc : 0;
+    if (f16 && L.parts == 2 && layer_split && layer_split[i] >= 0) {
+      if (layer_split[i] % kch != 0 || layer_split[i] > kc * kch) {
+        delete pl;
+        set_error("tc_chain: conv %d: split range %d is not a multiple of %d channels", i, layer_split[i], kch);
+        return HCF_EINVAL;
+      }
+      L.split_kc = layer_split[i] / kch;
+    }
     L.N = n_for(a.cout);
     if (a.ks == ks) {   // largest tap count (whole chunk, one dy row, one tap) of this layer that fits a ring slot
       const int tap = L.N * L.parts * ROW_BYTES;
@@ -1475,16 +1502,17 @@ static int chain_create(const hcf_conv_args* args, const void* const* wtc, const
 // (device, B*ceil(H/16)*ceil(W/8) int32) must be zeroed before every run; NULL is allowed for n == 1.
 extern "C" int hcf_conv_chain_create(const hcf_conv_args* args, const float* const* wtc, const int32_t* layer_passes,
                                      int32_t n, int32_t* done_flags, hcf_conv_tc_plan** out) {
-  return hcf::tc::chain_create(args, reinterpret_cast<const void* const*>(wtc), layer_passes, nullptr, n, done_flags,
-                               false, nullptr, 0, nullptr, out);
+  return hcf::tc::chain_create(args, reinterpret_cast<const void* const*>(wtc), layer_passes, nullptr, nullptr, n,
+                               done_flags, false, nullptr, 0, nullptr, out);
 }
 
 // The same chain on fp16 operands (see include/hcflow_b200.h).
 extern "C" int hcf_conv_chain16_create(const hcf_conv_args* args, const void* const* w16, const int32_t* layer_passes,
-                                       const int32_t* out_flags, int32_t n, int32_t* done_flags,
+                                       const int32_t* layer_split, const int32_t* out_flags, int32_t n, int32_t* done_flags,
                                        const hcf_shadow16* shadows, int32_t n_shadows, const hcf_seg16* seg16,
                                        hcf_conv_tc_plan** out) {
-  return hcf::tc::chain_create(args, w16, layer_passes, out_flags, n, done_flags, true, shadows, n_shadows, seg16, out);
+  return hcf::tc::chain_create(args, w16, layer_passes, layer_split, out_flags, n, done_flags, true, shadows, n_shadows,
+                               seg16, out);
 }
 
 extern "C" int hcf_conv_tc_plan_create(const hcf_conv_args* a, const float* wtc, int32_t passes,

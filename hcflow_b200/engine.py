@@ -431,14 +431,26 @@ class Engine:
                                        torch.zeros(t.shape, dtype=torch.float16, device=self.device))
         return self.shadow16[buf.name]
 
-    def _tc16_weights(self, op, passes):
-        key = self._wkey(op) + "#tc16_{}".format(passes)
+    def _split_channels(self, op, passes):
+        """fp16 chains: how many leading input channels of a split conv need hi + lo operands (-1 = all).  conv5 of an
+        RDB only needs them on the residual-stream channels x0 (the growth channels x1..x4 come out of one-pass convs
+        and enter the trunk through conv5 * 0.2): CPU emulation 1.45e-5 vs 1.25e-5 max-abs for the full split."""
+        if passes != 3:
+            return 0
+        if (op.tag == "enc.rdb.conv5" and len(op.segs) == 1 and op.res1 is not None and op.res1.C % 64 == 0
+                and op.segs[0][0].C > op.res1.C):
+            return op.res1.C
+        return -1
+
+    def _tc16_weights(self, op, passes, split_ch=-1):
+        key = self._wkey(op) + "#tc16_{}_{}".format(passes, split_ch)
         if key not in self.weights:
             w = prep.pad_weight_for_tc(self._raw_weight(op), [v.C for v, _ in op.segs], chunk=64)
             cout, kin, ks = w.shape[0], w.shape[1], w.shape[2]
-            nbytes = self.lib.hcf_conv_tc16_weight_bytes(kin, cout, ks, passes)
+            split_kin = 0 if passes != 3 else (kin if split_ch < 0 else split_ch)
+            nbytes = self.lib.hcf_conv_tc16_weight_bytes(kin, cout, ks, split_kin)
             img = torch.zeros(nbytes // 2, dtype=torch.float16)
-            L.check(self.lib.hcf_conv_tc16_pack_weights(w.data_ptr(), kin, cout, ks, passes, img.data_ptr()), "tc16_pack")
+            L.check(self.lib.hcf_conv_tc16_pack_weights(w.data_ptr(), kin, cout, ks, split_kin, img.data_ptr()), "tc16_pack")
             self.weights[key] = img.to(self.device)
         return self.weights[key]
 
@@ -477,6 +489,21 @@ class Engine:
         if not all(lib.hcf_conv_tc_supported(C.byref(p[1])) for p in pending):
             return False
         passes = [self._passes_for(op) for op in ops]
+        splits = [self._split_channels(op, ps) for op, ps in zip(ops, passes)]
+
+        def split_views(j):
+            """the input views of conv j that its split (hi + lo) covers"""
+            if passes[j] != 3:
+                return []
+            if splits[j] < 0:
+                return [v for v, _ in ops[j].segs]
+            out, left = [], splits[j]
+            for v, _ in ops[j].segs:
+                if left <= 0:
+                    break
+                out.append(v.sub(0, min(v.C, left)))
+                left -= (v.C + 63) // 64 * 64
+            return out
         last_idx = max(i for i, o in enumerate(self.ops) if o is ops[-1])
         flags = []
         for k, op in enumerate(ops):
@@ -485,7 +512,7 @@ class Engine:
             for j in range(k + 1, n):
                 if any(self._overlap(v, o) for v, _ in ops[j].segs for o in outs):
                     hi = True
-                    lo = lo or passes[j] == 3
+                    lo = lo or any(self._overlap(v, o) for v in split_views(j) for o in outs)
             for j in range(n):   # residual sources and pre-activation addends stay fp32
                 if any(self._overlap(v, o) for v in (ops[j].res1, ops[j].res2, ops[j].pre) if v is not None for o in outs):
                     f32 = True
@@ -525,7 +552,7 @@ class Engine:
                     loc16[key] = (self._shadow(v.buf)[0].data_ptr() + 2 * v.off, v.buf.C)
                 # the lo plane is needed as soon as ANY split conv of the chain reads these channels (e.g. the
                 # first RDB's conv5 reads x0 inside a wider view that is otherwise produced by the chain)
-                need_lo = any(passes[j] == 3 and any(self._overlap(v, s) for s, _ in ops[j].segs) for j in range(n))
+                need_lo = any(self._overlap(v, sv) for j in range(n) for sv in split_views(j))
                 if by_step and need_lo:
                     return False           # fused steps write the hi plane only
                 if not (by_conv or by_step) and key not in external:
@@ -555,20 +582,22 @@ class Engine:
         wptr = (C.c_void_p * n)()
         lp = (C.c_int32 * n)()
         of = (C.c_int32 * n)()
+        ls = (C.c_int32 * n)()
         for i, (op, a, _, _) in enumerate(pending):
             C.memmove(C.byref(arr[i]), C.byref(a), C.sizeof(L.ConvArgs))
             lp[i] = passes[i]
+            ls[i] = splits[i]
             of[i] = flags[i]
-            wptr[i] = self._tc16_weights(op, passes[i]).data_ptr()
+            wptr[i] = self._tc16_weights(op, passes[i], splits[i]).data_ptr()
         op0 = ops[0]
         tiles = self.B * ((op0.H + 15) // 16) * ((op0.W + 7) // 8)
         done = self._alloc_flags(tiles)
         handle = C.c_void_p()
-        rc = lib.hcf_conv_chain16_create(arr, wptr, lp, of, n, done.data_ptr(), sh, len(bufs), seg16, C.byref(handle))
+        rc = lib.hcf_conv_chain16_create(arr, wptr, lp, ls, of, n, done.data_ptr(), sh, len(bufs), seg16, C.byref(handle))
         if rc == -2:
             return False
         L.check(rc, "conv_chain16_create")
-        self._keep += [arr, wptr, lp, of, sh, seg16, done]
+        self._keep += [arr, wptr, lp, ls, of, sh, seg16, done]
         self._tc_plans.append(handle)
         npix = self.B * op0.H * op0.W
         for v, need_lo, st in external.values():

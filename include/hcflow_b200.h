@@ -148,7 +148,9 @@ int hcf_conv_chain_create(const hcf_conv_args* args, const float* const* wtc, co
  * geometry (same ld, same channel offsets): value = hi + lo / 2048, hi = fp16(value),
  * lo = fp16((value - hi) * 2048).  `shadows` lists them; views are matched to buffers by address range.
  * layer_passes[i] = 1: D = A_hi x W_hi (11-bit operands); 3: D = A_hi x W_hi + (A_hi x W_lo + A_lo x W_hi) / 2048
- * (~fp32 accuracy, needs the lo plane of its inputs).  out_flags[i] says which representations conv i writes:
+ * (~fp32 accuracy, needs the lo plane of its inputs); layer_split[i] (may be NULL; -1 = whole K) restricts the split
+ * to the leading layer_split[i] padded input channels, the rest of K runs one pass (an RDB's conv5 only needs it on
+ * the 64 residual-stream channels).  out_flags[i] says which representations conv i writes:
  * the fp32 view (residual sources and anything read outside the chain), the hi plane, the lo plane.
  * Inputs that no chain conv produced must be converted first (hcf_split16).  w16[i] comes from
  * hcf_conv_tc16_pack_weights with the same `passes`; the input-channel axis is padded per segment to
@@ -163,8 +165,10 @@ typedef struct {
 #define HCF_OUT_HI 2
 #define HCF_OUT_LO 4
 int hcf_conv_tc16_supported(const hcf_conv_args* a);
-int64_t hcf_conv_tc16_weight_bytes(int32_t kin, int32_t cout, int32_t ks, int32_t passes);
-int hcf_conv_tc16_pack_weights(const float* w_oihw, int32_t kin, int32_t cout, int32_t ks, int32_t passes, void* image);
+/* split_kin: number of LEADING (padded) input channels whose weights are packed as [hi ; lo] row blocks
+ * (multiple of 64; 0 = one pass, kin = split everywhere) */
+int64_t hcf_conv_tc16_weight_bytes(int32_t kin, int32_t cout, int32_t ks, int32_t split_kin);
+int hcf_conv_tc16_pack_weights(const float* w_oihw, int32_t kin, int32_t cout, int32_t ks, int32_t split_kin, void* image);
 /* seg16 (may be NULL): n x 3 explicit fp16 views for input segments whose fp32 geometry does not satisfy TMA's
  * 16-byte rules in fp16 (ld % 8, channel offset % 8): entries with hi != NULL replace the shadow lookup. */
 typedef struct {
@@ -174,7 +178,7 @@ typedef struct {
   int32_t _pad;
 } hcf_seg16;
 int hcf_conv_chain16_create(const hcf_conv_args* args, const void* const* w16, const int32_t* layer_passes,
-                            const int32_t* out_flags, int32_t n, int32_t* done_flags, const hcf_shadow16* shadows,
+                            const int32_t* layer_split, const int32_t* out_flags, int32_t n, int32_t* done_flags, const hcf_shadow16* shadows,
                             int32_t n_shadows, const hcf_seg16* seg16, hcf_conv_tc_plan** out);
 /* fp32 NHWC view (ld, C, npix pixels) -> hi / lo planes with row pitch dst_ld (lo may be NULL) */
 int hcf_split16(const float* src, int32_t ld, int32_t C, int64_t npix, void* hi, void* lo, int32_t dst_ld, void* stream);

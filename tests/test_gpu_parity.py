@@ -361,7 +361,7 @@ def test_chained_launch_is_bit_identical_to_separate_launches(precision, report)
 
 
 # ------------------------------------------------------------------------------ fp16 chains
-def _rdb_chain16(B, H, W, passes, seed=0):
+def _rdb_chain16(B, H, W, passes, seed=0, conv5_split=-1):
     """One ResidualDenseBlock (Basic.py:360-383) as a 5-conv fp16 chain through the C ABI: dense concat inside a
     192-channel buffer (fp16 hi / lo planes), x5 * 0.2 + x in the last epilogue.  Returns (got fp32 out, fp64 ref,
     hi plane of x1..x4, fp64 x1..x4)."""
@@ -383,6 +383,7 @@ def _rdb_chain16(B, H, W, passes, seed=0):
     arr = (L.ConvArgs * n)()
     wptr = (C.c_void_p * n)()
     lp = (C.c_int32 * n)(*passes)
+    ls = (C.c_int32 * n)(*([-1] * 4 + [conv5_split]))
     of = (C.c_int32 * n)()
     keep = []
     for k in range(n):
@@ -398,22 +399,24 @@ def _rdb_chain16(B, H, W, passes, seed=0):
         if k < 4:
             a.act = 2
             a.out, a.out_ld = X.data_ptr() + 4 * cin, 192
-            of[k] = L.OUT_HI | (L.OUT_LO if any(p == 3 for p in passes[k + 1:]) else 0)
+            later_split = any(p == 3 for p in passes[k + 1:4]) or (passes[4] == 3 and conv5_split < 0)
+            of[k] = L.OUT_HI | (L.OUT_LO if later_split else 0)
         else:
             a.act = 0
             a.out, a.out_ld = Y.data_ptr(), 192
             a.res1, a.res1_ld, a.alpha1 = X.data_ptr(), 192, 0.2
             of[k] = L.OUT_F32 | L.OUT_HI | L.OUT_LO
         wt = prep.pad_weight_for_tc(ws[k], [cin], chunk=64)
-        img = torch.zeros(lib.hcf_conv_tc16_weight_bytes(wt.shape[1], cout, 3, passes[k]) // 2, dtype=torch.float16)
-        L.check(lib.hcf_conv_tc16_pack_weights(wt.data_ptr(), wt.shape[1], cout, 3, passes[k], img.data_ptr()), "pack16")
+        skin = 0 if passes[k] != 3 else (wt.shape[1] if (k < 4 or conv5_split < 0) else conv5_split)
+        img = torch.zeros(lib.hcf_conv_tc16_weight_bytes(wt.shape[1], cout, 3, skin) // 2, dtype=torch.float16)
+        L.check(lib.hcf_conv_tc16_pack_weights(wt.data_ptr(), wt.shape[1], cout, 3, skin, img.data_ptr()), "pack16")
         img = img.cuda()
         wptr[k] = img.data_ptr()
         keep += [wp, bp, img]
     tiles = B * ((H + 15) // 16) * ((W + 7) // 8)
     done = torch.zeros(tiles, dtype=torch.int32, device="cuda")
     h = C.c_void_p()
-    L.check(lib.hcf_conv_chain16_create(arr, wptr, lp, of, n, done.data_ptr(), sh, 2, None, C.byref(h)), "chain16_create")
+    L.check(lib.hcf_conv_chain16_create(arr, wptr, lp, ls, of, n, done.data_ptr(), sh, 2, None, C.byref(h)), "chain16_create")
     L.check(lib.hcf_split16(X.data_ptr(), 192, 64, B * H * W, planes[0].data_ptr(), planes[1].data_ptr(), 192, st), "split16")
     L.check(lib.hcf_conv_tc_run(h, st), "chain16_run")
     torch.cuda.synchronize()
@@ -433,11 +436,12 @@ def _rdb_chain16(B, H, W, passes, seed=0):
 # outputs of magnitude ~1..4.  1 pass: fp16 operands (11 bits, round-to-nearest); the split recovers fp32-level
 # accuracy for the layers that use it.  measured values are written to the parity report.
 @pytest.mark.parametrize("mode,passes,tol", [("one_pass", [1, 1, 1, 1, 1], 3e-3), ("conv5_split", [1, 1, 1, 1, 3], 3e-3),
+                                             ("conv5_split_x0_only", [1, 1, 1, 1, 3], 3e-3),
                                              ("all_split", [3, 3, 3, 3, 3], 2e-5)])
 @pytest.mark.parametrize("shape", [(2, 40, 40), (1, 21, 13)], ids=["40x40", "partial_tiles"])
 def test_conv_chain16_rdb_matches_fp64(shape, mode, passes, tol, report):
     B, H, W = shape
-    got, ref, mid, mid_ref, y16 = _rdb_chain16(B, H, W, passes)
+    got, ref, mid, mid_ref, y16 = _rdb_chain16(B, H, W, passes, conv5_split=64 if mode == "conv5_split_x0_only" else -1)
     err = maxabs(got, ref)
     err_mid = maxabs(mid, mid_ref)
     err16 = maxabs(y16, got)          # hi + lo / 2048 planes reproduce the fp32 output to ~2^-22 relative
@@ -521,8 +525,8 @@ def _fcn_chain(kind, B, H, W, zc=6, cond=128, hidden=64, cout=12, seed=0):
         co, ks = w.shape[0], w.shape[2]
         if f16:
             wt = prep.pad_weight_for_tc(w, [cin], chunk=64)
-            img = torch.zeros(lib.hcf_conv_tc16_weight_bytes(wt.shape[1], co, ks, passes) // 2, dtype=torch.float16)
-            L.check(lib.hcf_conv_tc16_pack_weights(wt.data_ptr(), wt.shape[1], co, ks, passes, img.data_ptr()), "pack16")
+            img = torch.zeros(lib.hcf_conv_tc16_weight_bytes(wt.shape[1], co, ks, 0) // 2, dtype=torch.float16)
+            L.check(lib.hcf_conv_tc16_pack_weights(wt.data_ptr(), wt.shape[1], co, ks, 0, img.data_ptr()), "pack16")
         else:
             wt = prep.pad_weight_for_tc(w, [cin])
             img = torch.zeros(lib.hcf_conv_tc_weight_bytes(wt.shape[1], co, ks, passes) // 4, dtype=torch.float32)
@@ -544,7 +548,7 @@ def _fcn_chain(kind, B, H, W, zc=6, cond=128, hidden=64, cout=12, seed=0):
             sh = (L.Shadow16 * len(planes))()
             for i, (t, hi, lo) in enumerate(planes):
                 sh[i].f32, sh[i].bytes, sh[i].hi, sh[i].lo = t.data_ptr(), t.numel() * 4, hi.data_ptr(), lo.data_ptr()
-            L.check(lib.hcf_conv_chain16_create(arr, wptr, lp, of, n, done.data_ptr(), sh, len(planes), seg16,
+            L.check(lib.hcf_conv_chain16_create(arr, wptr, lp, None, of, n, done.data_ptr(), sh, len(planes), seg16,
                                                 C.byref(h)), "chain16_create")
         else:
             L.check(lib.hcf_conv_chain_create(arr, wptr, lp, n, done.data_ptr(), C.byref(h)), "chain_create")
