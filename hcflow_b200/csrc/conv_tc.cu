@@ -747,6 +747,18 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
           pixv[it] = (gy < p.H && gx < p.W) ? (uint32_t)((b * p.H + gy) * p.W + gx) : 0xffffffffu;
         }
       };
+      // a layer with ONE residual / addend tensor and two column groups (N = 64: an RDB's conv5 without the RRDB
+      // residual, the sub-net's first conv) fetches the second group's tile into the idle r2v registers up front
+      const bool ahead2 = res_pf && res2 == nullptr && N > 32 && N <= 64 && MT == 1;
+      auto res_prefetch_2nd = [&]() {
+        const int ch_ = 32 + (lane & 7) * 4;
+        if (ch_ + 3 < cout) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+            if (pixv[it] != 0xffffffffu)
+              r2v[it] = __ldcg(reinterpret_cast<const float4*>(res1 + (pixv[it] * (uint32_t)res1_ld + ch_)));
+        }
+      };
       auto res_prefetch = [&](int c0_) {
         const int ch_ = c0_ + (lane & 7) * 4;
         if (ch_ + 3 < cout) {
@@ -768,6 +780,7 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
           asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(seen) : "r"(dep_seq) : "memory");
         } while (seen <= t_it);
         if (res_pf) res_prefetch(0);
+        if (ahead2) res_prefetch_2nd();
         if (step_z) {
           const int mm = q * 32 + lane;
           const int gy = y0 + mm / TW, gx = x0 + mm % TW;    // (fused steps run with MT == 1)
@@ -931,7 +944,10 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
               }
             }
             if (res_pf) {   // next column group's residuals: in flight during its row phase
-              if (c0 + 32 < N) {
+              if (ahead2) {
+#pragma unroll
+                for (int it = 0; it < 8; ++it) r1v[it] = r2v[it];
+              } else if (c0 + 32 < N) {
                 res_prefetch(c0 + 32);
               } else if (mt + 1 < MT) {
                 pix_setup(mt + 1);

@@ -632,3 +632,21 @@ def test_prior_draw_consumes_the_reference_rng_stream():
     got = torch.empty_like(z).normal_(0.0, 1.0).mul_(0.8)
     got2 = torch.empty_like(z).normal_(0.0, 1.0).mul_(0.8)
     assert torch.equal(got, want) and torch.equal(got2, want2)
+
+
+@pytest.mark.parametrize("precision,tol", [("f16x3", 2e-3), ("tf32x3", 2e-3), ("f16", 2e-2)])
+def test_ragged_size_against_oracle(precision, tol, report):
+    """LR 12x20 (HR 48x80): every level has partial tiles in both directions (16x8 pixel tiles), B=3 is not a
+    multiple of anything -- the chained launches, the fused FlowStep epilogue and the shared-conditioning addend
+    against the oracle on the CPU."""
+    opt, net, sd = _net_cuda("sr_x4", precision)
+    B, h, w = 3, 12, 20
+    lr = synth.synthetic_lr(B, h, w, seed=21)
+    unit = synth.synthetic_noise(orc.noise_shapes(opt, B, h, w, True), seed=22)
+    with torch.no_grad():
+        net(lr=lr.cuda(), eps_std=0.7, reverse=True, eps=unit)
+        raw = net.last["hr_raw"].cpu()
+        _, want = orc.sr_reverse(lr, sd, opt, [0.7 * e for e in unit])
+    err = maxabs(raw, want)
+    report["ragged_12x20/{}".format(precision)] = err
+    assert err < tol, (precision, err)
