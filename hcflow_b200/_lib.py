@@ -118,6 +118,8 @@ SYMBOLS = {
     "hcf_haar_inverse": (C.c_int, [C.POINTER(SqueezeArgs), C.c_void_p]),
     "hcf_copy_view": (C.c_int, [C.POINTER(SqueezeArgs), C.c_void_p]),
     "hcf_upsample_nearest": (C.c_int, [C.POINTER(SqueezeArgs), C.c_int32, C.c_void_p]),
+    "hcf_u8_hwc_to_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p]),
+    "hcf_nhwc_to_u8_hwc": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "hcf_gauss_logp_const": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_int32, C.c_void_p,
                                        C.c_void_p]),
 }

@@ -36,6 +36,10 @@ class _HCFlowBase(nn.Module):
         self.use_chains = True   # fuse runs of tensor-core convs into one persistent chained launch
         self.share_cond = True   # tensor-core modes: the sub-nets' shared conditioning conv once per level (engine.py)
         self.fuse_steps = True   # tensor-core modes, inverse pass: FlowStep tail in the last sub-net conv's epilogue
+        # opt-in: when the SAME lr tensor (same storage, same version counter) is sampled again, keep the
+        # deepest level's encoder features of the previous call instead of recomputing them
+        self.reuse_lr_features = False
+        self._last_lr_key = None
         self._engines = {}
         self.last = {}
 
@@ -51,14 +55,14 @@ class _HCFlowBase(nn.Module):
             self.precision = precision
             self._engines.clear()
 
-    def engine(self, direction, B, h, w, device):
+    def engine(self, direction, B, h, w, device, io="f32"):
         from .engine import Engine
         key = (direction, B, h, w, str(device), self.precision, self.use_graph, self.use_chains, self.share_cond,
-               self.fuse_steps)
+               self.fuse_steps, io)
         eng = self._engines.get(key)
         if eng is None:
             eng = Engine(self, direction, B, h, w, device, precision=self.precision, use_graph=self.use_graph,
-                         use_chains=self.use_chains, share_cond=self.share_cond, fuse_steps=self.fuse_steps)
+                         use_chains=self.use_chains, share_cond=self.share_cond, fuse_steps=self.fuse_steps, io=io)
             self._engines[key] = eng
         return eng
 
@@ -91,12 +95,33 @@ class _HCFlowBase(nn.Module):
         lr = self._check(lr, "lr")
         B, _, h, w = lr.shape
         eng = self.engine("reverse", B, h, w, lr.device)
+        key = (id(eng), lr.data_ptr(), lr._version, tuple(lr.shape))
+        same = self.reuse_lr_features and key == self._last_lr_key
+        self._last_lr_key = key
         with torch.cuda.device(lr.device):
             eng.ext["lr"].copy_(lr)
             self._draw_eps(eng, eps_std, eps, lr.device)
-            eng.run()
+            eng.run(reuse_lr_features=same)
             self.last = {"hr_raw": eng.ext["hr_raw"].clone()}
             return eng.ext["hr"].clone()
+
+
+    def sample_uint8(self, lr_u8, eps_std=None, eps=None, bgr=True):
+        """Inverse pass on 8-bit images: lr_u8 uint8 [B,h,w,3] as cv2 / the LMDB reader deliver it (HWC, BGR
+        unless bgr=False) -> uint8 [B,H,W,3] in the same convention.  Replaces, on the device, the reference's
+        read_img / BGR->RGB / HWC->CHW (codes/data/util.py:72-86, GTLQ_dataset.py:109-115) in front of the net and
+        tensor2img (codes/utils/util.py:790-816) behind it; the flow itself is the same launch plan."""
+        if lr_u8.dtype != torch.uint8 or lr_u8.dim() != 4 or lr_u8.shape[3] != 3:
+            raise ValueError("lr_u8 must be uint8 [B,h,w,3], got {} {}".format(lr_u8.dtype, tuple(lr_u8.shape)))
+        if not lr_u8.is_cuda:
+            raise RuntimeError("hcflow_b200 runs on CUDA tensors only (no CPU fallback)")
+        B, h, w, _ = lr_u8.shape
+        eng = self.engine("reverse", B, h, w, lr_u8.device, io="u8" if bgr else "u8rgb")
+        with torch.cuda.device(lr_u8.device):
+            eng.ext["lr_u8"].copy_(lr_u8)
+            self._draw_eps(eng, eps_std, eps, lr_u8.device)
+            eng.run()
+            return eng.ext["hr_u8"].clone()
 
 
 class HCFlowNet_SR(_HCFlowBase):

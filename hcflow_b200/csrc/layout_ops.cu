@@ -179,6 +179,49 @@ extern "C" int hcf_split16(const float* src, int32_t ld, int32_t C, int64_t npix
   return finish_launch("hcf_split16");
 }
 
+// ---- uint8 image edges: images enter and leave the engine as the 8-bit HWC arrays cv2 produces.
+// in:  codes/data/util.py:72-86 (astype(float32) / 255.), GTLQ_dataset.py:109-115 (BGR -> RGB, HWC -> CHW)
+// out: codes/utils/util.py:790-816 tensor2img (clamp [0,1], RGB -> BGR, (x * 255.0).round() -> uint8, CHW -> HWC)
+__global__ void __launch_bounds__(hcf::LT) u8_to_nhwc_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst,
+                                                             long long npix, int ld, int swap_rb) {
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  const uint8_t* sp = src + pix * 3;
+  float* d = dst + pix * ld;
+  const float c0 = (float)sp[0] / 255.f, c1 = (float)sp[1] / 255.f, c2 = (float)sp[2] / 255.f;
+  d[0] = swap_rb ? c2 : c0;
+  d[1] = c1;
+  d[2] = swap_rb ? c0 : c2;
+}
+
+__global__ void __launch_bounds__(hcf::LT) nhwc_to_u8_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst,
+                                                             long long npix, int ld, int swap_rb) {
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  const float* sp = src + pix * ld;
+  uint8_t* d = dst + pix * 3;
+  float v[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) v[c] = rintf(fminf(fmaxf(sp[c], 0.f), 1.f) * 255.f);   // numpy round = half to even
+  d[0] = (uint8_t)(swap_rb ? v[2] : v[0]);
+  d[1] = (uint8_t)v[1];
+  d[2] = (uint8_t)(swap_rb ? v[0] : v[2]);
+}
+
+extern "C" int hcf_u8_hwc_to_nhwc(const uint8_t* src, float* dst, int32_t ld, int64_t npix, int32_t swap_rb, void* stream) {
+  using namespace hcf;
+  HCF_REQUIRE(src && dst && ld >= 3 && npix > 0, "u8_hwc_to_nhwc: bad args");
+  u8_to_nhwc_kernel<<<(unsigned)((npix + LT - 1) / LT), LT, 0, (cudaStream_t)stream>>>(src, dst, npix, ld, swap_rb);
+  return finish_launch("hcf_u8_hwc_to_nhwc");
+}
+
+extern "C" int hcf_nhwc_to_u8_hwc(const float* src, int32_t ld, uint8_t* dst, int64_t npix, int32_t swap_rb, void* stream) {
+  using namespace hcf;
+  HCF_REQUIRE(src && dst && ld >= 3 && npix > 0, "nhwc_to_u8_hwc: bad args");
+  nhwc_to_u8_kernel<<<(unsigned)((npix + LT - 1) / LT), LT, 0, (cudaStream_t)stream>>>(src, dst, npix, ld, swap_rb);
+  return finish_launch("hcf_nhwc_to_u8_hwc");
+}
+
 // nearest-neighbour upsampling by 2^shift between NHWC views (F.interpolate(..., mode='nearest'),
 // FlowNet_SR_x4.py:98,117): materialises a conv input segment so that the conv can run on the tensor cores
 __global__ void __launch_bounds__(hcf::LT) upsample_kernel(const float4* __restrict__ src, float4* __restrict__ dst,

@@ -270,6 +270,11 @@ int hcf_haar_inverse(const hcf_squeeze_args* a, void* stream);
 /* dst[..., :C] = src[..., :C] for two NHWC views of size [B,H,W] (Basic.py:489-499 Split / cat when a view
  * would break TMA alignment). */
 int hcf_copy_view(const hcf_squeeze_args* a, void* stream);
+/* 8-bit image edges: src uint8 [npix][3] as cv2 delivers it (BGR when swap_rb) -> the 3 leading channels of
+ * an fp32 NHWC view in [0,1], RGB (codes/data/util.py:72-86, GTLQ_dataset.py:109-115); and back: clamp [0,1],
+ * (x * 255).round() half-to-even, RGB -> BGR when swap_rb (codes/utils/util.py:790-816 tensor2img). */
+int hcf_u8_hwc_to_nhwc(const uint8_t* src, float* dst, int32_t ld, int64_t npix, int32_t swap_rb, void* stream);
+int hcf_nhwc_to_u8_hwc(const float* src, int32_t ld, uint8_t* dst, int64_t npix, int32_t swap_rb, void* stream);
 /* nearest-neighbour upsampling by 2^shift (1..3) from the low-res view src to the high-res view dst (a->H, a->W =
  * high-res size; C % 4 == 0, 16-byte aligned views): materialises an up-sampled conv segment
  * (F.interpolate(mode='nearest'), FlowNet_SR_x4.py:98,117) so that the conv runs on the tensor cores. */

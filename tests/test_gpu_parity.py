@@ -650,3 +650,45 @@ def test_ragged_size_against_oracle(precision, tol, report):
     err = maxabs(raw, want)
     report["ragged_12x20/{}".format(precision)] = err
     assert err < tol, (precision, err)
+
+
+def test_uint8_image_edges_match_the_reference_conversions():
+    """sample_uint8: uint8 HWC BGR in / out.  Expected values restate the reference's host-side conversions
+    (codes/data/util.py:72-86 read_img: astype(float32) / 255.; GTLQ_dataset.py:109-115: BGR -> RGB, HWC -> CHW;
+    codes/utils/util.py:790-816 tensor2img: clamp, RGB -> BGR, (x * 255.0).round(), uint8) around the fp32 module call
+    with the same noise: the 8-bit outputs must be identical."""
+    import numpy as np
+    opt, net, sd = _net_cuda("sr_x4", "f16x3")
+    B, h, w = 2, 12, 20
+    rng = np.random.RandomState(3)
+    lr_u8 = rng.randint(0, 256, size=(B, h, w, 3)).astype(np.uint8)
+    unit = synth.synthetic_noise(orc.noise_shapes(opt, B, h, w, True), seed=4)
+    img = lr_u8.astype(np.float32) / 255.
+    lr_f = torch.from_numpy(np.ascontiguousarray(np.transpose(img[:, :, :, [2, 1, 0]], (0, 3, 1, 2)))).float()
+    with torch.no_grad():
+        hr = net(lr=lr_f.cuda(), eps_std=0.8, reverse=True, eps=unit).cpu()
+        got = net.sample_uint8(torch.from_numpy(lr_u8).cuda(), eps_std=0.8, eps=unit).cpu().numpy()
+    t = hr.float().clamp_(0, 1).numpy()
+    want = np.stack([(np.transpose(t[i][[2, 1, 0], :, :], (1, 2, 0)) * 255.0).round().astype(np.uint8) for i in range(B)])
+    assert got.shape == want.shape == (B, 4 * h, 4 * w, 3) and got.dtype == np.uint8
+    assert np.array_equal(got, want), int(np.abs(got.astype(int) - want.astype(int)).max())
+
+
+def test_lr_feature_reuse_is_bit_identical(report):
+    """net.reuse_lr_features: sampling the same LR tensor again skips the deepest level's encoder chain
+    and must give exactly the bits of a full run with the same noise; a new LR tensor triggers a full run."""
+    opt, net, sd = _net_cuda("sr_x4", "f16x3")
+    B = 4
+    lr = synth.synthetic_lr(B, 24, 24, seed=31).cuda()
+    lr2 = synth.synthetic_lr(B, 24, 24, seed=32).cuda()
+    e1 = synth.synthetic_noise(orc.noise_shapes(opt, B, 24, 24, True), seed=33)
+    e2 = synth.synthetic_noise(orc.noise_shapes(opt, B, 24, 24, True), seed=34)
+    with torch.no_grad():
+        want = [net(lr=x, eps_std=0.8, reverse=True, eps=e).clone() for x, e in ((lr, e1), (lr, e2), (lr2, e1), (lr2, e2))]
+        net.reuse_lr_features = True
+        got = [net(lr=x, eps_std=0.8, reverse=True, eps=e).clone() for x, e in ((lr, e1), (lr, e2), (lr2, e1), (lr2, e2))]
+        eng = [e for e in net._engines.values()][-1]
+    assert "tail" in eng._graphs and len(eng._lr_only_calls()) >= 2
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    report["lr_feature_reuse"] = {"skipped_launches": len(eng._lr_only_calls()), "launches": eng.launches_per_run}
