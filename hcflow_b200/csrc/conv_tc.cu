@@ -68,6 +68,7 @@ struct LayerDesc {
   int map_idx[3];     // tensor map of each segment (fp16 kernels: the hi plane)
   int map_lo[3];      // fp16 kernels, split layers: tensor map of the lo plane
   int seg_end[3];     // chunk index where segment i ends (prefix sums)
+  int seg_last_k[3];  // K-steps (of 4 per chunk) that hold real channels in the LAST chunk of each segment
   int kchunks;        // total 32-channel chunks
   int N;              // UMMA N (multiple of 16, <= 128)
   int cout;
@@ -562,7 +563,7 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
     uint32_t a_it = 0, b_it = 0, t_it = 0;
     int cur_layer = -1, kchunks = 0, slab_taps = 1, slabs = 1, tap0 = 0;
     uint32_t parts = 1, nb = 0, nb_n = 0, idesc_n = 0, idesc = 0, n_cols = 0;
-    int split_kc = 0;
+    int split_kc = 0, e0 = 0, e1 = 0, lk0 = 4, lk1 = 4, lk2 = 4;
     HCF_T(tm0);
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++t_it) {
       const int layer = item / p.n_tiles;
@@ -579,6 +580,8 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
         nb = NB * (ROW_BYTES >> 4);      // one tap of B in 16-byte units (split chunk)
         nb_n = N * (ROW_BYTES >> 4);     // ... of a one-pass chunk
         split_kc = parts == 2 ? __ldg(&L->split_kc) : 0;
+        e0 = __ldg(&L->seg_end[0]); e1 = __ldg(&L->seg_end[1]);
+        lk0 = __ldg(&L->seg_last_k[0]); lk1 = __ldg(&L->seg_last_k[1]); lk2 = __ldg(&L->seg_last_k[2]);
         const uint32_t fmt = F16 ? 0u : 2u;   // A / B format: F16 = 0, TF32 = 2; D = F32
         idesc_n = (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((128u >> 4) << 24);
         idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((NB >> 3) << 17) | ((128u >> 4) << 24);
@@ -604,6 +607,9 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
         HCF_ACC(PROF_M_CONVA, tfa1, tfa2);
         const uint64_t a0 = a_tmpl + ((smem_base + sA * A_STAGE) >> 4);
         const bool split = PASSES == 3 && parts == 2 && kc < split_kc;   // this chunk: hi + lo on both operands
+        // a segment's last chunk may be partly padding (96 = 64 + 32 channels, the 3..12 channels of z1): only the
+        // K-steps that hold real channels are issued
+        const int kmax = (kc == kchunks - 1) ? lk2 : ((kc == e0 - 1) ? lk0 : ((kc == e1 - 1) ? lk1 : 4));
         const uint32_t nb_kc = split ? nb : nb_n;
         const uint32_t idesc_kc = split ? idesc : idesc_n;
         for (int sl = 0; sl < slabs; ++sl) {
@@ -623,6 +629,7 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
               const uint64_t b_tap = b0 + (uint32_t)t * nb_kc;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
+                if (k >= kmax) break;
                 const uint64_t bd = b_tap + 2u * k;
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
@@ -1386,10 +1393,15 @@ static int chain_create(const hcf_conv_args* args, const void* const* wtc, const
           L.map_idx[s] = map_for(sg.ptr, sg.ld, sg.C);
         }
         kc += (sg.C + kch - 1) / kch;
+        const int rem = sg.C % kch == 0 ? kch : sg.C % kch;     // channels in the segment's last chunk
+        L.seg_last_k[s] = (rem + kch / 4 - 1) / (kch / 4);
+      } else {
+        L.seg_last_k[s] = 4;
       }
       L.seg_end[s] = s < a.nseg ? kc : (1 << 30);
     }
     L.seg_end[a.nseg - 1] = 1 << 30;
+    L.seg_last_k[2] = L.seg_last_k[a.nseg - 1];   // slot 2 = the FINAL segment's value (matched by kc == kchunks - 1)
     L.kchunks = kc;
     L.split_kc = L.parts == 2 ? kc : 0;
     if (f16 && L.parts == 2 && layer_split && layer_split[i] >= 0) {
