@@ -13,6 +13,7 @@ import torch
 from . import _lib as L
 from . import plan as P
 from . import prep
+from . import rewrite
 
 
 class Engine:
@@ -133,97 +134,16 @@ class Engine:
         return "{}{}|{}".format(op.weight, op.w_in or "", ",".join(str(v.C) for v, _ in op.segs))
 
     def _raw_weight(self, op):
-        """[Cout, Cin, ks, ks] fp32 CPU weight of a conv op; engine-level rewrites may slice the input-channel
-        axis (w_in) or concatenate several parameters along Cout (weight = tuple of (key, lo, hi))."""
-        sd = self._sd_cpu
-        if isinstance(op.weight, str):
-            w = sd[op.weight].detach().float()
-            return w[:, op.w_in[0]:op.w_in[1]].contiguous() if op.w_in else w
-        return torch.cat([sd[k].detach().float()[:, lo:hi] for k, lo, hi in op.weight], 0).contiguous()
+        return rewrite.raw_weight(self._sd_cpu, op)
 
     def _rewrite_ops(self):
-        """Engine-level rewrite of the plan for the tensor-core modes.  The conditional FlowSteps of a level all run
-        their sub-net's first conv on cat(z1, u) with the SAME encoder feature u (ConditionalFlow.py:62-66,
-        AffineCouplings.py:31): W * cat(z1, u) = W_z * z1 + W_u * u, and the W_u * u parts of all steps are one wide
-        conv over u (Cout = steps x 64, UMMA N = 128) computed once per level; each step then convolves only its few
-        z1 channels and adds its slice before ActNorm + ReLU (hcf_conv_args.pre)."""
-        ops = list(self.plan.ops)
-        if self.precision == "fp32":
-            return ops
-        # up-sampled conv segments (cat[z, up2(cf2), up4(cf3)] of the encoders' first conv) are materialised once, so
-        # that conv joins the level's chained tensor-core launch instead of running on the CUDA cores
-        mat = []
-        for op in ops:
-            if isinstance(op, P.ConvOp) and any(up > 0 for _, up in op.segs) and all(
-                    v.C % 4 == 0 and v.off % 4 == 0 and v.buf.C % 4 == 0 for v, up in op.segs if up > 0):
-                segs = []
-                for v, up in op.segs:
-                    if up > 0:
-                        ub = P.Buf("up{}_{}_{}".format(up, v.buf.name, v.off), op.H, op.W, v.C)
-                        if ub.name not in self.bufs:
-                            self.bufs[ub.name] = torch.zeros(self.B, op.H, op.W, v.C, dtype=torch.float32, device=self.device)
-                        dst = P.View(ub, 0, v.C)
-                        mat.append(P.LayoutOp("upsample", op.H, op.W, v.C, v, dst, post=up))
-                        segs.append((dst, 0))
-                    else:
-                        segs.append((v, 0))
-                op = P.ConvOp(op.H, op.W, segs, op.ks, op.cout, op.weight, op.bias, op.scale, op.act, op.out, op.out2,
-                              op.res1, op.alpha1, op.res2, op.alpha2, op.tag)
-            mat.append(op)
-        ops = mat
-        if not self.share_cond:
-            return self._fuse_steps_pass(ops)
-        groups = {}
-        for i, op in enumerate(ops):
-            if isinstance(op, P.ConvOp) and op.tag == "fcn.conv1" and len(op.segs) == 2 and op.segs[1][1] == 0:
-                v = op.segs[1][0]
-                groups.setdefault((v.buf.name, v.off, v.C, op.H, op.W, op.cout, op.segs[0][0].C), []).append(i)
-        inserts = {}
-        for (bname, off, cc, H, W, cout, zc), idxs in groups.items():
-            if len(idxs) < 2 or cout > 128 or cout % 4 != 0:
-                continue
-            n = len(idxs)
-            per = max(1, 128 // cout)
-            ubuf = P.Buf("ucond_{}_{}".format(bname, off), H, W, n * cout)
-            self.bufs[ubuf.name] = torch.zeros(self.B, H, W, ubuf.C, dtype=torch.float32, device=self.device)
-            cond = ops[idxs[0]].segs[1][0]
-            uops = []
-            for g in range(0, n, per):
-                mem = idxs[g:g + per]
-                uops.append(P.ConvOp(H, W, [(cond, 0)], 3, cout * len(mem),
-                                     tuple((ops[m].weight, zc, zc + cc) for m in mem), None, None, P.ACT_NONE,
-                                     P.View(ubuf, g * cout, cout * len(mem)), tag="fcn.ucond"))
-            inserts[idxs[0]] = uops
-            for j, m in enumerate(idxs):
-                o = ops[m]
-                ops[m] = P.ConvOp(o.H, o.W, [o.segs[0]], o.ks, o.cout, o.weight, o.bias, o.scale, o.act, o.out, tag=o.tag,
-                                  w_in=(0, zc), pre=P.View(ubuf, j * cout, cout))
-        out = []
-        for i, op in enumerate(ops):
-            out.extend(inserts.get(i, []))
-            out.append(op)
-        return self._fuse_steps_pass(out)
-
-    def _fuse_steps_pass(self, out):
-        if not self.fuse_steps:
-            return out
-        # FlowStep tail fused into the sub-net's last conv (hcf_conv_step): removes one launch per step and lets the
-        # convs of consecutive steps of a level run as ONE chained launch
-        fused = []
-        for op in out:
-            prev = fused[-1] if fused else None
-            if (isinstance(op, P.StepOp) and op.variant == "inverse" and op.mode == "affine" and op.h is not None
-                    and isinstance(prev, P.ConvOp) and prev.tag == "fcn.conv3" and prev.step is None
-                    and prev.out == op.h and prev.out2 is None and prev.res1 is None and prev.res2 is None
-                    and prev.cout == 2 * (op.z.C - op.n_pass) and prev.cout <= 32 and op.z.C <= 24
-                    and (prev.H, prev.W) == (op.H, op.W)):
-                prev.step = op
-                continue
-            if isinstance(op, P.ConvOp) and op.tag == "fcn.conv3":
-                op = P.ConvOp(op.H, op.W, op.segs, op.ks, op.cout, op.weight, op.bias, op.scale, op.act, op.out,
-                              tag=op.tag, w_in=op.w_in, pre=op.pre)   # private copy: the plan's op stays untouched
-            fused.append(op)
-        return fused
+        """The plan as the tensor-core modes execute it (rewrite.py): materialised up-sampled segments, shared
+        conditioning convs, fused FlowStep tails; the extra buffers are allocated here."""
+        ops, extra = rewrite.rewrite_ops(self.plan.ops, self.precision, self.share_cond, self.fuse_steps)
+        for name, b in extra.items():
+            if name not in self.bufs:
+                self.bufs[name] = torch.zeros(self.B, b.H, b.W, b.C, dtype=torch.float32, device=self.device)
+        return ops
 
     # ------------------------------------------------------------------ lowering
     def _lower(self):

@@ -1,0 +1,113 @@
+"""Engine-level rewrites of a launch plan for the tensor-core modes (pure functions over plan ops: no CUDA, so
+the host logic is covered by the CPU tests through tests/plan_emulator.py).
+
+  1. up-sampled conv segments (cat[z, up2(cf2), up4(cf3)] of an encoder's first conv, FlowNet_SR_x4.py:98,117) are
+     materialised once, so that conv joins the level's chained tensor-core launch;
+  2. shared conditioning: the conditional FlowSteps of a level all run their sub-net's first conv on cat(z1, u) with
+     the SAME encoder feature u (ConditionalFlow.py:62-66, AffineCouplings.py:31): W * cat(z1, u) = W_z * z1 + W_u * u,
+     and the W_u * u parts of all steps are wide convs over u (Cout = 2 steps x 64 = UMMA N 128) computed once per
+     level; each step convolves only its few z1 channels and adds its slice before ActNorm + ReLU (hcf_conv_args.pre);
+  3. the FlowStep tail (FlowStep.py:55-64, reverse) fused into the sub-net's last conv (hcf_conv_step): removes one
+     launch per step and lets the convs of consecutive steps of a level run as ONE chained launch.
+"""
+import torch
+
+from . import plan as P
+
+
+def raw_weight(sd, op):
+    """[Cout, Cin, ks, ks] fp32 CPU weight of a conv op; rewrites may slice the input-channel axis (op.w_in) or
+    concatenate several parameters along Cout (op.weight = tuple of (key, lo, hi))."""
+    if isinstance(op.weight, str):
+        w = sd[op.weight].detach().float()
+        return w[:, op.w_in[0]:op.w_in[1]].contiguous() if op.w_in else w
+    return torch.cat([sd[k].detach().float()[:, lo:hi] for k, lo, hi in op.weight], 0).contiguous()
+
+
+def materialise_upsampled(ops, bufs):
+    out = []
+    for op in ops:
+        if isinstance(op, P.ConvOp) and any(up > 0 for _, up in op.segs) and all(
+                v.C % 4 == 0 and v.off % 4 == 0 and v.buf.C % 4 == 0 for v, up in op.segs if up > 0):
+            segs = []
+            for v, up in op.segs:
+                if up > 0:
+                    ub = bufs.setdefault("up{}_{}_{}".format(up, v.buf.name, v.off),
+                                         P.Buf("up{}_{}_{}".format(up, v.buf.name, v.off), op.H, op.W, v.C))
+                    dst = P.View(ub, 0, v.C)
+                    out.append(P.LayoutOp("upsample", op.H, op.W, v.C, v, dst, post=up))
+                    segs.append((dst, 0))
+                else:
+                    segs.append((v, 0))
+            op = P.ConvOp(op.H, op.W, segs, op.ks, op.cout, op.weight, op.bias, op.scale, op.act, op.out, op.out2,
+                          op.res1, op.alpha1, op.res2, op.alpha2, op.tag)
+        out.append(op)
+    return out
+
+
+def share_conditioning(ops, bufs):
+    ops = list(ops)
+    groups = {}
+    for i, op in enumerate(ops):
+        if isinstance(op, P.ConvOp) and op.tag == "fcn.conv1" and len(op.segs) == 2 and op.segs[1][1] == 0:
+            v = op.segs[1][0]
+            groups.setdefault((v.buf.name, v.off, v.C, op.H, op.W, op.cout, op.segs[0][0].C), []).append(i)
+    inserts = {}
+    for (bname, off, cc, H, W, cout, zc), idxs in groups.items():
+        if len(idxs) < 2 or cout > 128 or cout % 4 != 0:
+            continue
+        n = len(idxs)
+        per = max(1, 128 // cout)
+        ubuf = bufs.setdefault("ucond_{}_{}".format(bname, off), P.Buf("ucond_{}_{}".format(bname, off), H, W, n * cout))
+        cond = ops[idxs[0]].segs[1][0]
+        uops = []
+        for g in range(0, n, per):
+            mem = idxs[g:g + per]
+            uops.append(P.ConvOp(H, W, [(cond, 0)], 3, cout * len(mem),
+                                 tuple((ops[m].weight, zc, zc + cc) for m in mem), None, None, P.ACT_NONE,
+                                 P.View(ubuf, g * cout, cout * len(mem)), tag="fcn.ucond"))
+        inserts[idxs[0]] = uops
+        for j, m in enumerate(idxs):
+            o = ops[m]
+            ops[m] = P.ConvOp(o.H, o.W, [o.segs[0]], o.ks, o.cout, o.weight, o.bias, o.scale, o.act, o.out, tag=o.tag,
+                              w_in=(0, zc), pre=P.View(ubuf, j * cout, cout))
+    out = []
+    for i, op in enumerate(ops):
+        out.extend(inserts.get(i, []))
+        out.append(op)
+    return out
+
+
+STEP_MAXC = 24   # csrc/conv_tc.cu
+
+
+def fuse_steps(ops):
+    fused = []
+    for op in ops:
+        prev = fused[-1] if fused else None
+        if (isinstance(op, P.StepOp) and op.variant == "inverse" and op.mode == "affine" and op.h is not None
+                and isinstance(prev, P.ConvOp) and prev.tag == "fcn.conv3" and prev.step is None
+                and prev.out == op.h and prev.out2 is None and prev.res1 is None and prev.res2 is None
+                and prev.cout == 2 * (op.z.C - op.n_pass) and prev.cout <= 32 and op.z.C <= STEP_MAXC
+                and (prev.H, prev.W) == (op.H, op.W)):
+            prev.step = op
+            continue
+        if isinstance(op, P.ConvOp) and op.tag == "fcn.conv3":
+            op = P.ConvOp(op.H, op.W, op.segs, op.ks, op.cout, op.weight, op.bias, op.scale, op.act, op.out,
+                          tag=op.tag, w_in=op.w_in, pre=op.pre)   # private copy: the plan's op stays untouched
+        fused.append(op)
+    return fused
+
+
+def rewrite_ops(plan_ops, precision, share_cond=True, fuse=True):
+    """-> (ops, {name: Buf} of the extra fp32 buffers the rewritten ops use)."""
+    ops = list(plan_ops)
+    bufs = {}
+    if precision == "fp32":
+        return ops, bufs
+    ops = materialise_upsampled(ops, bufs)
+    if share_cond:
+        ops = share_conditioning(ops, bufs)
+    if fuse:
+        ops = fuse_steps(ops)
+    return ops, bufs

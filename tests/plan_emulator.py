@@ -13,14 +13,19 @@ import torch.nn.functional as F
 
 from hcflow_b200 import plan as P
 from hcflow_b200 import prep
+from hcflow_b200 import rewrite
 
 
 class Emulator:
-    def __init__(self, net, plan, dtype=torch.float32):
+    def __init__(self, net, plan, dtype=torch.float32, ops=None, extra_bufs=None):
+        """ops / extra_bufs: an engine-level rewrite of plan.ops (hcflow_b200.rewrite) to interpret instead."""
         self.plan = plan
+        self.ops = list(plan.ops) if ops is None else ops
         self.dtype = dtype
         self.sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
-        self.bufs = {n: torch.zeros(plan.B, b.H, b.W, b.C, dtype=dtype) for n, b in plan.bufs.items()}
+        allb = dict(plan.bufs)
+        allb.update(extra_bufs or {})
+        self.bufs = {n: torch.zeros(plan.B, b.H, b.W, b.C, dtype=dtype) for n, b in allb.items()}
         self.ext = {}
         self.logdet = torch.zeros(plan.B, dtype=torch.float64)
         self.quant = getattr(net, "quant", 256)
@@ -31,7 +36,7 @@ class Emulator:
     def _conv(self, op):
         npad = prep.npad_for(op.cout)
         segc = [v.C for v, _ in op.segs]
-        wp = prep.pack_conv_weight(self.sd[op.weight], segc, npad).to(self.dtype)  # [taps, kpad, npad]
+        wp = prep.pack_conv_weight(rewrite.raw_weight(self.sd, op), segc, npad).to(self.dtype)  # [taps, kpad, npad]
         ins = []
         for (v, up), c in zip(op.segs, segc):
             x = self.view(v).permute(0, 3, 1, 2)
@@ -46,6 +51,8 @@ class Emulator:
         ks = op.ks
         w = wp.permute(2, 1, 0).reshape(npad, x.shape[1], ks, ks)
         y = F.conv2d(x, w, None, padding=ks // 2)
+        if op.pre is not None:   # pre-activation addend (hcf_conv_args.pre)
+            y[:, :op.cout] = y[:, :op.cout] + self.view(op.pre).permute(0, 3, 1, 2)
         if op.bias:
             y = y + prep.pad_vec(prep.derive(self.sd, op.bias), npad, 0.0).to(self.dtype).view(1, -1, 1, 1)
         if op.scale:
@@ -63,6 +70,8 @@ class Emulator:
         self.view(op.out).copy_(y)
         if op.out2 is not None:
             self.view(op.out2).copy_(y)
+        if op.step is not None:   # fused FlowStep tail (hcf_conv_step): h is consumed right away
+            self._step(op.step)
 
     def _step(self, op):
         z = self.view(op.z)
@@ -127,6 +136,9 @@ class Emulator:
             C = op.C
             if op.variant == "copy":
                 dst.copy_(src.clone())
+            elif op.variant == "upsample":   # nearest, factor 2^post (hcf_upsample_nearest)
+                f = 1 << op.post
+                dst.copy_(src.repeat_interleave(f, dim=1).repeat_interleave(f, dim=2))
             elif op.variant == "squeeze":   # src hi-res C -> dst low-res 4C
                 B, H2, W2, _ = src.shape
                 x = src.reshape(B, H2 // 2, 2, W2 // 2, 2, C).permute(0, 1, 3, 5, 2, 4)  # b,y,x,c,i,j
@@ -157,7 +169,7 @@ class Emulator:
             hr = self.ext["hr"]
             const += prep.quant_logdet(self.quant, hr.shape[2] * hr.shape[3])
         self.logdet.fill_(const)
-        for op in self.plan.ops:
+        for op in self.ops:
             if isinstance(op, P.ConvOp):
                 self._conv(op)
             elif isinstance(op, P.StepOp):

@@ -61,3 +61,28 @@ def test_forward_plan_matches_golden(cfg):
         assert maxabs(out["fake_lr"], g["fwd_fake_lr"]) < 2e-4
         assert maxabs(out["fake_z1"], g["fwd_z1"]) < 2e-3
         assert maxabs(out["fake_z2"], g["fwd_z2"]) < 2e-3
+
+
+@pytest.mark.parametrize("cfg", CASES)
+def test_rewritten_reverse_plan_matches_golden(cfg):
+    """The engine-level rewrites of the tensor-core modes (hcflow_b200/rewrite.py: materialised up-sampled segments,
+    shared conditioning convs + pre-activation addend, FlowStep tails fused into the sub-net's last conv), interpreted
+    on the CPU, must still reproduce the reference goldens -- and must actually have rewritten something."""
+    from hcflow_b200 import rewrite
+    g = load_golden(cfg)
+    opt, net, sd = net_and_weights(cfg)
+    lr, hr, eps = _inputs(g, opt)
+    plan = P.build_plan(net, "reverse", g["B"], g["h"], g["w"])
+    ops, extra = rewrite.rewrite_ops(plan.ops, "f16x3")
+    assert rewrite.rewrite_ops(plan.ops, "fp32")[0] == list(plan.ops)
+    n_step = sum(isinstance(o, P.StepOp) for o in plan.ops)
+    n_left = sum(isinstance(o, P.StepOp) for o in ops)
+    n_fused = sum(isinstance(o, P.ConvOp) and o.step is not None for o in ops)
+    assert n_fused + n_left == n_step
+    assert not any(isinstance(o, P.ConvOp) and any(up for _, up in o.segs) for o in ops)
+    if is_sr(opt):
+        assert n_fused > 0 and any(isinstance(o, P.ConvOp) and o.pre is not None for o in ops)
+        assert any(isinstance(o, P.LayoutOp) and o.variant == "upsample" for o in ops)
+    em = Emulator(net, plan, ops=ops, extra_bufs=extra)
+    out = em.run(lr=lr, **{"eps{}".format(i): e for i, e in enumerate(eps)})
+    assert maxabs(out["hr_raw"], g["inv_raw"]) < 2e-4
