@@ -103,6 +103,7 @@ SYMBOLS = {
                               C.c_void_p]),
     "hcf_conv_tc_plan_layers": (C.c_int32, [C.c_void_p]),
     "hcf_conv_tc_run": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hcf_conv_tc_plan_refresh": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hcf_conv_tc_plan_destroy": (None, [C.c_void_p]),
     "hcf_step_inverse": (C.c_int, [C.POINTER(StepArgs), C.c_void_p]),
     "hcf_step_forward_head": (C.c_int, [C.POINTER(StepArgs), C.c_void_p]),

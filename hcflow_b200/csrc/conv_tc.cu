@@ -110,6 +110,7 @@ struct Params {
                       // 64 no dependency waits
   const LayerDesc* layers;
   int* done;          // chain mode: per-tile count of completed layers (zeroed before the launch)
+  const float* epi;   // [n_layers][256]: bias (0) | scale (1) of every layer, padded: one coalesced load per layer change
   int step_tab;       // 1: the chain has fused FlowStep layers (shared memory carries their W^-1 / ActNorm tables)
   long long* prof;    // HCF_TC_PROF=1: cycles per role / wait class summed over CTAs (see PROF_* below)
 };
@@ -369,7 +370,7 @@ __device__ __forceinline__ bool deps_ready(const Deps& d, int layer) {
 
 // F16: operands are fp16 (hi / lo planes, 64 channels per 128-byte row, kind::f16); otherwise fp32 words read as TF32.
 template <int MT, int PASSES, int KS, bool F16>
-__global__ void __launch_bounds__((PASSES == 3 || F16) ? 320 : 192, 1)
+__global__ void __launch_bounds__(F16 ? 384 : (PASSES == 3 ? 320 : 192), 1)
 conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
   constexpr int HALO = KS / 2;
   constexpr int HALO_W = halo_w(KS);
@@ -395,6 +396,8 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
   // producer -> epilogue: number of this CTA's work items whose inputs have been acquired (monotonic counter; an
   // mbarrier would need the producer to be at most one phase ahead)
   const uint32_t dep_seq = tbar + 32u;
+  // fp16 kernels: items published by the publisher warp of epilogue group g (tbar + 36 + 4 g)
+  auto pub_seq = [&](int g) { return tbar + 36u + 4u * g; };
   const uint32_t tmem_slot = tbar + 48u;
   auto map_ptr = [&](int i) -> const CUtensorMap* { return &maps.m[i]; };
 
@@ -419,6 +422,8 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
       mbar_init(tmem_empty(a), 128);
     }
     asm volatile("st.shared.b32 [%0], %1;" ::"r"(dep_seq), "r"(0u) : "memory");
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(pub_seq(0)), "r"(0u) : "memory");
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(pub_seq(1)), "r"(0u) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -663,7 +668,7 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
     HCF_T(tm1);
     HCF_ACC(PROF_M_TOTAL, tm0, tm1);
     if (lane == 0) HCF_PROF_FLUSH(PROF_M_TOTAL, PROF_M_CONVA);
-  } else if (warp < 6 || F16) {
+  } else if (warp < 6 || (F16 && warp < 10)) {
     // ===================== epilogue =====================
     // fp16 kernels run TWO epilogue groups of four warps (warps 2-5 and 6-9): group g drains accumulator buffer g,
     // i.e. every other work item, so the single-warp-per-scheduler latency of the store code is halved.
@@ -729,10 +734,8 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
             (o16.lo == nullptr || o16.hi != nullptr))
           fast = (out ? 1 : 0) | (o16.hi ? 2 : 0) | (o16.lo ? 4 : 0);
         asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");   // everyone is done with the previous layer's bias / scale
-        if (et < N) {                                       // bias / scale are padded to >= N entries
-          s_bias[et] = has_bias ? __ldg(bias + et) : 0.f;
-          s_scale[et] = has_scale ? __ldg(scale + et) : 1.f;
-        }
+        s_bias[et] = __ldg(p.epi + (size_t)layer * 256 + et);          // inline table: no pointer chase
+        s_scale[et] = __ldg(p.epi + (size_t)layer * 256 + 128 + et);
         if (step_z) {
           if (step_w)
             for (int i = et; i < step_C * step_C; i += 128) st_w[i] = __ldg(step_w + i);
@@ -976,8 +979,20 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
       if (chain) {
         // publish: 128-thread barrier (the stores of every epilogue thread happen before it), then ONE thread
         // makes them visible at gpu scope and bumps the tile's counter (release side of the producer's acquire)
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-        if (et == 0) red_release_add(p.done + tile, 1);
+        if (F16) {
+          // hand the release to the group's publisher warp (the gpu-scope MEMBAR costs ~1.5k cycles): wait until it
+          // has published this group's previous item (so that the barrier is at most one phase ahead), then arrive
+          // without blocking
+          const uint32_t own = t_it >> 1;   // index of this item among the group's items
+          uint32_t seen;
+          do {
+            asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(seen) : "r"(pub_seq(grp)) : "memory");
+          } while (seen < own);
+          asm volatile("bar.arrive %0, 160;" ::"r"(3 + grp) : "memory");
+        } else {
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+          if (et == 0) red_release_add(p.done + tile, 1);
+        }
       }
       HCF_T(tl4);
       HCF_ACC(PROF_E_PUBLISH, tl3, tl4);
@@ -989,6 +1004,24 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
 #ifdef HCF_TC_PROF_BUILD
       if (prof_on && blockIdx.x == 0) atomicAdd((unsigned long long*)p.prof + PROF_LAUNCHES, 1ull);
 #endif
+    }
+  } else if (F16) {
+    // ===================== publishers (fp16 kernels, warps 10 and 11) =====================
+    // one warp per epilogue group: joins the group's 128 threads on a named barrier (their stores happen before it),
+    // then ONE lane makes them visible at gpu scope and bumps the tile's counter (release side of the producer's
+    // acquire) -- off the epilogue's critical path
+    if (chain) {
+      const int grp = warp - 10;
+      uint32_t own = 0;
+      for (int item = blockIdx.x + grp * gridDim.x; item < n_items; item += 2 * gridDim.x, ++own) {
+        const int tile = item % p.n_tiles;
+        asm volatile("bar.sync %0, 160;" ::"r"(3 + grp) : "memory");
+        if (lane == 0) {
+          red_release_add(p.done + tile, 1);
+          asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"(pub_seq(grp)), "r"(own + 1u) : "memory");
+        }
+        __syncwarp();
+      }
     }
   } else {
     // ===================== A_lo converters (PASSES == 3) =====================
@@ -1110,11 +1143,17 @@ static KernelFn pick_kernel(int mt, int passes, int ks, bool f16) {
 }  // namespace tc
 }  // namespace hcf
 
+extern "C" int hcf_conv_tc_plan_refresh(hcf_conv_tc_plan* pl, void* stream);
+extern "C" void hcf_conv_tc_plan_destroy(hcf_conv_tc_plan* p);
+
 struct hcf_conv_tc_plan {
   hcf::tc::Maps maps;
   hcf::tc::Params p;
   hcf::tc::KernelFn fn;
   hcf::tc::LayerDesc* d_layers;
+  float* d_epi;
+  std::vector<const float*>* epi_src;   // per layer: bias, scale device pointers and N (for hcf_conv_tc_plan_refresh)
+  std::vector<int>* epi_n;
   long long* d_prof;
   mutable long runs;
   size_t smem_bytes;
@@ -1496,25 +1535,40 @@ static int chain_create(const hcf_conv_args* args, const void* const* wtc, const
       return HCF_EINVAL;
     }
   }
-  cudaError_t e = cudaMalloc(&pl->d_layers, sizeof(LayerDesc) * n);
+  // inline epilogue constants: [layer][bias 128 | scale 128], gathered on the device from the padded per-layer vectors
+  pl->epi_src = new std::vector<const float*>();
+  pl->epi_n = new std::vector<int>();
+  for (int i = 0; i < n; ++i) {
+    pl->epi_src->push_back(args[i].bias);
+    pl->epi_src->push_back(args[i].scale);
+    pl->epi_n->push_back(layers[i].N);   // bias / scale are padded to >= N entries
+  }
+  cudaError_t e = cudaMalloc(&pl->d_epi, sizeof(float) * 256 * n);
+  if (e == cudaSuccess) {
+    std::vector<float> ident((size_t)256 * n);
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < 128; ++j) { ident[256 * i + j] = 0.f; ident[256 * i + 128 + j] = 1.f; }
+    e = cudaMemcpy(pl->d_epi, ident.data(), sizeof(float) * 256 * n, cudaMemcpyHostToDevice);
+  }
+  if (e == cudaSuccess && hcf_conv_tc_plan_refresh(pl, nullptr) != 0) e = cudaErrorUnknown;
+  p.epi = pl->d_epi;
+  if (e == cudaSuccess) e = cudaMalloc(&pl->d_layers, sizeof(LayerDesc) * n);
   if (e == cudaSuccess)
     e = cudaMemcpy(pl->d_layers, layers.data(), sizeof(LayerDesc) * n, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
-    if (pl->d_layers) cudaFree(pl->d_layers);
-    delete pl;
     set_error("tc_chain: layer table upload: %s", cudaGetErrorString(e));
+    hcf_conv_tc_plan_destroy(pl);
     return (int)e;
   }
   p.layers = pl->d_layers;
   pl->grid = dim3((unsigned)(p.n_tiles < sms ? p.n_tiles : sms));
-  pl->threads = (passes == 3 || f16) ? 320 : 192;
+  pl->threads = f16 ? 384 : (passes == 3 ? 320 : 192);
   pl->fn = pick_kernel(mt, passes, ks, f16);
   e = cudaFuncSetAttribute(reinterpret_cast<const void*>(pl->fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
                            SMEM_LIMIT);
   if (e != cudaSuccess) {
-    cudaFree(pl->d_layers);
-    delete pl;
     set_error("tc_chain: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    hcf_conv_tc_plan_destroy(pl);
     return (int)e;
   }
   *out = pl;
@@ -1541,6 +1595,27 @@ extern "C" int hcf_conv_chain16_create(const hcf_conv_args* args, const void* co
                                        hcf_conv_tc_plan** out) {
   return hcf::tc::chain_create(args, w16, layer_passes, layer_split, out_flags, n, done_flags, true, shadows, n_shadows,
                                seg16, out);
+}
+
+// Re-gathers the per-layer bias / scale vectors into the plan's inline table (they are read through it, not through
+// the argument pointers): call after the arrays behind hcf_conv_args.bias / .scale were rewritten in place.
+extern "C" int hcf_conv_tc_plan_refresh(hcf_conv_tc_plan* pl, void* stream) {
+  using namespace hcf;
+  HCF_REQUIRE(pl && pl->d_epi && pl->epi_src && pl->epi_n, "tc_plan_refresh: bad plan");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (size_t i = 0; i < pl->epi_n->size(); ++i) {
+    const float* b = (*pl->epi_src)[2 * i];
+    const float* sc = (*pl->epi_src)[2 * i + 1];
+    const size_t bytes = sizeof(float) * (size_t)(*pl->epi_n)[i];
+    cudaError_t e = cudaSuccess;
+    if (b) e = cudaMemcpyAsync(pl->d_epi + 256 * i, b, bytes, cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess && sc) e = cudaMemcpyAsync(pl->d_epi + 256 * i + 128, sc, bytes, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) {
+      set_error("tc_plan_refresh: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+  }
+  return 0;
 }
 
 extern "C" int hcf_conv_tc_plan_create(const hcf_conv_args* a, const float* wtc, int32_t passes,
@@ -1578,5 +1653,8 @@ extern "C" void hcf_conv_tc_plan_destroy(hcf_conv_tc_plan* p) {
     cudaFree(p->d_prof);
   }
   if (p->d_layers) cudaFree(p->d_layers);
+  if (p->d_epi) cudaFree(p->d_epi);
+  delete p->epi_src;
+  delete p->epi_n;
   delete p;
 }

@@ -38,6 +38,7 @@ class Engine:
         self._lr_features_valid = False
         self._keep = []          # ctypes structs must outlive the launches
         self._params = None
+        self._tc_registry = {}   # weight-image key -> (op, passes, split channels, fp16?) for in-place reload
         self._tc_plans = []
         self.weights = {}
         self.bufs = {}
@@ -128,6 +129,10 @@ class Engine:
             self.logdet_const += prep.quant_logdet(self.net.quant, self.h * s * self.w * s)
         self.logdet_init.fill_(self.logdet_const)
         self._sig = self.weight_signature()
+        for hnd in self._tc_plans:   # plans read bias / scale through their own gathered table
+            L.check(self.lib.hcf_conv_tc_plan_refresh(hnd, torch.cuda.current_stream(self.device).cuda_stream), "plan_refresh")
+        for key, (op, passes, split_ch, f16) in self._tc_registry.items():   # tensor-core weight images, in place
+            self.weights[key].copy_(self._pack_tc(op, passes, split_ch, f16))
 
     @staticmethod
     def _wkey(op):
@@ -346,15 +351,26 @@ class Engine:
     def _tc_eligible(self, a):
         return self.precision != "fp32" and bool(self.lib.hcf_conv_tc_supported(C.byref(a)))
 
+    def _pack_tc(self, op, passes, split_ch, f16):
+        """UMMA-ready weight image of a conv (host tensor): TF32 words or fp16 [hi ; lo] row blocks."""
+        if f16:
+            w = prep.pad_weight_for_tc(self._raw_weight(op), [v.C for v, _ in op.segs], chunk=64)
+            cout, kin, ks = w.shape[0], w.shape[1], w.shape[2]
+            split_kin = 0 if passes != 3 else (kin if split_ch < 0 else split_ch)
+            img = torch.zeros(self.lib.hcf_conv_tc16_weight_bytes(kin, cout, ks, split_kin) // 2, dtype=torch.float16)
+            L.check(self.lib.hcf_conv_tc16_pack_weights(w.data_ptr(), kin, cout, ks, split_kin, img.data_ptr()), "tc16_pack")
+            return img
+        w = prep.pad_weight_for_tc(self._raw_weight(op), [v.C for v, _ in op.segs])
+        cout, kin, ks = w.shape[0], w.shape[1], w.shape[2]
+        img = torch.zeros(self.lib.hcf_conv_tc_weight_bytes(kin, cout, ks, passes) // 4, dtype=torch.float32)
+        L.check(self.lib.hcf_conv_tc_pack_weights(w.data_ptr(), kin, cout, ks, passes, img.data_ptr()), "tc_pack")
+        return img
+
     def _tc_weights(self, op, passes):
         key = self._wkey(op) + "#tc{}".format(passes)
         if key not in self.weights:
-            w = prep.pad_weight_for_tc(self._raw_weight(op), [v.C for v, _ in op.segs])
-            cout, kin, ks = w.shape[0], w.shape[1], w.shape[2]
-            nbytes = self.lib.hcf_conv_tc_weight_bytes(kin, cout, ks, passes)
-            img = torch.zeros(nbytes // 4, dtype=torch.float32)
-            L.check(self.lib.hcf_conv_tc_pack_weights(w.data_ptr(), kin, cout, ks, passes, img.data_ptr()), "tc_pack")
-            self.weights[key] = img.to(self.device)
+            self.weights[key] = self._pack_tc(op, passes, -1, False).to(self.device)
+            self._tc_registry[key] = (op, passes, -1, False)
         return self.weights[key]
 
     # ---- fp16 chains ("f16" / "f16x3"): hi / lo planes shadowing the fp32 buffers -----------------------
@@ -396,13 +412,8 @@ class Engine:
     def _tc16_weights(self, op, passes, split_ch=-1):
         key = self._wkey(op) + "#tc16_{}_{}".format(passes, split_ch)
         if key not in self.weights:
-            w = prep.pad_weight_for_tc(self._raw_weight(op), [v.C for v, _ in op.segs], chunk=64)
-            cout, kin, ks = w.shape[0], w.shape[1], w.shape[2]
-            split_kin = 0 if passes != 3 else (kin if split_ch < 0 else split_ch)
-            nbytes = self.lib.hcf_conv_tc16_weight_bytes(kin, cout, ks, split_kin)
-            img = torch.zeros(nbytes // 2, dtype=torch.float16)
-            L.check(self.lib.hcf_conv_tc16_pack_weights(w.data_ptr(), kin, cout, ks, split_kin, img.data_ptr()), "tc16_pack")
-            self.weights[key] = img.to(self.device)
+            self.weights[key] = self._pack_tc(op, passes, split_ch, True).to(self.device)
+            self._tc_registry[key] = (op, passes, split_ch, True)
         return self.weights[key]
 
     @staticmethod

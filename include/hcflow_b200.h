@@ -184,6 +184,9 @@ int hcf_conv_chain16_create(const hcf_conv_args* args, const void* const* w16, c
 int hcf_split16(const float* src, int32_t ld, int32_t C, int64_t npix, void* hi, void* lo, int32_t dst_ld, void* stream);
 int32_t hcf_conv_tc_plan_layers(const hcf_conv_tc_plan* p);
 int hcf_conv_tc_run(const hcf_conv_tc_plan* p, void* stream);
+/* a plan reads bias / scale through an inline per-layer table gathered at creation: call this after the arrays
+ * behind hcf_conv_args.bias / .scale were rewritten in place (weight reload); copies are queued on `stream` */
+int hcf_conv_tc_plan_refresh(hcf_conv_tc_plan* p, void* stream);
 void hcf_conv_tc_plan_destroy(hcf_conv_tc_plan* p);
 
 /* ---- flow step ------------------------------------------------------------------ */

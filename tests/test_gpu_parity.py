@@ -692,3 +692,26 @@ def test_lr_feature_reuse_is_bit_identical(report):
     for a, b in zip(got, want):
         assert torch.equal(a, b)
     report["lr_feature_reuse"] = {"skipped_launches": len(eng._lr_only_calls()), "launches": eng.launches_per_run}
+
+
+@pytest.mark.parametrize("precision", ["f16x3", "tf32x3", "fp32"])
+def test_weight_reload_refreshes_every_derived_array(precision):
+    """load_state_dict on a net whose engine is already built (checkpoint reload, base_model.py:96-120): packed conv
+    weights, tensor-core weight images, the plans' inline bias / scale tables, W^-1 and the ActNorm vectors must all
+    follow -- the result has to equal a fresh net's bit for bit."""
+    opt, net, sd = _net_cuda("sr_x4", precision)
+    sd2 = synth.synthetic_state_dict(net.state_dict(), seed=2)
+    B, h, w = 2, 12, 12
+    lr = synth.synthetic_lr(B, h, w, seed=41).cuda()
+    unit = synth.synthetic_noise(orc.noise_shapes(opt, B, h, w, True), seed=42)
+    with torch.no_grad():
+        first = net(lr=lr, eps_std=0.8, reverse=True, eps=unit)
+        net.load_state_dict(sd2, strict=True)
+        got = net(lr=lr, eps_std=0.8, reverse=True, eps=unit)
+        fresh = build_net(opt)
+        fresh.load_state_dict(sd2, strict=True)
+        fresh = fresh.cuda().eval()
+        fresh.set_precision(precision)
+        want = fresh(lr=lr, eps_std=0.8, reverse=True, eps=unit)
+    assert not torch.equal(first, got)
+    assert torch.equal(got, want), float((got - want).abs().max())
