@@ -34,6 +34,7 @@ class ConvArgs(C.Structure):
         ("res1", C.c_void_p), ("res2", C.c_void_p),
         ("res2_ld", C.c_int32), ("alpha1", C.c_float), ("alpha2", C.c_float), ("pre_ld", C.c_int32),
         ("pre", C.c_void_p), ("step", C.POINTER(ConvStep)),
+        ("raw2", C.c_void_p), ("raw2_ld", C.c_int32), ("_pad2", C.c_int32),
     ]
 
 
@@ -144,7 +145,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.hcf_abi_version() != 1:
+    if lib.hcf_abi_version() != 2:
         raise HcfError("ABI version mismatch")
     _lib = lib
     return lib

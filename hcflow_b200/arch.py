@@ -36,6 +36,7 @@ class _HCFlowBase(nn.Module):
         self.use_chains = True   # fuse runs of tensor-core convs into one persistent chained launch
         self.share_cond = True   # tensor-core modes: the sub-nets' shared conditioning conv once per level (engine.py)
         self.fuse_steps = True   # tensor-core modes, inverse pass: FlowStep tail in the last sub-net conv's epilogue
+        self.pair_convs = True   # tensor-core modes: RDB growth convs in pairs (rewrite.pair_rdb_convs)
         # opt-in: when the SAME lr tensor (same storage, same version counter) is sampled again, keep the
         # deepest level's encoder features of the previous call instead of recomputing them
         self.reuse_lr_features = False
@@ -58,11 +59,12 @@ class _HCFlowBase(nn.Module):
     def engine(self, direction, B, h, w, device, io="f32"):
         from .engine import Engine
         key = (direction, B, h, w, str(device), self.precision, self.use_graph, self.use_chains, self.share_cond,
-               self.fuse_steps, io)
+               self.fuse_steps, io, self.pair_convs)
         eng = self._engines.get(key)
         if eng is None:
             eng = Engine(self, direction, B, h, w, device, precision=self.precision, use_graph=self.use_graph,
-                         use_chains=self.use_chains, share_cond=self.share_cond, fuse_steps=self.fuse_steps, io=io)
+                         use_chains=self.use_chains, share_cond=self.share_cond, fuse_steps=self.fuse_steps, io=io,
+                         pair_convs=self.pair_convs)
             self._engines[key] = eng
         return eng
 

@@ -232,7 +232,7 @@ int validate_conv_args(const hcf_conv_args* a) {
 }  // namespace hcf
 
 extern "C" int hcf_conv_fp32(const hcf_conv_args* a, void* stream) {
-  if (a && (a->pre || a->step)) {
+  if (a && (a->pre || a->step || a->raw2)) {
     hcf::set_error("conv_fp32: the pre-activation addend and the fused FlowStep are tensor-core kernel features");
     return HCF_ENOTSUP;
   }

@@ -1,35 +1,42 @@
-// 3x3 convolution as a persistent implicit GEMM on the 5th-generation tensor cores
-// (tcgen05 / TMEM / TMA, sm_100a).
+// 3x3 / 1x1 convolutions as a persistent implicit GEMM on the 5th-generation tensor cores
+// (tcgen05 / TMEM / TMA, sm_100a), single or CHAINED, with fused epilogues up to a whole FlowStep tail.
 //
-//   D[128 pixels, N] += A[128 pixels, 32 ch] * B[N, 32 ch]^T     per (tap, 32-channel chunk)
+//   D[128 pixels, N] += A[128 pixels, K chunk] * B[N, K chunk]^T     per (tap, chunk of one 128-byte row per pixel:
+//                                                                      32 fp32 channels read as TF32, or 64 fp16)
 //
 // Work item = MT vertically adjacent 16x8 pixel tiles of one image (UMMA M = 128 each) x all
 // N = ceil16(Cout) <= 128 output channels.  CTAs are persistent (grid = #SMs, items strided by
 // gridDim.x) and warp-specialised.  A launch executes either one convolution or a CHAIN of
-// dependent convolutions on the same pixel grid (e.g. the 211 convs of an RRDB encoder level):
-// item = (layer, tile) in layer-major order; a tile of layer l may start once the 3x3 tile
-// neighbourhood of layer l-1 is complete, tracked by per-tile counters in global memory
-// (release by the epilogue, acquire by the producer), so there is no kernel boundary, no
-// ramp-up / drain and no wave quantisation between the convs.  Roles:
-//   warp 0      TMA producer.  Per 32-channel chunk ONE 4-D TMA tile load brings the
-//               (16*MT+2) x 10 halo tile [rows][10][32 ch] (128-byte swizzle; out-of-bounds -> 0
-//               is exactly the conv's zero padding) into the A ring; the pre-swizzled weights
-//               stream through a second ring in (chunk, dy) slabs [3 taps][N][32 ch].
-//   warp 1      TMEM owner + MMA issuer: 9 taps x 4 K-steps of tcgen05.mma.kind::tf32 per chunk
-//               and sub-tile.  The nine taps do NOT reload activations: tap (dy,dx) is a smem
-//               descriptor whose start is shifted by (dy*10+dx) 128-byte rows into the same halo
+// dependent convolutions on the same pixel grid (the 213 convs of an RRDB encoder level; the shared
+// conditioning convs + all coupling sub-nets + FlowStep tails of a level): item = (layer, tile) in
+// layer-major order; a tile of layer l may start once the 3x3 tile neighbourhood of layer l-1 is
+// complete, tracked by per-tile counters in global memory (release after the epilogue, acquire by
+// the producer), so there is no kernel boundary, no ramp-up / drain and no wave quantisation
+// between the convs.  Template: MT, PASSES (3: some layer uses the operand split), KS (3: 3x3 with
+// 1x1 layers through the centre tap), F16 (fp16 hi / lo operand planes instead of TF32 words).  Roles:
+//   warp 0      TMA producer.  Per chunk ONE 4-D TMA tile load brings the (16*MT+2) x 10 halo tile
+//               [rows][10][128 B] (128-byte swizzle; out-of-bounds -> 0 is exactly the conv's zero
+//               padding) into the A ring (fp16 split chunks: the hi and the lo plane); the
+//               pre-swizzled weights stream through a second ring in slabs of 9 / 3 / 1 taps.  In a
+//               chain it first polls the dependency counters (relaxed loads, prefetched one item
+//               ahead), fences, and tells the epilogue groups that the item's inputs may be read.
+//   warp 1      TMEM owner + MMA issuer: taps x K-steps of tcgen05.mma per chunk (only the K-steps
+//               that hold real channels).  The nine taps do NOT reload activations: tap (dy,dx) is a
+//               smem descriptor whose start is shifted by (dy*10+dx) 128-byte rows into the same halo
 //               tile and whose 8-row-group stride (SBO) is the halo row pitch (1280 B).  The
 //               128B-swizzle XOR is a function of the absolute smem address, so a shifted view
-//               of a TMA-written tile stays consistent (verified on B200).
-//   warps 2..5  epilogue: tcgen05.ld -> bias / scale / activation / residuals -> global.  The
-//               accumulator is double-buffered in TMEM (2 x MT x N columns), so the epilogue of
-//               item i overlaps the loads and MMAs of item i+1.
-//   warps 6..9  (PASSES == 3 only) 3xTF32 split: the tensor core reads an fp32 word as TF32 by
-//               ignoring the low 13 mantissa bits, so the "hi" parts are free; these warps form
-//               A_lo = a - trunc(a) next to every A stage and B_lo = w - trunc(w) is precomputed on
-//               the host.  The three products take TWO MMAs per K-step: A x [B ; B_lo] as one
-//               2N-row operand (columns [0,N) and [N,2N) of the accumulator) and A_lo x B into
-//               columns [0,N); the epilogue adds the two column groups.
+//               of a TMA-written tile stays consistent (verified on B200).  Split chunks issue
+//               A_hi x [B_hi ; B_lo] (2N accumulator columns: main | correction) and A_lo x B_hi.
+//   warps 2..5  epilogue group 0 (and warps 6..9 = group 1 in the fp16 kernels: group g drains TMEM
+//               accumulator buffer g, i.e. every other item): tcgen05.ld -> per-warp staging transpose
+//               in shared memory -> 8 lanes per pixel: pre-activation addend, bias / scale,
+//               activation, residuals (prefetched tiles), full-line stores of the fp32 and / or
+//               fp16 hi / lo representations -- or, for the last conv of a coupling sub-net, the
+//               FlowStep inverse (affine coupling, W^-1, ActNorm) on z in place (thread = pixel).
+//   warps 6..9  (TF32 kernels with PASSES == 3) form A_lo = a - trunc(a) next to every A stage; the
+//               tensor core reads an fp32 word as TF32 by ignoring the low 13 mantissa bits.
+//   warps 10,11 (fp16 kernels) publishers: one per epilogue group, take the gpu-scope release of a
+//               finished tile (MEMBAR + counter increment) off the epilogue's path.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -67,6 +74,7 @@ struct LayerDesc {
   int nseg;
   int map_idx[3];     // tensor map of each segment (fp16 kernels: the hi plane)
   int map_lo[3];      // fp16 kernels, split layers: tensor map of the lo plane
+  int seg_coff[3];    // channel offset of the segment inside its tensor map (views of one buffer share a map)
   int seg_end[3];     // chunk index where segment i ends (prefix sums)
   int seg_last_k[3];  // K-steps (of 4 per chunk) that hold real channels in the LAST chunk of each segment
   int kchunks;        // total 32-channel chunks
@@ -89,6 +97,7 @@ struct LayerDesc {
   const float* res1; int res1_ld; float alpha1;
   const float* res2; int res2_ld; float alpha2;
   const float* pre; int pre_ld;   // added to the accumulator before bias / scale / activation
+  float* raw2; int raw2_ld;       // accumulator columns [32, cout) stored RAW as fp32 (a later conv's partial sum)
   // fused FlowStep inverse (FlowStep.py:55-64): this conv is the sub-net's last layer; its output h is not stored,
   // the epilogue applies  z2 = z2 * exp(-ls(h)) - shift(h);  z = W^-1 z;  z = z * exp(-logs) - bias  in place
   float* step_z; int step_z_ld, step_C, step_npass;
@@ -453,7 +462,7 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
       uint32_t a_it = 0, b_it = 0, p_it = 0;
       // per-layer fields stay in registers; a CTA sees the same layer for ~n_tiles/gridDim.x items in a row
       int cur_layer = -1, kchunks = 0, se0 = 0, se1 = 0, m0 = 0, m1 = 0, m2 = 0, slab_taps = 1, slabs = 1;
-      int l0 = 0, l1 = 0, l2 = 0, lparts = 1, ltaps = KS * KS, lsplit = 0;
+      int l0 = 0, l1 = 0, l2 = 0, lparts = 1, ltaps = KS * KS, lsplit = 0, co0 = 0, co1 = 0, co2 = 0;
       uint32_t tap_n = 0;   // bytes of one tap of B at one row block (N rows)
       const uint8_t* wimg = nullptr;
       Deps deps;
@@ -475,6 +484,7 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
           se0 = __ldg(&L->seg_end[0]); se1 = __ldg(&L->seg_end[1]);
           m0 = __ldg(&L->map_idx[0]); m1 = __ldg(&L->map_idx[1]); m2 = __ldg(&L->map_idx[2]);
           l0 = __ldg(&L->map_lo[0]); l1 = __ldg(&L->map_lo[1]); l2 = __ldg(&L->map_lo[2]);
+          co0 = __ldg(&L->seg_coff[0]); co1 = __ldg(&L->seg_coff[1]); co2 = __ldg(&L->seg_coff[2]);
           lparts = __ldg(&L->parts);
           lsplit = lparts == 2 ? __ldg(&L->split_kc) : 0;
           tap_n = (uint32_t)__ldg(&L->N) * ROW_BYTES;
@@ -541,10 +551,11 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
             mbar_expect_tx(fullA(sA), two ? 2 * A_BYTES : A_BYTES);
             const int mi = kc < se0 ? m0 : (kc < se1 ? m1 : m2);
             const int kl = kc < se0 ? kc : (kc < se1 ? kc - se0 : kc - se1);
-            tma_load_4d(smem_base + sA * A_STAGE, map_ptr(mi), fullA(sA), kl * KCHX, x0 - HALO, y0 - HALO, b);
+            const int cch = kl * KCHX + (kc < se0 ? co0 : (kc < se1 ? co1 : co2));   // channel coordinate in the map
+            tma_load_4d(smem_base + sA * A_STAGE, map_ptr(mi), fullA(sA), cch, x0 - HALO, y0 - HALO, b);
             if (two) {
               const int li = kc < se0 ? l0 : (kc < se1 ? l1 : l2);
-              tma_load_4d(smem_base + sA * A_STAGE + A_PART, map_ptr(li), fullA(sA), kl * KCHX, x0 - HALO, y0 - HALO, b);
+              tma_load_4d(smem_base + sA * A_STAGE + A_PART, map_ptr(li), fullA(sA), cch, x0 - HALO, y0 - HALO, b);
             }
           }
           ++a_it;
@@ -696,6 +707,7 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
     float* step_z = nullptr; int step_z_ld = 0, step_C = 0, step_npass = 0, step_z16_ld = 0;
     const float* step_w = nullptr; const float* step_sc = nullptr; const float* step_b = nullptr;
     __half* step_z16 = nullptr;
+    float* raw2 = nullptr; int raw2_ld = 0;
     HCF_T(te0);
     for (int item = blockIdx.x + grp * gridDim.x; item < n_items; item += EG * gridDim.x, t_it += EG) {
       const int layer = item / p.n_tiles, tile = item - layer * p.n_tiles;
@@ -725,6 +737,8 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
           step_w = ldg_ptr(&L->step_w); step_sc = ldg_ptr(&L->step_sc); step_b = ldg_ptr(&L->step_b);
           step_z16 = ldg_ptr(&L->step_z16); step_z16_ld = __ldg(&L->step_z16_ld);
         }
+        raw2 = ldg_ptr(&L->raw2);
+        if (raw2) { raw2_ld = __ldg(&L->raw2_ld); cout = 32; }   // the main path sees columns [0, 32) only
         is_pre = false;
         if (const float* pre = ldg_ptr(&L->pre)) {   // host guarantees: no res1 / res2 on such a layer
           res1 = pre; res1_ld = __ldg(&L->pre_ld); is_pre = true;
@@ -869,7 +883,17 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
           HCF_ACC(PROF_E_ROW, tr0, tr1);
           // ---- coalesced domain (8 lanes = the 32 channels of one pixel, 4 pixels per instruction):
           //      residuals -> full-line global stores (fp32 and / or fp16 hi / lo planes)
-          if (!(p.debug & 8)) {
+          if (raw2 && c0 >= 32 && !(p.debug & 8)) {
+            // partial sum of a LATER conv over the inputs it shares with this one (an RDB's conv2 / conv4 over the
+            // channels conv1 / conv3 read): stored raw, that conv adds it before its bias (hcf_conv_args.pre)
+            const int chr = c0 - 32 + (lane & 7) * 4;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int pl = it * 4 + (lane >> 3);
+              if (pixv[it] != 0xffffffffu)
+                __stcg(reinterpret_cast<float4*>(raw2 + (pixv[it] * (uint32_t)raw2_ld + chr)), stage[pl * 8 + ((lane & 7) ^ (pl & 7))]);
+            }
+          } else if (!(p.debug & 8)) {
             const int cidx = lane & 7;
             const int ch = c0 + cidx * 4;
             const bool ch_ok = ch < cout && cidx * 4 < gw;
@@ -1311,6 +1335,7 @@ static int chain_create(const hcf_conv_args* args, const void* const* wtc, const
       if (args[i].res1 && args[i].res1_ld > ldm) ldm = args[i].res1_ld;
       if (args[i].res2 && args[i].res2_ld > ldm) ldm = args[i].res2_ld;
       if (args[i].pre && args[i].pre_ld > ldm) ldm = args[i].pre_ld;
+      if (args[i].raw2 && args[i].raw2_ld > ldm) ldm = args[i].raw2_ld;
       HCF_REQUIRE(npix * (uint64_t)ldm < (1ull << 32), "tc_chain: conv %d: buffer too large for 32-bit element offsets", i);
     }
   }
@@ -1382,21 +1407,72 @@ static int chain_create(const hcf_conv_args* args, const void* const* wtc, const
   // reads beyond its last chunk, so such segments of one buffer share a map of the widest extent seen.
   // fp16 chains treat every multiple of 32 that way: the half-empty last chunk then reads finite stale values
   // of the same buffer against zero weight rows (buffers are zero-initialised and only ever hold conv outputs).
-  struct MapKey { const void* ptr; int ld; int C; bool ragged; };
+  // Channel-slice views of ONE buffer (same row pitch, pointers less than one pixel row apart) share a map whose
+  // base is the lowest of them; a segment addresses it with its channel offset.  Ragged views keep their own map.
+  struct MapKey { const char* ptr; int ld; int C; bool ragged; };
   std::vector<MapKey> keys;
-  auto map_for = [&](const void* ptr, int ld, int C) {
-    const bool ragged = (C % (f16 ? 32 : kch)) != 0;
-    int found = -1;
-    for (size_t k = 0; k < keys.size(); ++k)
-      if (keys[k].ptr == ptr && keys[k].ld == ld && keys[k].ragged == ragged && (!ragged || keys[k].C == C)) found = (int)k;
-    if (found < 0) {
-      keys.push_back({ptr, ld, C, ragged});
-      found = (int)keys.size() - 1;
-    } else if (!ragged && keys[found].C < C) {
-      keys[found].C = C;
+  const int esz_i = f16 ? 2 : 4;
+  auto is_ragged = [&](int C) { return (C % (f16 ? 32 : kch)) != 0; };
+  auto map_note = [&](const void* vptr, int ld, int C) {   // pass 1: cluster bases
+    const char* ptr = reinterpret_cast<const char*>(vptr);
+    if (is_ragged(C)) return;
+    for (size_t k = 0; k < keys.size(); ++k) {
+      if (keys[k].ragged || keys[k].ld != ld) continue;
+      const long long d = ptr - keys[k].ptr;
+      if (d > -(long long)ld * esz_i && d < (long long)ld * esz_i) {
+        if (d < 0) { keys[k].C += (int)(-d / esz_i); keys[k].ptr = ptr; }
+        const int need = (int)((ptr - keys[k].ptr) / esz_i) + C;
+        if (need > keys[k].C) keys[k].C = need;
+        return;
+      }
     }
-    return found;
+    keys.push_back({ptr, ld, C, false});
   };
+  auto map_for = [&](const void* vptr, int ld, int C, int* coff) {   // pass 2: key index + channel offset
+    const char* ptr = reinterpret_cast<const char*>(vptr);
+    *coff = 0;
+    if (is_ragged(C)) {
+      for (size_t k = 0; k < keys.size(); ++k)
+        if (keys[k].ragged && keys[k].ptr == ptr && keys[k].ld == ld && keys[k].C == C) return (int)k;
+      keys.push_back({ptr, ld, C, true});
+      return (int)keys.size() - 1;
+    }
+    for (size_t k = 0; k < keys.size(); ++k) {
+      if (keys[k].ragged || keys[k].ld != ld) continue;
+      const long long d = ptr - keys[k].ptr;
+      if (d >= 0 && d < (long long)ld * esz_i) {
+        *coff = (int)(d / esz_i);
+        return (int)k;
+      }
+    }
+    return -1;   // unreachable after pass 1
+  };
+  auto seg_planes = [&](int i, int s_, __half** hi, __half** lo, int* ld16) -> int {   // fp16: the planes of a segment
+    const hcf_seg& sg = args[i].seg[s_];
+    *ld16 = sg.ld;
+    const hcf_seg16* ov = seg16 ? &seg16[i * 3 + s_] : nullptr;
+    if (ov && ov->hi) {
+      *hi = reinterpret_cast<__half*>(const_cast<void*>(ov->hi));
+      *lo = reinterpret_cast<__half*>(const_cast<void*>(ov->lo));
+      *ld16 = ov->ld;
+      return 0;
+    }
+    return shadow_of(shadows, n_shadows, sg.ptr, hi, lo) ? 0 : -1;
+  };
+  for (int i = 0; i < n; ++i)   // pass 1
+    for (int s_ = 0; s_ < args[i].nseg; ++s_) {
+      const hcf_seg& sg = args[i].seg[s_];
+      if (f16) {
+        __half *hi = nullptr, *lo = nullptr;
+        int ld16 = 0;
+        if (seg_planes(i, s_, &hi, &lo, &ld16) == 0) {
+          map_note(hi, ld16, sg.C);
+          if (layer_passes[i] == 3 && lo) map_note(lo, ld16, sg.C);
+        }
+      } else {
+        map_note(sg.ptr, sg.ld, sg.C);
+      }
+    }
   std::vector<LayerDesc> layers(n);
   for (int i = 0; i < n; ++i) {
     const hcf_conv_args& a = args[i];
@@ -1411,12 +1487,7 @@ static int chain_create(const hcf_conv_args* args, const void* const* wtc, const
         if (f16) {
           __half *hi = nullptr, *lo = nullptr;
           int ld16 = sg.ld;
-          const hcf_seg16* ov = seg16 ? &seg16[i * 3 + s] : nullptr;
-          if (ov && ov->hi) {
-            hi = reinterpret_cast<__half*>(const_cast<void*>(ov->hi));
-            lo = reinterpret_cast<__half*>(const_cast<void*>(ov->lo));
-            ld16 = ov->ld;
-          } else if (!shadow_of(shadows, n_shadows, sg.ptr, &hi, &lo)) {
+          if (seg_planes(i, s, &hi, &lo, &ld16) != 0) {
             delete pl;
             set_error("tc_chain: conv %d segment %d: no fp16 planes registered for this buffer", i, s);
             return HCF_EINVAL;
@@ -1426,10 +1497,11 @@ static int chain_create(const hcf_conv_args* args, const void* const* wtc, const
             set_error("tc_chain: conv %d segment %d: fp16 view breaks TMA's 16-byte rules", i, s);
             return HCF_ENOTSUP;
           }
-          L.map_idx[s] = map_for(hi, ld16, sg.C);
-          L.map_lo[s] = L.parts == 2 ? map_for(lo, ld16, sg.C) : 0;
+          int coff_lo = 0;
+          L.map_idx[s] = map_for(hi, ld16, sg.C, &L.seg_coff[s]);
+          L.map_lo[s] = L.parts == 2 ? map_for(lo, ld16, sg.C, &coff_lo) : 0;   // (same geometry: same offset)
         } else {
-          L.map_idx[s] = map_for(sg.ptr, sg.ld, sg.C);
+          L.map_idx[s] = map_for(sg.ptr, sg.ld, sg.C, &L.seg_coff[s]);
         }
         kc += (sg.C + kch - 1) / kch;
         const int rem = sg.C % kch == 0 ? kch : sg.C % kch;     // channels in the segment's last chunk
@@ -1469,6 +1541,13 @@ static int chain_create(const hcf_conv_args* args, const void* const* wtc, const
     L.res1 = a.res1; L.res1_ld = a.res1_ld; L.alpha1 = a.alpha1;
     L.res2 = a.res2; L.res2_ld = a.res2_ld; L.alpha2 = a.alpha2;
     L.pre = a.pre; L.pre_ld = a.pre_ld;
+    L.raw2 = a.raw2; L.raw2_ld = a.raw2_ld;
+    if (a.raw2 && !(a.cout == 64 && !a.res1 && !a.res2 && !a.out2 && !a.step && a.raw2_ld % 4 == 0 && aligned16(a.raw2) &&
+                    a.raw2_ld >= 32)) {
+      delete pl;
+      set_error("tc_chain: conv %d: raw2 needs cout == 64, no residuals / second output, a 16-byte aligned view", i);
+      return HCF_EINVAL;
+    }
     if (a.step) {
       const hcf_conv_step& st = *a.step;
       if (!(st.z && st.C >= 2 && st.C <= STEP_MAXC && st.n_pass >= 1 && st.n_pass < st.C && st.z_ld >= st.C &&
@@ -1527,7 +1606,7 @@ static int chain_create(const hcf_conv_args* args, const void* const* wtc, const
     const cuuint64_t ld_b = (cuuint64_t)k.ld * esz;
     const cuuint64_t strides[3] = {ld_b, ld_b * a0->W, ld_b * a0->W * a0->H};
     CUresult r = enc(&pl->maps.m[i], f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
-                     const_cast<void*>(k.ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     const_cast<char*>(k.ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       delete pl;

@@ -20,7 +20,7 @@ class Engine:
     """One compiled plan = (net weights, direction, B, h, w, precision) on one device."""
 
     def __init__(self, net, direction, B, h, w, device, precision="fp32", use_graph=True, use_chains=True,
-                 share_cond=True, fuse_steps=True, io="f32"):
+                 share_cond=True, fuse_steps=True, io="f32", pair_convs=True):
         if not torch.cuda.is_available():
             raise L.HcfError("hcflow_b200 needs a CUDA device (no CPU fallback)")
         self.lib = L.load()
@@ -53,6 +53,7 @@ class Engine:
         self.use_chains = use_chains
         self.share_cond = share_cond   # the coupling sub-nets' shared conditioning part once per level (TC modes)
         self.fuse_steps = fuse_steps   # FlowStep tail in the last sub-net conv's epilogue (TC modes, inverse pass)
+        self.pair_convs = pair_convs   # RDB growth convs in pairs: N = 64 accumulators, partial sums through `pre`
         self._step_structs = {}  # id(conv op) -> L.ConvStep
         self._flag_pool = None   # dependency counters of all chained launches: one buffer, zeroed once per pass
         self._flag_used = 0
@@ -144,7 +145,7 @@ class Engine:
     def _rewrite_ops(self):
         """The plan as the tensor-core modes execute it (rewrite.py): materialised up-sampled segments, shared
         conditioning convs, fused FlowStep tails; the extra buffers are allocated here."""
-        ops, extra = rewrite.rewrite_ops(self.plan.ops, self.precision, self.share_cond, self.fuse_steps)
+        ops, extra = rewrite.rewrite_ops(self.plan.ops, self.precision, self.share_cond, self.fuse_steps, self.pair_convs)
         for name, b in extra.items():
             if name not in self.bufs:
                 self.bufs[name] = torch.zeros(self.B, b.H, b.W, b.C, dtype=torch.float32, device=self.device)
@@ -181,6 +182,8 @@ class Engine:
                     a.alpha2 = op.alpha2
                 if op.pre is not None:
                     a.pre, a.pre_ld = self._vptr(op.pre)
+                if op.raw2 is not None:
+                    a.raw2, a.raw2_ld = self._vptr(op.raw2)
                 if op.step is not None:
                     stp = L.ConvStep()
                     stp.z, stp.z_ld = self._vptr(op.step.z)
@@ -421,7 +424,7 @@ class Engine:
         if isinstance(op, P.ConvOp):
             if op.step is not None:    # h is consumed in the epilogue, z is updated in place
                 return [op.step.z]
-            return [v for v in (op.out, op.out2) if v is not None]
+            return [v for v in (op.out, op.out2, op.raw2) if v is not None]
         if isinstance(op, P.StepOp):
             return [op.z]
         if isinstance(op, P.PriorOp):

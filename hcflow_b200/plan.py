@@ -62,6 +62,7 @@ class ConvOp:
     w_in: Optional[Tuple[int, int]] = None
     pre: Optional[View] = None
     step: Optional[object] = None   # a StepOp("inverse") executed by this conv's epilogue (fused FlowStep tail)
+    raw2: Optional[View] = None     # cout == 64: accumulator columns [32, 64) stored raw (fp32) here, [0, 32) -> out
 
 
 @dataclass

@@ -7,7 +7,8 @@ the host logic is covered by the CPU tests through tests/plan_emulator.py).
      the SAME encoder feature u (ConditionalFlow.py:62-66, AffineCouplings.py:31): W * cat(z1, u) = W_z * z1 + W_u * u,
      and the W_u * u parts of all steps are wide convs over u (Cout = 2 steps x 64 = UMMA N 128) computed once per
      level; each step convolves only its few z1 channels and adds its slice before ActNorm + ReLU (hcf_conv_args.pre);
-  3. the FlowStep tail (FlowStep.py:55-64, reverse) fused into the sub-net's last conv (hcf_conv_step): removes one
+  3. the growth convs of every residual dense block in pairs (pair_rdb_convs);
+  4. the FlowStep tail (FlowStep.py:55-64, reverse) fused into the sub-net's last conv (hcf_conv_step): removes one
      launch per step and lets the convs of consecutive steps of a level run as ONE chained launch.
 """
 import torch
@@ -78,6 +79,44 @@ def share_conditioning(ops, bufs):
     return out
 
 
+def pair_rdb_convs(ops, bufs):
+    """Dense-block growth convs in pairs (Basic.py:377-381): conv_{k+1} reads everything conv_k reads plus conv_k's
+    32 new channels.  On the tensor cores a conv with 32 output channels pays for fetching the activation operand
+    (UMMA N = 32 keeps the tensor pipe 40 % busy at best, N = 64: 67 %), so conv_k also accumulates, in 32 more
+    accumulator columns, conv_{k+1}'s partial sum over the shared input channels (raw fp32, `raw2`), and conv_{k+1}
+    shrinks to a conv over the 32 new channels that adds the partial before its bias (`pre`).  Pairs (conv1, conv2)
+    and (conv3, conv4) of every RDB with 32 growth channels."""
+    ops = list(ops)
+    i = 0
+    while i + 1 < len(ops):
+        a, b = ops[i], ops[i + 1]
+        ok = (isinstance(a, P.ConvOp) and isinstance(b, P.ConvOp) and a.tag in ("enc.rdb.conv1", "enc.rdb.conv3")
+              and b.tag == {"enc.rdb.conv1": "enc.rdb.conv2", "enc.rdb.conv3": "enc.rdb.conv4"}.get(a.tag)
+              and a.cout == 32 and b.cout == 32 and a.ks == b.ks == 3 and len(a.segs) == 1 and len(b.segs) == 1
+              and a.segs[0][1] == 0 and b.segs[0][1] == 0 and (a.H, a.W) == (b.H, b.W)
+              and isinstance(a.weight, str) and isinstance(b.weight, str) and a.w_in is None and b.w_in is None
+              and a.out2 is None and b.out2 is None and a.res1 is None and b.res1 is None and a.pre is None and b.pre is None
+              and a.act == b.act and a.scale is None and b.scale is None)
+        if ok:
+            va, vb = a.segs[0][0], b.segs[0][0]
+            # conv_{k+1}'s input = conv_k's input followed by conv_k's output, contiguous in one buffer
+            ok = (va.buf.name == vb.buf.name == a.out.buf.name and va.off == vb.off and vb.C == va.C + 32
+                  and a.out.off == va.off + va.C and a.out.C == 32 and va.C % 32 == 0)
+        if not ok:
+            i += 1
+            continue
+        name = "rdbpart_{}x{}".format(a.H, a.W)
+        pbuf = bufs.setdefault(name, P.Buf(name, a.H, a.W, 32))
+        part = P.View(pbuf, 0, 32)
+        cin = a.segs[0][0].C
+        ops[i] = P.ConvOp(a.H, a.W, a.segs, 3, 64, ((a.weight, 0, cin), (b.weight, 0, cin)), a.bias, None, a.act, a.out,
+                          tag=a.tag, raw2=part)
+        ops[i + 1] = P.ConvOp(b.H, b.W, [(a.out, 0)], 3, 32, b.weight, b.bias, None, b.act, b.out, tag=b.tag,
+                              w_in=(cin, cin + 32), pre=part)
+        i += 2
+    return ops
+
+
 STEP_MAXC = 24   # csrc/conv_tc.cu
 
 
@@ -99,13 +138,17 @@ def fuse_steps(ops):
     return fused
 
 
-def rewrite_ops(plan_ops, precision, share_cond=True, fuse=True):
+def rewrite_ops(plan_ops, precision, share_cond=True, fuse=True, pair=True):
     """-> (ops, {name: Buf} of the extra fp32 buffers the rewritten ops use)."""
     ops = list(plan_ops)
     bufs = {}
     if precision == "fp32":
         return ops, bufs
     ops = materialise_upsampled(ops, bufs)
+    # measured (B200, x4 B=16): pairing cuts the TF32 chains by 9 % (12.25 -> 11.09 ms/step) but not the fp16 ones
+    # (10.65 -> 10.82): their growth convs are no longer bound by the MMA operand fetch
+    if pair and not precision.startswith("f16"):
+        ops = pair_rdb_convs(ops, bufs)
     if share_cond:
         ops = share_conditioning(ops, bufs)
     if fuse:

@@ -30,7 +30,7 @@ extern "C" {
 #define HCF_EINVAL (-1)   /* bad argument (shape / alignment / unsupported size) */
 #define HCF_ENOTSUP (-2)  /* combination not implemented by this kernel */
 
-#define HCF_ABI_VERSION 1
+#define HCF_ABI_VERSION 2
 
 /* ---- introspection -------------------------------------------------------------- */
 int hcf_abi_version(void);
@@ -115,6 +115,12 @@ typedef struct {
                        accumulator BEFORE bias / scale / activation (the part of a conv over an input that is
                        shared by several convs, computed once by another conv); excludes res1 / res2 */
   const hcf_conv_step* step; /* may be NULL; host pointer, read when the plan is created */
+  float* raw2;     /* may be NULL; tensor-core kernels, cout == 64: accumulator columns [32, 64) are stored RAW (no
+                      bias / scale / activation) as fp32 to raw2[..., c - 32] and only columns [0, 32) take the normal
+                      epilogue into out: the conv computes, on the inputs they share, the partial sum of a later conv
+                      next to its own output (that conv adds it through `pre`) */
+  int32_t raw2_ld;
+  int32_t _pad2;
 } hcf_conv_args;
 
 /* fp32 CUDA-core (FFMA) implementation: exact-fp32 parity mode and odd shapes. */

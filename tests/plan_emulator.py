@@ -61,6 +61,12 @@ class Emulator:
             y = F.relu(y)
         elif op.act == P.ACT_LRELU:
             y = F.leaky_relu(y, 0.2)
+        if op.raw2 is not None:   # columns [32, 64) leave raw (before bias / activation): recompute them without
+            raw = F.conv2d(x, w, None, padding=ks // 2)[:, 32:64].permute(0, 2, 3, 1)
+            self.view(op.raw2).copy_(raw)
+            y = y[:, :32].permute(0, 2, 3, 1).clone()
+            self.view(op.out).copy_(y)
+            return
         y = y[:, :op.cout].permute(0, 2, 3, 1)
         if op.res1 is not None:
             y = y * op.alpha1 + self.view(op.res1)

@@ -73,14 +73,16 @@ def test_rewritten_reverse_plan_matches_golden(cfg):
     opt, net, sd = net_and_weights(cfg)
     lr, hr, eps = _inputs(g, opt)
     plan = P.build_plan(net, "reverse", g["B"], g["h"], g["w"])
-    ops, extra = rewrite.rewrite_ops(plan.ops, "f16x3")
+    ops, extra = rewrite.rewrite_ops(plan.ops, "tf32x3")   # (the fp16 modes apply everything but the conv pairing)
+    assert not any(isinstance(o, P.ConvOp) and o.raw2 is not None for o in rewrite.rewrite_ops(plan.ops, "f16x3")[0])
     assert rewrite.rewrite_ops(plan.ops, "fp32")[0] == list(plan.ops)
     n_step = sum(isinstance(o, P.StepOp) for o in plan.ops)
     n_left = sum(isinstance(o, P.StepOp) for o in ops)
     n_fused = sum(isinstance(o, P.ConvOp) and o.step is not None for o in ops)
     assert n_fused + n_left == n_step
     assert not any(isinstance(o, P.ConvOp) and any(up for _, up in o.segs) for o in ops)
-    if is_sr(opt):
+    if is_sr(opt):   # (the rescaling net's dense blocks grow by 16 channels: not paired)
+        assert any(isinstance(o, P.ConvOp) and o.raw2 is not None for o in ops)
         assert n_fused > 0 and any(isinstance(o, P.ConvOp) and o.pre is not None for o in ops)
         assert any(isinstance(o, P.LayoutOp) and o.variant == "upsample" for o in ops)
     em = Emulator(net, plan, ops=ops, extra_bufs=extra)
