@@ -327,7 +327,7 @@ __device__ __forceinline__ void step_inverse_pixel(float* __restrict__ scratch, 
 // ------------------------------------------------------------------ kernel
 // profile slots (HCF_TC_PROF=1): cycles summed over CTAs, printed by hcf_conv_tc_plan_destroy
 enum { PROF_P_TOTAL = 0, PROF_P_DEPS, PROF_P_EMPTYA, PROF_P_EMPTYB, PROF_M_TOTAL, PROF_M_TMEM, PROF_M_FULLA, PROF_M_FULLB,
-       PROF_M_CONVA, PROF_E_TOTAL, PROF_E_TMEMFULL, PROF_E_BODY, PROF_E_PUBLISH, PROF_E_LAYER, PROF_E_ROW, PROF_E_COAL, PROF_LAUNCHES, PROF_N };
+       PROF_M_CONVA, PROF_E_TOTAL, PROF_E_TMEMFULL, PROF_E_BODY, PROF_E_PUBLISH, PROF_E_LAYER, PROF_E_ROW, PROF_E_COAL, PROF_M_ISSUE, PROF_LAUNCHES, PROF_N };
 // compiled in only with -DHCF_TC_PROF_BUILD (HCF_BUILD_PROF=1 python -m hcflow_b200.build --force): the accumulators
 // cost ~30 registers per thread
 #ifdef HCF_TC_PROF_BUILD
@@ -635,6 +635,7 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
           tc_fence_after();
           HCF_T(tfb1);
           HCF_ACC(PROF_M_FULLB, tfb0, tfb1);
+          HCF_T(tis0);
           if (elect_one()) {
             const uint64_t b0 = b_tmpl + ((b_base + sB * slot_bytes) >> 4);
             for (int t = 0; t < ((p.debug & 2) ? 0 : slab_taps); ++t) {
@@ -670,6 +671,8 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
             }
           }
           __syncwarp();
+          HCF_T(tis1);
+          HCF_ACC(PROF_M_ISSUE, tis0, tis1);
           accum = 1u;
           ++b_it;
         }
@@ -678,7 +681,7 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
     }
     HCF_T(tm1);
     HCF_ACC(PROF_M_TOTAL, tm0, tm1);
-    if (lane == 0) HCF_PROF_FLUSH(PROF_M_TOTAL, PROF_M_CONVA);
+    if (lane == 0) { HCF_PROF_FLUSH(PROF_M_TOTAL, PROF_M_CONVA); HCF_PROF_FLUSH(PROF_M_ISSUE, PROF_M_ISSUE); }
   } else if (warp < 6 || (F16 && warp < 10)) {
     // ===================== epilogue =====================
     // fp16 kernels run TWO epilogue groups of four warps (warps 2-5 and 6-9): group g drains accumulator buffer g,
@@ -849,6 +852,10 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                 }
               }
             }
+            // the accumulator has been read (tcgen05.wait::ld inside tmem_ld16): hand the TMEM buffer back NOW, the
+            // per-pixel FlowStep arithmetic below runs while the MMA warp already fills it with a later item
+            tc_fence_before();
+            mbar_arrive(tmem_empty(acc));
             const int mm = q * 32 + lane;
             const int gy = y0 + mt * TH + mm / TW, gx = x0 + mm % TW;
             if (gy < p.H && gx < p.W && !(p.debug & 8)) {
@@ -879,6 +886,11 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
             }
           }
           __syncwarp();
+          if (mt == MT - 1 && c0 + 32 >= N) {
+            // last TMEM read of the item done: release the accumulator buffer before the (long) store phase
+            tc_fence_before();
+            mbar_arrive(tmem_empty(acc));
+          }
           HCF_T(tr1);
           HCF_ACC(PROF_E_ROW, tr0, tr1);
           // ---- coalesced domain (8 lanes = the 32 channels of one pixel, 4 pixels per instruction):
@@ -996,8 +1008,6 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
           HCF_ACC(PROF_E_COAL, tr1, tr2);
         }
       }
-      tc_fence_before();
-      mbar_arrive(tmem_empty(acc));   // all TMEM reads of this item are complete (wait::ld above)
       HCF_T(tl3);
       HCF_ACC(PROF_E_BODY, tl2, tl3);
       if (chain) {
@@ -1720,7 +1730,7 @@ extern "C" void hcf_conv_tc_plan_destroy(hcf_conv_tc_plan* p) {
     if (cudaMemcpy(h, p->d_prof, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess) {
       static const char* names[hcf::tc::PROF_N] = {"P.total", "P.deps", "P.emptyA", "P.emptyB", "M.total", "M.tmem_empty",
                                                    "M.fullA", "M.fullB", "M.convA", "E.total", "E.tmem_full", "E.body",
-                                                   "E.publish", "E.layer", "E.row", "E.coal", "launches"};
+                                                   "E.publish", "E.layer", "E.row", "E.coal", "M.issue", "launches"};
       const double items = (double)p->p.n_items / p->grid.x;
       const double launches = h[hcf::tc::PROF_LAUNCHES] > 0 ? (double)h[hcf::tc::PROF_LAUNCHES] : 1.0;
       fprintf(stderr, "[hcf prof] chain layers=%d tiles=%d items/CTA=%.1f launches=%.0f; cycles per item:", p->p.n_layers,
