@@ -145,3 +145,41 @@ def test_reference_factory_builds_the_dropin_after_install(tmp_path):
     script.write_text(_REF_WORKER.format(root=ROOT))
     out = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("cout,kin,ks,split_kin", [(32, 64, 3, 0), (64, 192, 3, 64), (64, 192, 3, 192), (22, 64, 3, 0),
+                                                   (64, 64, 1, 0)])
+def test_fp16_weight_image_layout(cout, kin, ks, split_kin):
+    """hcf_conv_tc16_pack_weights (host code, no GPU): per 64-channel chunk [tap][rows][64 fp16], rows = [hi N ; lo N]
+    for the chunks below split_kin, 16-byte groups XOR-swizzled by (row & 7) like a TMA SWIZZLE_128B write, and
+    hi + lo / 2048 reproduces the fp32 weight to ~2^-22 relative."""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(cout + kin)
+    w = (torch.randn(cout, kin, ks, ks, generator=g) * 0.05).contiguous()
+    N = (cout + 15) // 16 * 16
+    nbytes = lib.hcf_conv_tc16_weight_bytes(kin, cout, ks, split_kin)
+    assert nbytes == (kin + split_kin) // 64 * ks * ks * N * 128
+    img = torch.zeros(nbytes // 2, dtype=torch.float16)
+    assert lib.hcf_conv_tc16_pack_weights(w.data_ptr(), kin, cout, ks, split_kin, img.data_ptr()) == 0
+    base = 0
+    for kc in range(kin // 64):
+        parts = 2 if kc * 64 < split_kin else 1
+        NB = N * parts
+        blk = img[base:base + ks * ks * NB * 64].view(ks * ks, NB, 8, 8)       # [tap][row][16-byte group][8]
+        rows = torch.arange(NB).view(1, NB, 1, 1).expand(ks * ks, NB, 8, 8)
+        grp = torch.arange(8).view(1, 1, 8, 1).expand(ks * ks, NB, 8, 8)
+        unsw = torch.gather(blk, 2, (grp ^ (rows & 7)))                            # undo the swizzle
+        unsw = unsw.reshape(ks * ks, NB, 64).float()
+        ref = w[:, kc * 64:(kc + 1) * 64].permute(2, 3, 0, 1).reshape(ks * ks, cout, 64)
+        hi = unsw[:, :cout]
+        assert torch.equal(hi, ref.half().float())
+        assert float(unsw[:, cout:N].abs().max()) == 0.0 if N > cout else True
+        if parts == 2:
+            lo = unsw[:, N:N + cout]
+            assert torch.equal(lo, ((ref - hi) * 2048.0).half().float())
+            rel = ((hi + lo / 2048.0) - ref).abs().max() / ref.abs().max()
+            assert float(rel) < 2.0 ** -20
+        base += ks * ks * NB * 64
+    assert base == img.numel()
+    assert lib.hcf_conv_tc16_weight_bytes(kin + 1, cout, ks, 0) == 0
+    assert lib.hcf_conv_tc16_pack_weights(w.data_ptr(), kin, cout, ks, 32, img.data_ptr()) != 0   # split not a multiple of 64
