@@ -111,6 +111,8 @@ struct Params {
   int n_tiles;        // B * tiles_x * tiles_y  (work items per layer)
   int n_layers;       // > 1: a chain of dependent convs executed by ONE persistent launch
   int n_items;        // n_layers * n_tiles
+  int tpc;            // 0: items rotate over the CTAs (item = blockIdx + q * grid); > 0: every CTA OWNS tpc tiles
+                      // (n_tiles == tpc * grid) and walks the layers over them -- few-tile grids (40x40 level)
   int nb_max;         // max over layers of B rows per tap (N, or 2N in 3-pass mode)
   int sa, sb;         // ring depths
   int slot_bytes;     // bytes of one B ring slot
@@ -448,6 +450,16 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
 
   const int per_img = p.tiles_x * p.tiles_y;
   const int n_items = (p.debug & 32) ? 0 : p.n_items;   // timing experiment: prologue + teardown only
+  // q-th work item of this CTA (-1 = none)
+  auto item_at = [&](int q) -> int {
+    if (p.tpc > 0) {
+      const int layer = q / p.tpc;
+      if (layer >= p.n_layers || n_items == 0) return -1;
+      return layer * p.n_tiles + (int)blockIdx.x + (q - layer * p.tpc) * (int)gridDim.x;
+    }
+    const int item = (int)blockIdx.x + q * (int)gridDim.x;
+    return item < n_items ? item : -1;
+  };
   const bool chain = p.done != nullptr;
 #ifdef HCF_TC_PROF_BUILD
   const bool prof_on = p.prof != nullptr;
@@ -467,12 +479,12 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
       const uint8_t* wimg = nullptr;
       Deps deps;
       HCF_T(tp0);
-      if (chain && (int)blockIdx.x < n_items) {   // counters of the first item (prefetched one item ahead below)
-        const int tile = blockIdx.x % p.n_tiles;
+      if (chain && item_at(0) >= 0) {   // counters of the first item (prefetched one item ahead below)
+        const int tile = item_at(0) % p.n_tiles;
         const int b = tile / per_img, r = tile % per_img;
         load_deps(deps, p.done, b * per_img, r / p.tiles_x, r % p.tiles_x, p.tiles_y, p.tiles_x);
       }
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      for (int seq = 0, item; (item = item_at(seq)) >= 0; ++seq) {
         const int layer = item / p.n_tiles, tile = item - layer * p.n_tiles;
         const int b = tile / per_img, r = tile % per_img;
         const int ty = r / p.tiles_x, tx = r % p.tiles_x;
@@ -528,8 +540,8 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
             HCF_ACC(PROF_P_DEPS, td0, td1);
           }
           asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"(dep_seq), "r"(p_it + 1u) : "memory");   // epilogue may prefetch
-          const int nitem = item + gridDim.x;                  // counters of the next item: in flight during this item's loads
-          if (nitem < n_items) {
+          const int nitem = item_at(seq + 1);                    // counters of the next item: in flight during this item's loads
+          if (nitem >= 0) {
             const int nt = nitem % p.n_tiles;
             const int nb = nt / per_img, nr = nt % per_img;
             load_deps(deps, p.done, nb * per_img, nr / p.tiles_x, nr % p.tiles_x, p.tiles_y, p.tiles_x);
@@ -581,7 +593,7 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
     uint32_t parts = 1, nb = 0, nb_n = 0, idesc_n = 0, idesc = 0, n_cols = 0;
     int split_kc = 0, e0 = 0, e1 = 0, lk0 = 4, lk1 = 4, lk2 = 4;
     HCF_T(tm0);
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++t_it) {
+    for (int seq = 0, item; (item = item_at(seq)) >= 0; ++seq, ++t_it) {
       const int layer = item / p.n_tiles;
       if (layer != cur_layer) {
         cur_layer = layer;
@@ -712,7 +724,7 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
     __half* step_z16 = nullptr;
     float* raw2 = nullptr; int raw2_ld = 0;
     HCF_T(te0);
-    for (int item = blockIdx.x + grp * gridDim.x; item < n_items; item += EG * gridDim.x, t_it += EG) {
+    for (int seq = grp, item; (item = item_at(seq)) >= 0; seq += EG, t_it += EG) {
       const int layer = item / p.n_tiles, tile = item - layer * p.n_tiles;
       const int b = tile / per_img, r = tile % per_img;
       const int y0 = (r / p.tiles_x) * TH * MT, x0 = (r % p.tiles_x) * TW;
@@ -1047,7 +1059,7 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
     if (chain) {
       const int grp = warp - 10;
       uint32_t own = 0;
-      for (int item = blockIdx.x + grp * gridDim.x; item < n_items; item += 2 * gridDim.x, ++own) {
+      for (int seq = grp, item; (item = item_at(seq)) >= 0; seq += 2, ++own) {
         const int tile = item % p.n_tiles;
         asm volatile("bar.sync %0, 160;" ::"r"(3 + grp) : "memory");
         if (lane == 0) {
@@ -1062,7 +1074,7 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
     if (PASSES == 3 && !F16) {
       const int et = threadIdx.x - 192;   // 0..127
       uint32_t a_it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      for (int seq = 0, item; (item = item_at(seq)) >= 0; ++seq) {
         const LayerDesc* L = p.layers + item / p.n_tiles;
         const int kchunks = __ldg(&L->kchunks);
         const int n4 = __ldg(&L->parts) == 2 ? A_BYTES / 16 : 0;   // one-pass layers need no A_lo
@@ -1651,6 +1663,20 @@ static int chain_create(const hcf_conv_args* args, const void* const* wtc, const
   }
   p.layers = pl->d_layers;
   pl->grid = dim3((unsigned)(p.n_tiles < sms ? p.n_tiles : sms));
+  p.tpc = 0;
+  if (n > 1 && p.n_tiles > sms && p.n_tiles <= 3 * sms) {
+    // few tiles per CTA and layer (40x40 level: 240 tiles on 148 SMs): instead of rotating the items over the CTAs,
+    // each CTA can own tpc tiles for all layers when the tile count divides into a grid that still covers >= 3/4 of
+    // the SMs.  Opt-in (HCF_TC_STATIC=1): measured on the same box, 120 owning CTAs are not faster than 148 rotating
+    // ones (encoder chain 2.29 vs 2.24 ms, FlowStep chains equal) -- profiles/r01b_static_ownership_ab.log
+    const char* env_s = getenv("HCF_TC_STATIC");
+    const bool want = env_s ? atoi(env_s) != 0 : false;
+    for (int t = 2; t <= 3 && want && p.tpc == 0; ++t)
+      if (p.n_tiles % t == 0 && p.n_tiles / t <= sms && 4 * (p.n_tiles / t) >= 3 * sms) {
+        p.tpc = t;
+        pl->grid = dim3((unsigned)(p.n_tiles / t));
+      }
+  }
   pl->threads = f16 ? 384 : (passes == 3 ? 320 : 192);
   pl->fn = pick_kernel(mt, passes, ks, f16);
   e = cudaFuncSetAttribute(reinterpret_cast<const void*>(pl->fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
