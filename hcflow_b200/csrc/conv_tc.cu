@@ -326,6 +326,65 @@ __device__ __forceinline__ void step_inverse_pixel(float* __restrict__ scratch, 
   }
 }
 
+// The same with the channel count as a template parameter (the nets use C = 6, 12, 21, 24): exact unrolling, the
+// C x C mix with independent accumulators per row and the rows' weights as 16-byte broadcast loads when C % 4 == 0,
+// no scratch round trip for the result.  (The generic version above spends most of its time in one dependent FMA
+// chain per row and in predicated-off iterations: 0.7 ms of a 10.7 ms step.)
+template <int C>
+__device__ __forceinline__ void step_inverse_pixel_t(const float* __restrict__ scratch, int lane, const float4 (&zq)[8],
+                                                     float* __restrict__ zp, int n_pass, bool has_w,
+                                                     const float* __restrict__ s_w, const float* __restrict__ s_sc,
+                                                     const float* __restrict__ s_b, __half* __restrict__ z16p) {
+  float z[C];
+#pragma unroll
+  for (int i = 0; i < C; ++i) {
+    const float4 q4 = zq[i >> 2];
+    z[i] = (i & 3) == 0 ? q4.x : ((i & 3) == 1 ? q4.y : ((i & 3) == 2 ? q4.z : q4.w));
+  }
+#pragma unroll
+  for (int i = 0; i < C; ++i) {
+    if (i >= n_pass) {
+      const int j = i - n_pass;
+      const float shift = scratch[(2 * j) * 32 + lane], scale = scratch[(2 * j + 1) * 32 + lane];
+      z[i] = z[i] * expf(-coupling_logscale(scale)) - shift;
+    }
+  }
+  float y[C];
+  if (has_w) {
+#pragma unroll
+    for (int i = 0; i < C; ++i) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      if (C % 4 == 0) {
+#pragma unroll
+        for (int j = 0; j < C; j += 4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(s_w + i * C + j);
+          a0 = fmaf(w4.x, z[j], a0); a1 = fmaf(w4.y, z[j + 1], a1);
+          a2 = fmaf(w4.z, z[j + 2], a2); a3 = fmaf(w4.w, z[j + 3], a3);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+          const float w = s_w[i * C + j];
+          if ((j & 3) == 0) a0 = fmaf(w, z[j], a0);
+          else if ((j & 3) == 1) a1 = fmaf(w, z[j], a1);
+          else if ((j & 3) == 2) a2 = fmaf(w, z[j], a2);
+          else a3 = fmaf(w, z[j], a3);
+        }
+      }
+      y[i] = (a0 + a1) + (a2 + a3);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < C; ++i) y[i] = z[i];
+  }
+#pragma unroll
+  for (int i = 0; i < C; ++i) {
+    const float v = y[i] * s_sc[i] - s_b[i];
+    zp[i] = v;
+    if (z16p && i < n_pass) z16p[i] = __float2half_rn(v);
+  }
+}
+
 // ------------------------------------------------------------------ kernel
 // profile slots (HCF_TC_PROF=1): cycles summed over CTAs, printed by hcf_conv_tc_plan_destroy
 enum { PROF_P_TOTAL = 0, PROF_P_DEPS, PROF_P_EMPTYA, PROF_P_EMPTYB, PROF_M_TOTAL, PROF_M_TMEM, PROF_M_FULLA, PROF_M_FULLB,
@@ -380,7 +439,9 @@ __device__ __forceinline__ bool deps_ready(const Deps& d, int layer) {
 }
 
 // F16: operands are fp16 (hi / lo planes, 64 channels per 128-byte row, kind::f16); otherwise fp32 words read as TF32.
-template <int MT, int PASSES, int KS, bool F16>
+// STEP: the chain contains fused FlowStep layers (only those variants carry the per-pixel FlowStep code: its
+// registers cost the encoder kernels 4 % when it was compiled into all of them).
+template <int MT, int PASSES, int KS, bool F16, bool STEP = false>
 __global__ void __launch_bounds__(F16 ? 384 : (PASSES == 3 ? 320 : 192), 1)
 conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
   constexpr int HALO = KS / 2;
@@ -746,8 +807,8 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
         out_ld = __ldg(&L->out_ld); out2_ld = __ldg(&L->out2_ld);
         res1_ld = __ldg(&L->res1_ld); res2_ld = __ldg(&L->res2_ld);
         alpha1 = __ldg(&L->alpha1); alpha2 = __ldg(&L->alpha2);
-        step_z = ldg_ptr(&L->step_z);
-        if (step_z) {
+        step_z = STEP ? ldg_ptr(&L->step_z) : nullptr;
+        if (STEP && step_z) {
           step_z_ld = __ldg(&L->step_z_ld); step_C = __ldg(&L->step_C); step_npass = __ldg(&L->step_npass);
           step_w = ldg_ptr(&L->step_w); step_sc = ldg_ptr(&L->step_sc); step_b = ldg_ptr(&L->step_b);
           step_z16 = ldg_ptr(&L->step_z16); step_z16_ld = __ldg(&L->step_z16_ld);
@@ -765,7 +826,7 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
         asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");   // everyone is done with the previous layer's bias / scale
         s_bias[et] = __ldg(p.epi + (size_t)layer * 256 + et);          // inline table: no pointer chase
         s_scale[et] = __ldg(p.epi + (size_t)layer * 256 + 128 + et);
-        if (step_z) {
+        if (STEP && step_z) {
           if (step_w)
             for (int i = et; i < step_C * step_C; i += 128) st_w[i] = __ldg(step_w + i);
           if (et < step_C) { st_sc[et] = __ldg(step_sc + et); st_b[et] = __ldg(step_b + et); }
@@ -811,7 +872,7 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
         }
       };
       pix_setup(0);
-      if (res_pf || step_z) {
+      if (res_pf || (STEP && step_z)) {
         // the producer has acquired this item's inputs (dependency counters + fence): from here on residuals, the
         // pre-activation addend and z may be read -- long before the accumulator is ready, so the latency hides
         uint32_t seen;
@@ -820,7 +881,7 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
         } while (seen <= t_it);
         if (res_pf) res_prefetch(0);
         if (ahead2) res_prefetch_2nd();
-        if (step_z) {
+        if (STEP && step_z) {
           const int mm = q * 32 + lane;
           const int gy = y0 + mm / TW, gx = x0 + mm % TW;    // (fused steps run with MT == 1)
           const bool in = gy < p.H && gx < p.W;
@@ -846,7 +907,7 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
         for (int c0 = 0; c0 < N; c0 += 32) {
           const int gw = min(32, N - c0);          // columns of this group (16 or 32)
           HCF_T(tr0);
-          if (step_z) {
+          if (STEP && step_z) {
             // ---- fused FlowStep inverse (N <= 32, single group): h never leaves the SM
             float* scratch = reinterpret_cast<float*>(stage);
 #pragma unroll
@@ -870,10 +931,18 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
             mbar_arrive(tmem_empty(acc));
             const int mm = q * 32 + lane;
             const int gy = y0 + mt * TH + mm / TW, gx = x0 + mm % TW;
-            if (gy < p.H && gx < p.W && !(p.debug & 8)) {
+            if (gy < p.H && gx < p.W && !(p.debug & (8 | 128))) {   // 128: timing experiment, no FlowStep arithmetic
               const uint32_t pix = (uint32_t)((b * p.H + gy) * p.W + gx);
-              step_inverse_pixel(scratch, lane, r1v, step_z + (size_t)pix * step_z_ld, step_C, step_npass,
-                                 step_w != nullptr, st_w, st_sc, st_b, step_z16 ? step_z16 + (size_t)pix * step_z16_ld : nullptr);
+              float* zp = step_z + (size_t)pix * step_z_ld;
+              __half* z16p = step_z16 ? step_z16 + (size_t)pix * step_z16_ld : nullptr;
+              const bool hw = step_w != nullptr;
+              switch (step_C) {
+                case 6: step_inverse_pixel_t<6>(scratch, lane, r1v, zp, step_npass, hw, st_w, st_sc, st_b, z16p); break;
+                case 12: step_inverse_pixel_t<12>(scratch, lane, r1v, zp, step_npass, hw, st_w, st_sc, st_b, z16p); break;
+                case 21: step_inverse_pixel_t<21>(scratch, lane, r1v, zp, step_npass, hw, st_w, st_sc, st_b, z16p); break;
+                case 24: step_inverse_pixel_t<24>(scratch, lane, r1v, zp, step_npass, hw, st_w, st_sc, st_b, z16p); break;
+                default: step_inverse_pixel(scratch, lane, r1v, zp, step_C, step_npass, hw, st_w, st_sc, st_b, z16p); break;
+              }
             }
             __syncwarp();
             continue;
@@ -1176,7 +1245,11 @@ static bool pick_rings(int mt, int passes, int ks, int NB, int extra, int* sa, i
 
 typedef void (*KernelFn)(const Maps, const Params);
 
-static KernelFn pick_kernel(int mt, int passes, int ks, bool f16) {
+static KernelFn pick_kernel(int mt, int passes, int ks, bool f16, bool step) {
+  if (step) {   // fused FlowStep layers: 3x3 chains, MT = 1 (chain_create enforces both)
+    if (f16) return passes == 3 ? conv_tc_kernel<1, 3, 3, true, true> : conv_tc_kernel<1, 1, 3, true, true>;
+    return passes == 3 ? conv_tc_kernel<1, 3, 3, false, true> : conv_tc_kernel<1, 1, 3, false, true>;
+  }
   if (f16) {
     if (ks == 1) return passes == 3 ? conv_tc_kernel<1, 3, 1, true> : conv_tc_kernel<1, 1, 1, true>;
     return passes == 3 ? conv_tc_kernel<1, 3, 3, true> : conv_tc_kernel<1, 1, 3, true>;
@@ -1678,7 +1751,12 @@ static int chain_create(const hcf_conv_args* args, const void* const* wtc, const
       }
   }
   pl->threads = f16 ? 384 : (passes == 3 ? 320 : 192);
-  pl->fn = pick_kernel(mt, passes, ks, f16);
+  if (tail_extra && ks != 3) {
+    hcf_conv_tc_plan_destroy(pl);
+    set_error("tc_chain: fused FlowStep layers need a 3x3 chain");
+    return HCF_ENOTSUP;
+  }
+  pl->fn = pick_kernel(mt, passes, ks, f16, tail_extra != 0);
   e = cudaFuncSetAttribute(reinterpret_cast<const void*>(pl->fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
                            SMEM_LIMIT);
   if (e != cudaSuccess) {
