@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the HCFlow inverse (sampling) pass -- BASELINE.json's metric.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp32|tf32|tf32x3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision f16x3|f16|tf32x3|tf32|fp32]
     python bench.py --impl reference ...      # the reference algorithm on the host CPU cores
 
 Workload (configs[1] of BASELINE.json): 4x SR, B=16 synthetic 40x40 LR tiles per GPU ->

@@ -715,3 +715,25 @@ def test_weight_reload_refreshes_every_derived_array(precision):
         want = fresh(lr=lr, eps_std=0.8, reverse=True, eps=unit)
     assert not torch.equal(first, got)
     assert torch.equal(got, want), float((got - want).abs().max())
+
+
+# forward (NLL) pass in the tensor-core modes: z within the modes' operand-rounding budget, log-det (fp64 accumulation
+# of per-pixel terms) to 1e-4 relative.  Measured values are written to the parity report.
+@pytest.mark.parametrize("precision,tol_z,tol_ld", [("f16x3", 2e-3, 1e-4), ("tf32x3", 2e-3, 1e-4), ("f16", 2e-2, 1e-3)])
+@pytest.mark.parametrize("cfg", ["sr_x4", "sr_x8"])
+def test_sr_forward_tensor_core_modes_match_reference_golden(cfg, precision, tol_z, tol_ld, report):
+    g = load_golden(cfg)
+    opt, net, sd = _net_cuda(cfg, precision)
+    lr, hr, unit, heat = _inputs(g, opt)
+    dq = torch.rand(hr.shape, generator=torch.Generator().manual_seed(77), dtype=torch.float32)
+    with torch.no_grad():
+        fake_lr, nll = net(hr=hr.cuda(), lr=lr.cuda(), u=None, reverse=False, training=False, dequant_noise=dq)
+    e_z = maxabs(net.last["z_raw"].cpu(), g["fwd_z"])
+    dirac = orc.gaussian_logp(lr, -torch.ones_like(lr) * 6, fake_lr.cpu()).double()
+    ld = net.last["objective"].cpu() - dirac
+    e_ld = float(((ld - g["fwd_logdet"].double()).abs() / g["fwd_logdet"].double().abs()).max())
+    eng = [e for e in net._engines.values()][-1]
+    report["e2e_forward_{}/{}".format(precision, cfg)] = {"z": e_z, "logdet_rel": e_ld, "tc_convs": eng.n_tc,
+                                                         "fp32_convs": eng.n_fp32_conv}
+    assert eng.n_tc > 0
+    assert e_z < tol_z and e_ld < tol_ld, (e_z, e_ld)
