@@ -233,16 +233,14 @@ struct Out16 { __half* hi; __half* lo; __half* hi2; __half* lo2; };
 // output view: which representations are written is a template parameter (one specialisation per layer kind of
 // a chain), so the per-pixel code is straight-line.  8 lanes cover the 32 channels of a pixel.
 // per-lane epilogue constants of one 32-column group (the lane's 4 channels)
-struct Chan4 { float4 bias, scale; int act; bool has_bias, has_scale; };
+struct Chan4 { float4 bias, scale; float slope; };
+// (o + bias) * scale, then max(o, slope * o): slope 1 = no activation, 0 = ReLU, 0.2 = LeakyReLU.  The inline table
+// holds bias 0 / scale 1 for layers without them, so the arithmetic is branch-free.
 __device__ __forceinline__ float4 chan_apply(float4 o, const Chan4& c) {
-  if (c.has_bias) { o.x += c.bias.x; o.y += c.bias.y; o.z += c.bias.z; o.w += c.bias.w; }
-  if (c.has_scale) { o.x *= c.scale.x; o.y *= c.scale.y; o.z *= c.scale.z; o.w *= c.scale.w; }
-  if (c.act == HCF_ACT_RELU) {
-    o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-  } else if (c.act == HCF_ACT_LRELU) {
-    o.x = o.x > 0.f ? o.x : 0.2f * o.x; o.y = o.y > 0.f ? o.y : 0.2f * o.y;
-    o.z = o.z > 0.f ? o.z : 0.2f * o.z; o.w = o.w > 0.f ? o.w : 0.2f * o.w;
-  }
+  o.x = (o.x + c.bias.x) * c.scale.x; o.y = (o.y + c.bias.y) * c.scale.y;
+  o.z = (o.z + c.bias.z) * c.scale.z; o.w = (o.w + c.bias.w) * c.scale.w;
+  o.x = fmaxf(o.x, c.slope * o.x); o.y = fmaxf(o.y, c.slope * o.y);
+  o.z = fmaxf(o.z, c.slope * o.z); o.w = fmaxf(o.w, c.slope * o.w);
   return o;
 }
 
@@ -995,7 +993,7 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
             Chan4 cc;   // bias / scale are padded to N entries; ch < N always
             cc.bias = *reinterpret_cast<const float4*>(s_bias + ch);
             cc.scale = *reinterpret_cast<const float4*>(s_scale + ch);
-            cc.act = act; cc.has_bias = has_bias; cc.has_scale = has_scale;
+            cc.slope = act == HCF_ACT_RELU ? 0.f : (act == HCF_ACT_LRELU ? 0.2f : 1.f);
 #define HCF_COAL(A, B_, C_) coal_store_fast<A, B_, C_>(stage, pixv, lane, ch, out_ld, out, o16.hi, o16.lo, cc, is_pre, hr1, hr2, \
                                                      r1v, r2v, alpha1, alpha2)
             switch (fast) {
