@@ -377,23 +377,6 @@ class Engine:
         return self.weights[key]
 
     # ---- fp16 chains ("f16" / "f16x3"): hi / lo planes shadowing the fp32 buffers -----------------------
-    @staticmethod
-    def _reads(op):
-        if isinstance(op, P.ConvOp):
-            return ([v for v, _ in op.segs] + [v for v in (op.res1, op.res2) if v is not None]
-                    + ([op.step.z] if op.step is not None else []))
-        if isinstance(op, P.StepOp):
-            return [v for v in (op.z, op.h) if v is not None]
-        if isinstance(op, P.PriorOp):
-            return [op.h, op.z]
-        if isinstance(op, P.LayoutOp):
-            return [op.src] if isinstance(op.src, P.View) else []
-        return []
-
-    @staticmethod
-    def _overlap(a, b):
-        return a.buf.name == b.buf.name and a.off < b.off + b.C and b.off < a.off + a.C
-
     def _shadow(self, buf):
         if buf.name not in self.shadow16:
             t = self.bufs[buf.name]
@@ -419,32 +402,6 @@ class Engine:
             self._tc_registry[key] = (op, passes, split_ch, True)
         return self.weights[key]
 
-    @staticmethod
-    def _writes(op):
-        if isinstance(op, P.ConvOp):
-            if op.step is not None:    # h is consumed in the epilogue, z is updated in place
-                return [op.step.z]
-            return [v for v in (op.out, op.out2, op.raw2) if v is not None]
-        if isinstance(op, P.StepOp):
-            return [op.z]
-        if isinstance(op, P.PriorOp):
-            return [op.z] if op.variant == "sample" else []
-        if isinstance(op, P.LayoutOp):
-            return [op.dst] if isinstance(op.dst, P.View) else []
-        return []
-
-    def _read_later(self, view, after_idx):
-        """Is `view` (written by a chain conv) read by an op after position `after_idx` before it is fully
-        overwritten?  (buffers are reused by later steps, so a plain overlap test would be too conservative)"""
-        for o in self.ops[after_idx + 1:]:
-            rd = self._reads(o) + ([o.pre] if isinstance(o, P.ConvOp) and o.pre is not None else [])
-            if any(self._overlap(v, view) for v in rd):
-                return True
-            if any(w.buf.name == view.buf.name and w.off <= view.off and w.off + w.C >= view.off + view.C
-                   for w in self._writes(o)):
-                return False
-        return False
-
     def _try_chain16(self, pending):
         """One persistent chained launch on fp16 operands (include/hcflow_b200.h, hcf_conv_chain16_create).
         Returns False (nothing emitted) when a conv of the run does not qualify."""
@@ -455,53 +412,21 @@ class Engine:
             return False
         passes = [self._passes_for(op) for op in ops]
         splits = [self._split_channels(op, ps) for op, ps in zip(ops, passes)]
-
-        def split_views(j):
-            """the input views of conv j that its split (hi + lo) covers"""
-            if passes[j] != 3:
-                return []
-            if splits[j] < 0:
-                return [v for v, _ in ops[j].segs]
-            out, left = [], splits[j]
-            for v, _ in ops[j].segs:
-                if left <= 0:
-                    break
-                out.append(v.sub(0, min(v.C, left)))
-                left -= (v.C + 63) // 64 * 64
-            return out
         last_idx = max(i for i, o in enumerate(self.ops) if o is ops[-1])
-        flags = []
-        for k, op in enumerate(ops):
-            outs = [v for v in (op.out, op.out2) if v is not None]
-            hi = lo = f32 = False
-            for j in range(k + 1, n):
-                if any(self._overlap(v, o) for v, _ in ops[j].segs for o in outs):
-                    hi = True
-                    lo = lo or any(self._overlap(v, o) for v in split_views(j) for o in outs)
-            for j in range(n):   # residual sources and pre-activation addends stay fp32
-                if any(self._overlap(v, o) for v in (ops[j].res1, ops[j].res2, ops[j].pre) if v is not None for o in outs):
-                    f32 = True
-            if any(self._read_later(o, last_idx) for o in outs):
-                f32 = True
-            if not (hi or f32):
-                f32 = True
-            flags.append((L.OUT_F32 if f32 else 0) | (L.OUT_HI if hi else 0) | (L.OUT_LO if lo else 0))
-        # inputs that no conv of the chain produced: converted to hi / lo right before the launch.  Views whose
+        lay = rewrite.chain16_layout(ops, passes, splits, self.ops[last_idx + 1:])   # pure data-flow decisions
+        if lay is None:
+            return False
+        flags = lay["flags"]
+        # inputs that no conv of the chain produced are converted to hi / lo right before the launch.  Views whose
         # geometry breaks TMA's 16-byte rules in fp16 (ld % 8, offset % 8) go through a private padded staging pair.
-        external = {}
         seg16 = (L.Seg16 * (3 * n))()
         staged = {}
         loc16 = {}     # (buffer, offset, C) -> (hi pointer, row pitch) of the fp16 copy the convs read
         for k, op in enumerate(ops):
             for si, (v, _) in enumerate(op.segs):
-                by_conv = any(self._overlap(v, o) for j in range(k) if ops[j].step is None
-                              for o in (ops[j].out, ops[j].out2) if o is not None)
-                by_step = any(ops[j].step is not None and self._overlap(v, ops[j].step.z) for j in range(k))
-                aligned = v.buf.C % 8 == 0 and v.off % 8 == 0
-                key = (v.buf.name, v.off, v.C)
-                if by_conv and not aligned:
-                    return False
-                if not aligned:
+                info = lay["segs"][k][si]
+                key = info["key"]
+                if info["staged"]:
                     if key not in staged:
                         ldp = (v.C + 7) // 8 * 8
                         name = "stage16_{}_{}_{}".format(*key)
@@ -515,18 +440,12 @@ class Engine:
                     loc16[key] = (hi_t.data_ptr(), ldp)
                 else:
                     loc16[key] = (self._shadow(v.buf)[0].data_ptr() + 2 * v.off, v.buf.C)
-                # the lo plane is needed as soon as ANY split conv of the chain reads these channels (e.g. the
-                # first RDB's conv5 reads x0 inside a wider view that is otherwise produced by the chain)
-                need_lo = any(self._overlap(v, sv) for j in range(n) for sv in split_views(j))
-                if by_step and need_lo:
-                    return False           # fused steps write the hi plane only
-                if not (by_conv or by_step) and key not in external:
-                    external[key] = (v, need_lo, staged.get(key))
-        for op in ops:   # where each fused FlowStep leaves the fp16 copy of z[:, :n_pass] for the next step's first conv
+        external = {key: (v, need_lo, staged.get(key) if is_staged else None)
+                    for key, (v, need_lo, is_staged) in lay["external"].items()}
+        for op, tkey in zip(ops, lay["step_target"]):   # where each fused FlowStep leaves the fp16 copy of z[:, :n_pass]
             if op.step is not None:
                 stp = self._step_structs[id(op)]
-                z = op.step.z
-                tgt = loc16.get((z.buf.name, z.off, op.step.n_pass))
+                tgt = loc16.get(tkey) if tkey else None
                 stp.z16_hi, stp.z16_ld = (tgt[0], tgt[1]) if tgt else (None, 0)
         bufs = {}
         for k, op in enumerate(ops):

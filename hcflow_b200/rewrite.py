@@ -154,3 +154,125 @@ def rewrite_ops(plan_ops, precision, share_cond=True, fuse=True, pair=True):
     if fuse:
         ops = fuse_steps(ops)
     return ops, bufs
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fp16 chains: which representation every conv writes, which inputs need converting, where fused steps leave z1
+OUT_F32, OUT_HI, OUT_LO = 1, 2, 4   # == _lib.OUT_* == HCF_OUT_* (include/hcflow_b200.h)
+
+
+def _overlap(a, b):
+    return a.buf.name == b.buf.name and a.off < b.off + b.C and b.off < a.off + a.C
+
+
+def op_reads(op):
+    if isinstance(op, P.ConvOp):
+        return ([v for v, _ in op.segs] + [v for v in (op.res1, op.res2, op.pre) if v is not None]
+                + ([op.step.z] if op.step is not None else []))
+    if isinstance(op, P.StepOp):
+        return [v for v in (op.z, op.h) if v is not None]
+    if isinstance(op, P.PriorOp):
+        return [op.h, op.z]
+    if isinstance(op, P.LayoutOp):
+        return [op.src] if isinstance(op.src, P.View) else []
+    return []
+
+
+def op_writes(op):
+    if isinstance(op, P.ConvOp):
+        if op.step is not None:    # h is consumed in the epilogue, z is updated in place
+            return [op.step.z]
+        return [v for v in (op.out, op.out2, op.raw2) if v is not None]
+    if isinstance(op, P.StepOp):
+        return [op.z]
+    if isinstance(op, P.PriorOp):
+        return [op.z] if op.variant == "sample" else []
+    if isinstance(op, P.LayoutOp):
+        return [op.dst] if isinstance(op.dst, P.View) else []
+    return []
+
+
+def read_later(view, later_ops):
+    """Is `view` (written by a chain conv) read by one of the ops that follow the chain before it is fully
+    overwritten?  (buffers are reused by later steps, so a plain overlap test would be too conservative)"""
+    for o in later_ops:
+        if any(_overlap(v, view) for v in op_reads(o)):
+            return True
+        if any(w.buf.name == view.buf.name and w.off <= view.off and w.off + w.C >= view.off + view.C
+               for w in op_writes(o)):
+            return False
+    return False
+
+
+def split_views(op, passes, split_ch):
+    """the input views of a conv that its split (hi + lo on both operands) covers"""
+    if passes != 3:
+        return []
+    if split_ch < 0:
+        return [v for v, _ in op.segs]
+    out, left = [], split_ch
+    for v, _ in op.segs:
+        if left <= 0:
+            break
+        out.append(v.sub(0, min(v.C, left)))
+        left -= (v.C + 63) // 64 * 64
+    return out
+
+
+def chain16_layout(ops, passes, splits, later_ops):
+    """Data-flow decisions for running the convs `ops` as one fp16 chain (engine._try_chain16 turns them into
+    pointers).  Returns None when the run does not qualify, else a dict:
+      flags[k]        OUT_F32 | OUT_HI | OUT_LO of conv k's output(s)
+      segs[k][s]      {"key": (buffer, offset, C), "staged": bool}  -- staged: the fp32 geometry breaks TMA's 16-byte
+                      rules in fp16 (ld % 8, offset % 8), the conv reads a private padded fp16 copy
+      external        {key: (view, need_lo, staged)} inputs that no conv / fused step of the chain produced: converted
+                      (hcf_split16) right before the launch
+      step_target[k]  key of the fp16 copy that conv k's fused FlowStep must leave for the next step's first conv (or None)
+    """
+    n = len(ops)
+    sv = [split_views(op, ps, sp) for op, ps, sp in zip(ops, passes, splits)]
+    flags = []
+    for k, op in enumerate(ops):
+        outs = [v for v in (op.out, op.out2) if v is not None]
+        hi = lo = f32 = False
+        for j in range(k + 1, n):
+            if any(_overlap(v, o) for v, _ in ops[j].segs for o in outs):
+                hi = True
+                lo = lo or any(_overlap(v, o) for v in sv[j] for o in outs)
+        for j in range(n):   # residual sources and pre-activation addends stay fp32
+            if any(_overlap(v, o) for v in (ops[j].res1, ops[j].res2, ops[j].pre) if v is not None for o in outs):
+                f32 = True
+        if any(read_later(o, later_ops) for o in outs):
+            f32 = True
+        if not (hi or f32):
+            f32 = True
+        flags.append((OUT_F32 if f32 else 0) | (OUT_HI if hi else 0) | (OUT_LO if lo else 0))
+    external, segs, known = {}, [], set()
+    for k, op in enumerate(ops):
+        row = []
+        for v, _ in op.segs:
+            by_conv = any(_overlap(v, o) for j in range(k) if ops[j].step is None
+                          for o in (ops[j].out, ops[j].out2) if o is not None)
+            by_step = any(ops[j].step is not None and _overlap(v, ops[j].step.z) for j in range(k))
+            aligned = v.buf.C % 8 == 0 and v.off % 8 == 0
+            key = (v.buf.name, v.off, v.C)
+            if by_conv and not aligned:
+                return None
+            # the lo plane is needed as soon as ANY split conv of the chain reads these channels (e.g. the first
+            # RDB's conv5 reads x0 inside a wider view that is otherwise produced by the chain)
+            need_lo = any(_overlap(v, s) for j in range(n) for s in sv[j])
+            if by_step and need_lo:
+                return None            # fused steps write the hi plane only
+            if not (by_conv or by_step) and key not in external:
+                external[key] = (v, need_lo, not aligned)
+            known.add(key)
+            row.append({"key": key, "staged": not aligned})
+        segs.append(row)
+    step_target = []
+    for op in ops:
+        if op.step is not None:
+            key = (op.step.z.buf.name, op.step.z.off, op.step.n_pass)
+            step_target.append(key if key in known else None)
+        else:
+            step_target.append(None)
+    return {"flags": flags, "segs": segs, "external": external, "step_target": step_target}

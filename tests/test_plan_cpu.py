@@ -88,3 +88,53 @@ def test_rewritten_reverse_plan_matches_golden(cfg):
     em = Emulator(net, plan, ops=ops, extra_bufs=extra)
     out = em.run(lr=lr, **{"eps{}".format(i): e for i, e in enumerate(eps)})
     assert maxabs(out["hr_raw"], g["inv_raw"]) < 2e-4
+
+
+def test_fp16_chain_layout_of_the_x4_encoder_and_flowstep_chains():
+    """rewrite.chain16_layout (the data-flow decisions behind hcf_conv_chain16_create) on the real x4 plan: the RDB
+    growth channels exist only as an fp16 hi plane, the residual stream keeps fp32 + hi + lo, inputs produced outside
+    the chain are converted once, and a fused FlowStep leaves its z1 copy where the next step's first conv reads it."""
+    from hcflow_b200 import _lib, rewrite
+    assert (rewrite.OUT_F32, rewrite.OUT_HI, rewrite.OUT_LO) == (_lib.OUT_F32, _lib.OUT_HI, _lib.OUT_LO)
+    opt, net, sd = net_and_weights("sr_x4")
+    plan = P.build_plan(net, "reverse", 2, 16, 16)
+    ops, _ = rewrite.rewrite_ops(plan.ops, "f16x3")
+    # runs of consecutive convs on one grid = the chains the engine builds
+    runs, cur = [], []
+    for i, o in enumerate(ops):
+        if isinstance(o, P.ConvOp) and (not cur or (ops[cur[-1]].H, ops[cur[-1]].W) == (o.H, o.W)) and (not cur or cur[-1] == i - 1):
+            cur.append(i)
+        else:
+            if len(cur) > 1:
+                runs.append(cur)
+            cur = [i] if isinstance(o, P.ConvOp) else []
+    if len(cur) > 1:
+        runs.append(cur)
+    assert len(runs) == 6          # per level: encoder, conditional FlowSteps, main FlowSteps
+
+    def passes_of(o):              # Engine._passes_for / _split_channels of the default mode
+        one = o.tag.startswith("fcn.") or o.tag in ("enc.rdb.conv1", "enc.rdb.conv2", "enc.rdb.conv3", "enc.rdb.conv4")
+        ps = 1 if one else 3
+        sp = 0 if ps == 1 else (o.res1.C if o.tag == "enc.rdb.conv5" else -1)
+        return ps, sp
+    for run in runs:
+        chain = [ops[i] for i in run]
+        ps, sp = zip(*[passes_of(o) for o in chain])
+        lay = rewrite.chain16_layout(chain, list(ps), list(sp), ops[run[-1] + 1:])
+        assert lay is not None
+        for o, fl in zip(chain, lay["flags"]):
+            if o.tag in ("enc.rdb.conv1", "enc.rdb.conv2", "enc.rdb.conv3", "enc.rdb.conv4"):
+                assert fl == rewrite.OUT_HI, (o.tag, fl)                       # growth channels: hi plane only
+            if o.tag == "enc.rdb.conv5":
+                assert fl == rewrite.OUT_F32 | rewrite.OUT_HI | rewrite.OUT_LO  # residual stream
+            if o.tag == "fcn.ucond":
+                assert fl == rewrite.OUT_F32                                    # read back as a pre-activation addend
+            if o.tag in ("fcn.conv1", "fcn.conv2"):
+                assert fl == rewrite.OUT_HI
+        if chain[0].tag == "enc.conv_first":
+            assert len(lay["external"]) == len(chain[0].segs)                   # only the first conv's inputs come from outside
+            assert all(need_lo for _, need_lo, _ in lay["external"].values())  # conv_first is a split layer
+        if any(o.step is not None for o in chain):
+            tg = [t for o, t in zip(chain, lay["step_target"]) if o.step is not None]
+            assert all(t is not None for t in tg[:-1])                          # every step but the last feeds a next conv1
+            assert all(not need_lo for _, need_lo, _ in lay["external"].values())
