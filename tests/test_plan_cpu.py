@@ -138,3 +138,26 @@ def test_fp16_chain_layout_of_the_x4_encoder_and_flowstep_chains():
             tg = [t for o, t in zip(chain, lay["step_target"]) if o.step is not None]
             assert all(t is not None for t in tg[:-1])                          # every step but the last feeds a next conv1
             assert all(not need_lo for _, need_lo, _ in lay["external"].values())
+
+
+@pytest.mark.parametrize("cfg", ["sr_x4", "sr_x8"])
+def test_rewritten_forward_plan_matches_golden(cfg):
+    """The forward (NLL) plan as the tensor-core modes rewrite it (shared conditioning convs, materialised up-sampled
+    segments; forward FlowSteps stay separate ops) still reproduces the reference's z and log-det."""
+    import math
+    from hcflow_b200 import rewrite
+    g = load_golden(cfg)
+    opt, net, sd = net_and_weights(cfg)
+    lr, hr, eps = _inputs(g, opt)
+    plan = P.build_plan(net, "forward", g["B"], g["h"], g["w"])
+    ops, extra = rewrite.rewrite_ops(plan.ops, "tf32x3")
+    assert any(isinstance(o, P.ConvOp) and o.pre is not None for o in ops)
+    assert not any(isinstance(o, P.ConvOp) and o.step is not None for o in ops)       # only inverse steps are fused
+    assert sum(isinstance(o, P.StepOp) for o in ops) == sum(isinstance(o, P.StepOp) for o in plan.ops)
+    em = Emulator(net, plan, ops=ops, extra_bufs=extra)
+    dq = torch.rand(hr.shape, generator=torch.Generator().manual_seed(77), dtype=torch.float32)
+    out = em.run(hr=hr, lr=lr, dequant=dq)
+    assert maxabs(out["z_raw"], g["fwd_z"]) < 2e-4
+    H, W = hr.shape[2], hr.shape[3]
+    nll = float(((-em.logdet) / (math.log(2.0) * H * W)).mean())
+    assert abs(nll - float(g["fwd_nll"])) < 1e-4 * abs(float(g["fwd_nll"]))
