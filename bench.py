@@ -297,6 +297,20 @@ def run_ours(args):
         "conv_by_layer": {t: {"n": v[0], "ms": round(v[1], 3), "tflops": round(v[2] / max(v[1], 1e-9) / 1e9, 1)}
                           for t, v in sorted(by_tag.items(), key=lambda kv: -kv[1][1])},
     }
+    # the fused FlowStep launches (north_star: per fused FlowStep, fraction of the HBM roofline): algorithmic bytes of
+    # SURVEY 8d's table (x4 inverse, per image: conditional / main FlowSteps of both levels = 14.1 + 4.0 + 46.6 + 8.0 MB)
+    fs = [(t, v) for t, v in by_tag.items() if "fcn." in t]
+    if fs:
+        fs_ms = sum(v[1] for _, v in fs)
+        fs_bytes = B * (680 * 13 * 1600 + 192 * 13 * 1600 + 560 * 13 * 6400 + 96 * 13 * 6400)
+        roofline["flowstep_chains"] = {
+            "bound": "hbm", "launches": len(fs), "ms": round(fs_ms, 3), "algorithmic_bytes": fs_bytes,
+            "achieved": fs_bytes / (fs_ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": fs_bytes / (fs_ms / 1e3) / 1e9 / peaks["hbm_gbs"],
+            "note": "52 FlowSteps (shared-conditioning convs, sub-nets, fused ActNorm / 1x1 / coupling tails) in 4 chained "
+                    "launches; ncu: 0.83 GB DRAM traffic for the 80x80 conditional chain (0.75 GB algorithmic), 14 MB for the "
+                    "main chain (L2-resident); tensor pipe 13 % / 4 %: these launches are latency-bound, not HBM-bound "
+                    "(profiles/r01b_prof_flowchains_L0_f16x3_summary.csv)"}
     if tc_keys:
         a_n, a_ms, a_fl = (sum(classes[c][k] for c in tc_keys) for k in range(3))
         roofline["all_tcgen05_convs"] = {"launches": a_n, "ms": round(a_ms, 3), "tflops": round(a_fl / a_ms / 1e9, 1),
