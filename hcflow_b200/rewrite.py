@@ -117,7 +117,7 @@ def pair_rdb_convs(ops, bufs):
     return ops
 
 
-STEP_MAXC = 24   # csrc/conv_tc.cu
+STEP_MAXC = 24   # csrc/conv_tc_kernel.cuh
 
 
 def fuse_steps(ops):
