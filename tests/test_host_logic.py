@@ -183,3 +183,32 @@ def test_fp16_weight_image_layout(cout, kin, ks, split_kin):
     assert base == img.numel()
     assert lib.hcf_conv_tc16_weight_bytes(kin + 1, cout, ks, 0) == 0
     assert lib.hcf_conv_tc16_pack_weights(w.data_ptr(), kin, cout, ks, 32, img.data_ptr()) != 0   # split not a multiple of 64
+
+
+@pytest.mark.parametrize("cout,kin,ks,passes", [(32, 64, 3, 1), (64, 96, 3, 3), (22, 32, 3, 1), (64, 64, 1, 3)])
+def test_tf32_weight_image_layout(cout, kin, ks, passes):
+    """hcf_conv_tc_pack_weights (host code): per 32-channel chunk [tap][rows][32 fp32], rows = [raw N ; lo N] for the
+    3xTF32 split (lo = w - trunc_tf32(w), the part the tensor core ignores when it reads an fp32 word as TF32),
+    16-byte groups XOR-swizzled by (row & 7)."""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(cout * 7 + kin)
+    w = (torch.randn(cout, kin, ks, ks, generator=g) * 0.05).contiguous()
+    N = (cout + 15) // 16 * 16
+    parts = 2 if passes == 3 else 1
+    NB = N * parts
+    nbytes = lib.hcf_conv_tc_weight_bytes(kin, cout, ks, passes)
+    assert nbytes == kin // 32 * ks * ks * NB * 128
+    img = torch.zeros(nbytes // 4, dtype=torch.float32)
+    assert lib.hcf_conv_tc_pack_weights(w.data_ptr(), kin, cout, ks, passes, img.data_ptr()) == 0
+    blk = img.view(kin // 32, ks * ks, NB, 8, 4)                                   # [chunk][tap][row][16-byte group][4]
+    rows = torch.arange(NB).view(1, 1, NB, 1, 1).expand_as(blk)
+    grp = torch.arange(8).view(1, 1, 1, 8, 1).expand_as(blk)
+    unsw = torch.gather(blk, 3, (grp ^ (rows & 7))).reshape(kin // 32, ks * ks, NB, 32)
+    ref = w.view(cout, kin // 32, 32, ks * ks).permute(1, 3, 0, 2)                 # [chunk][tap][cout][32]
+    assert torch.equal(unsw[:, :, :cout], ref)
+    if N > cout:
+        assert float(unsw[:, :, cout:N].abs().max()) == 0.0
+    if parts == 2:
+        hi = (ref.contiguous().view(torch.int32) & -8192).view(torch.float32)     # TF32 read = drop 13 mantissa bits
+        assert torch.equal(unsw[:, :, N:N + cout], ref - hi)
+    assert lib.hcf_conv_tc_weight_bytes(kin + 8, cout, ks, passes) == 0
