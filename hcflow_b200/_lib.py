@@ -19,7 +19,8 @@ class Seg(C.Structure):
 
 class ConvStep(C.Structure):
     _fields_ = [("z", C.c_void_p), ("z_ld", C.c_int32), ("C", C.c_int32), ("n_pass", C.c_int32), ("z16_ld", C.c_int32),
-                ("w", C.c_void_p), ("an_scale", C.c_void_p), ("an_bias", C.c_void_p), ("z16_hi", C.c_void_p)]
+                ("w", C.c_void_p), ("an_scale", C.c_void_p), ("an_bias", C.c_void_p), ("z16_hi", C.c_void_p),
+                ("z16_lo", C.c_void_p)]
 
 
 class ConvArgs(C.Structure):
@@ -80,6 +81,7 @@ class Seg16(C.Structure):
 
 
 OUT_F32, OUT_HI, OUT_LO = 1, 2, 4
+ABI_VERSION = 3   # == HCF_ABI_VERSION (include/hcflow_b200.h)
 
 # every symbol include/hcflow_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
@@ -145,7 +147,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.hcf_abi_version() != 2:
+    if lib.hcf_abi_version() != ABI_VERSION:
         raise HcfError("ABI version mismatch")
     _lib = lib
     return lib

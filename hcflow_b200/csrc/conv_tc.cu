@@ -488,6 +488,7 @@ static int chain_create(const hcf_conv_args* args, const void* const* wtc, const
       L.step_z = st.z; L.step_z_ld = st.z_ld; L.step_C = st.C; L.step_npass = st.n_pass;
       L.step_w = st.w; L.step_sc = st.an_scale; L.step_b = st.an_bias;
       L.step_z16 = reinterpret_cast<__half*>(st.z16_hi); L.step_z16_ld = st.z16_ld;
+      L.step_z16_lo = reinterpret_cast<__half*>(st.z16_lo);
       L.out = nullptr; L.out2 = nullptr;
     }
     bool ov = aligned16(a.out) && a.out_ld % 4 == 0;

@@ -106,6 +106,7 @@ struct LayerDesc {
   float* step_z; int step_z_ld, step_C, step_npass;
   const float* step_w; const float* step_sc; const float* step_b;
   __half* step_z16; int step_z16_ld;   // fp16 chains: hi plane of z[:, :n_pass] for the next step's first conv
+  __half* step_z16_lo;                 // ... and its lo plane (that conv runs split), may be null
 };
 
 struct Params {
@@ -294,7 +295,8 @@ constexpr int STEP_TAB_BYTES = (STEP_MAXC * STEP_MAXC + 2 * STEP_MAXC) * 4 + 64;
 __device__ __forceinline__ void step_inverse_pixel(float* __restrict__ scratch, int lane, const float4 (&zq)[8],
                                                    float* __restrict__ zp, int C, int n_pass, bool has_w,
                                                    const float* __restrict__ s_w, const float* __restrict__ s_sc,
-                                                   const float* __restrict__ s_b, __half* __restrict__ z16p) {
+                                                   const float* __restrict__ s_b, __half* __restrict__ z16p,
+                                                   __half* __restrict__ z16lo) {
   float z[STEP_MAXC];   // z arrives in the (otherwise unused) residual prefetch registers: 6 x float4
 #pragma unroll
   for (int i = 0; i < STEP_MAXC / 4; ++i) {
@@ -323,7 +325,11 @@ __device__ __forceinline__ void step_inverse_pixel(float* __restrict__ scratch, 
   for (int i = 0; i < C; ++i) {
     const float v = scratch[i * 32 + lane];
     zp[i] = v;
-    if (z16p && i < n_pass) z16p[i] = __float2half_rn(v);
+    if (z16p && i < n_pass) {
+      const __half hh = __float2half_rn(v);
+      z16p[i] = hh;
+      if (z16lo) z16lo[i] = __float2half_rn((v - __half2float(hh)) * 2048.0f);
+    }
   }
 }
 
@@ -335,7 +341,8 @@ template <int C>
 __device__ __forceinline__ void step_inverse_pixel_t(const float* __restrict__ scratch, int lane, const float4 (&zq)[8],
                                                      float* __restrict__ zp, int n_pass, bool has_w,
                                                      const float* __restrict__ s_w, const float* __restrict__ s_sc,
-                                                     const float* __restrict__ s_b, __half* __restrict__ z16p) {
+                                                     const float* __restrict__ s_b, __half* __restrict__ z16p,
+                                                     __half* __restrict__ z16lo) {
   float z[C];
 #pragma unroll
   for (int i = 0; i < C; ++i) {
@@ -382,7 +389,11 @@ __device__ __forceinline__ void step_inverse_pixel_t(const float* __restrict__ s
   for (int i = 0; i < C; ++i) {
     const float v = y[i] * s_sc[i] - s_b[i];
     zp[i] = v;
-    if (z16p && i < n_pass) z16p[i] = __float2half_rn(v);
+    if (z16p && i < n_pass) {
+      const __half hh = __float2half_rn(v);
+      z16p[i] = hh;
+      if (z16lo) z16lo[i] = __float2half_rn((v - __half2float(hh)) * 2048.0f);
+    }
   }
 }
 
@@ -783,7 +794,7 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
     bool is_pre = false;   // res1 holds the pre-activation addend (prefetched through the same registers)
     float* step_z = nullptr; int step_z_ld = 0, step_C = 0, step_npass = 0, step_z16_ld = 0;
     const float* step_w = nullptr; const float* step_sc = nullptr; const float* step_b = nullptr;
-    __half* step_z16 = nullptr;
+    __half* step_z16 = nullptr; __half* step_z16_lo = nullptr;
     float* raw2 = nullptr; int raw2_ld = 0;
     HCF_T(te0);
     for (int seq = grp, item; (item = item_at(seq)) >= 0; seq += EG, t_it += EG) {
@@ -813,6 +824,7 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
           step_z_ld = __ldg(&L->step_z_ld); step_C = __ldg(&L->step_C); step_npass = __ldg(&L->step_npass);
           step_w = ldg_ptr(&L->step_w); step_sc = ldg_ptr(&L->step_sc); step_b = ldg_ptr(&L->step_b);
           step_z16 = ldg_ptr(&L->step_z16); step_z16_ld = __ldg(&L->step_z16_ld);
+          step_z16_lo = ldg_ptr(&L->step_z16_lo);
         }
         raw2 = ldg_ptr(&L->raw2);
         if (raw2) { raw2_ld = __ldg(&L->raw2_ld); cout = 32; }   // the main path sees columns [0, 32) only
@@ -917,6 +929,12 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                 float v[16];
                 const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (acc * MT + mt) * p.nb_max + (uint32_t)(h * 16);
                 tmem_ld16(tcol, v);
+                if (PASSES == 3 && parts == 2) {   // split sub-net conv: main + correction columns
+                  float lo[16];
+                  tmem_ld16(tcol + (uint32_t)N, lo);
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) v[j] = F16 ? fmaf(lo[j], 1.0f / 2048.0f, v[j]) : v[j] + lo[j];
+                }
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                   float t = v[j];
@@ -936,13 +954,14 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
               const uint32_t pix = (uint32_t)((b * p.H + gy) * p.W + gx);
               float* zp = step_z + (size_t)pix * step_z_ld;
               __half* z16p = step_z16 ? step_z16 + (size_t)pix * step_z16_ld : nullptr;
+              __half* z16lo = (step_z16 && step_z16_lo) ? step_z16_lo + (size_t)pix * step_z16_ld : nullptr;
               const bool hw = step_w != nullptr;
               switch (step_C) {
-                case 6: step_inverse_pixel_t<6>(scratch, lane, r1v, zp, step_npass, hw, st_w, st_sc, st_b, z16p); break;
-                case 12: step_inverse_pixel_t<12>(scratch, lane, r1v, zp, step_npass, hw, st_w, st_sc, st_b, z16p); break;
-                case 21: step_inverse_pixel_t<21>(scratch, lane, r1v, zp, step_npass, hw, st_w, st_sc, st_b, z16p); break;
-                case 24: step_inverse_pixel_t<24>(scratch, lane, r1v, zp, step_npass, hw, st_w, st_sc, st_b, z16p); break;
-                default: step_inverse_pixel(scratch, lane, r1v, zp, step_C, step_npass, hw, st_w, st_sc, st_b, z16p); break;
+                case 6: step_inverse_pixel_t<6>(scratch, lane, r1v, zp, step_npass, hw, st_w, st_sc, st_b, z16p, z16lo); break;
+                case 12: step_inverse_pixel_t<12>(scratch, lane, r1v, zp, step_npass, hw, st_w, st_sc, st_b, z16p, z16lo); break;
+                case 21: step_inverse_pixel_t<21>(scratch, lane, r1v, zp, step_npass, hw, st_w, st_sc, st_b, z16p, z16lo); break;
+                case 24: step_inverse_pixel_t<24>(scratch, lane, r1v, zp, step_npass, hw, st_w, st_sc, st_b, z16p, z16lo); break;
+                default: step_inverse_pixel(scratch, lane, r1v, zp, step_C, step_npass, hw, st_w, st_sc, st_b, z16p, z16lo); break;
               }
             }
             __syncwarp();

@@ -30,7 +30,7 @@ extern "C" {
 #define HCF_EINVAL (-1)   /* bad argument (shape / alignment / unsupported size) */
 #define HCF_ENOTSUP (-2)  /* combination not implemented by this kernel */
 
-#define HCF_ABI_VERSION 2
+#define HCF_ABI_VERSION 3
 
 /* ---- introspection -------------------------------------------------------------- */
 int hcf_abi_version(void);
@@ -86,6 +86,7 @@ typedef struct {
   const float* an_scale; /* exp(-logs) [C] */
   const float* an_bias;  /* [C] */
   void* z16_hi;          /* optional: fp16 copy of the new z[:, :n_pass], row pitch z16_ld (fp16 chains) */
+  void* z16_lo;          /* optional (with z16_hi): its lo plane, fp16((z - hi) * 2048): the next step's first conv runs split */
 } hcf_conv_step;
 
 typedef struct {

@@ -38,6 +38,12 @@ CASES = {
     "sr_x4": ("sr_x4", 2, 12, 12, 0.8),
     "sr_x8": ("sr_x8", 1, 8, 8, 0.8),
     "rescaling_x4": ("rescaling_x4", 1, 10, 10, 1.0),
+    # stress fixtures (hcflow_b200.synth.STRESS): coupling outputs h of order 1 like a trained flow's, on a flow shallow
+    # enough not to diverge -- the regular fixtures keep every coupling within 2 % of the identity, which hides
+    # operand-rounding error of the coupling sub-nets
+    "sr_x4_stress": ("sr_x4", 2, 12, 12, 0.8),
+    "sr_x8_stress": ("sr_x8", 1, 8, 8, 0.8),
+    "rescaling_x4_stress": ("rescaling_x4", 1, 10, 10, 1.0),
 }
 
 
@@ -89,12 +95,20 @@ def main():
     networks = ref_loader.load()
     from models.modules import Basic as RB  # reference module
     os.makedirs(GOLD, exist_ok=True)
+    only = set(sys.argv[1:])
     for name, (cfg, B, h, w, heat) in CASES.items():
+        if only and name not in only:
+            continue
         opt = popt.load_config(cfg)
         check_yaml_matches_reference(cfg, opt)
+        stress = synth.STRESS.get(name)
+        if stress:
+            opt = popt.shrink_config(opt, K=stress["K"], after=stress["after"])
         SR = opt["network_G"]["which_model_G"] == "HCFlowNet_SR"
         net = build_reference(networks, opt)
         sd = synth.synthetic_state_dict(net.state_dict(), seed=1)
+        if stress:
+            sd = synth.stress_state_dict(sd, stress["s_weight"], stress["s_bias"])
         net.load_state_dict(sd, strict=True)
         mark_inited(net)
         scale = opt["scale"]
@@ -180,7 +194,25 @@ def main():
         out["modules"] = mods
         path = os.path.join(GOLD, name + ".pt")
         torch.save(out, path)
-        print("wrote", path, os.path.getsize(path), "bytes;",
+        hmax = []
+        if True:   # coupling strength of the fixture (max |h| over the sub-net calls of the inverse pass), for the record
+            f0, d0 = orc.fcn, orc.dense_block
+
+            def rec(fn):
+                def wrapped(*a, **k):
+                    y = fn(*a, **k)
+                    hmax.append(float(y.abs().max()))
+                    return y
+                return wrapped
+            orc.fcn, orc.dense_block = rec(f0), rec(d0)
+            try:
+                with torch.no_grad():
+                    orc.flownet_reverse(lr, sd, opt, eps, SR)
+            finally:
+                orc.fcn, orc.dense_block = f0, d0
+            out["h_absmax"] = max(hmax)
+            torch.save(out, path)
+        print("wrote", path, os.path.getsize(path), "bytes; |h|max {:.3f};".format(max(hmax)),
               "inv_raw range [{:.3f}, {:.3f}]".format(float(out["inv_raw"].min()), float(out["inv_raw"].max())),
               "fwd_nll" if SR else "", float(out["fwd_nll"]) if SR else "")
 

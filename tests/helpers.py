@@ -18,12 +18,18 @@ _CACHE = {}
 
 
 def net_and_weights(cfg, seed=1):
-    """(opt, product net on CPU with synthetic weights loaded, state_dict)."""
+    """(opt, product net on CPU with synthetic weights loaded, state_dict).  ``cfg`` may name a stress fixture
+    (synth.STRESS: shallow flow, coupling outputs of order 1)."""
     key = (cfg, seed)
     if key not in _CACHE:
-        opt = popt.load_config(cfg)
+        stress = synth.STRESS.get(cfg)
+        opt = popt.load_config(stress["cfg"] if stress else cfg)
+        if stress:
+            opt = popt.shrink_config(opt, K=stress["K"], after=stress["after"])
         net = build_net(opt)
         sd = synth.synthetic_state_dict(net.state_dict(), seed=seed)
+        if stress:
+            sd = synth.stress_state_dict(sd, stress["s_weight"], stress["s_bias"])
         net.load_state_dict(sd, strict=True)
         net.eval()
         _CACHE[key] = (opt, net, sd)

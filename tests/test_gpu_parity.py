@@ -29,7 +29,7 @@ def _rand(*shape, seed=0, scale=1.0):
 # ------------------------------------------------------------------------------ library
 def test_native_library_is_loaded():
     lib = L.load()
-    assert lib.hcf_abi_version() == 2
+    assert lib.hcf_abi_version() == L.ABI_VERSION
     with open("/proc/self/maps") as f:
         assert "libhcflow_b200.so" in f.read()
 

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     declared -= {"hcf_conv_tc_plan"}
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     lib = _lib.load()  # raises if the .so is missing or a symbol is not exported
-    assert lib.hcf_abi_version() == 2
+    assert lib.hcf_abi_version() == _lib.ABI_VERSION
     assert lib.hcf_last_error() is not None
 
 
