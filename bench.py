@@ -83,55 +83,114 @@ class ClockSampler(threading.Thread):
                 "reasons": [n for b, n in self.REASONS.items() if self.mask & b]}
 
 
-# --------------------------------------------------------------------------- CPU arms
-def oracle_inverse_mps(batch, budget_s, warmup, steps=None):
-    """Times the oracle (CPU restatement of the reference algorithm) on all host threads."""
+# --------------------------------------------------------------------------- reference arms
+def reference_net(device):
+    """The UNMODIFIED reference net (codes/models/networks.py:36-41 define_G) with the synthetic weights, from the copy
+    oracle/build_ref.py staged under oracle/_ref (or /root/reference in the authoring container).  None if absent."""
+    from hcflow_b200 import options as popt, synth
+    from oracle import ref_loader
+    if not ref_loader.available():
+        return None
+    import numpy as np
+    networks = ref_loader.load()
+    opt = popt.load_config("sr_x4")
+    torch.manual_seed(0)
+    np.random.seed(0)
+    net = networks.define_G(opt, 0)
+    net.load_state_dict(synth.synthetic_state_dict(net.state_dict(), seed=1), strict=True)
+    for m in net.modules():     # HCFlowSRModel.load marks ActNorm initialised (HCFlow_SR_model.py:462-465)
+        if hasattr(m, "inited"):
+            m.inited = True
+    return net.to(device).eval()
+
+
+def cpu_inverse_mps(batch, budget_s, warmup, steps=None):
+    """Times the reference's CPU path for the inverse pass on all host threads: the unmodified reference modules when
+    they are staged (kind "reference"; test_HCFlow.py's call, HCFlow_SR_model.py:308-312), else the oracle port."""
     from hcflow_b200 import options as popt, synth
     from hcflow_b200.arch import build_net
     from oracle import hcflow_oracle as orc
-    opt = popt.load_config("sr_x4")
-    net = build_net(opt)
-    sd = synth.synthetic_state_dict(net.state_dict(), seed=1)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     lr = synth.synthetic_lr(batch, LR_HW, LR_HW, seed=0)
-    eps = [HEAT * e for e in synth.synthetic_noise(orc.noise_shapes(opt, batch, LR_HW, LR_HW, True))]
+    ref = reference_net("cpu")
+    if ref is not None:
+        kind = "reference"
+
+        def one():
+            return ref(lr=lr, z=None, u=None, eps_std=HEAT, reverse=True, training=False)
+    else:
+        kind = "port"
+        opt = popt.load_config("sr_x4")
+        sd = synth.synthetic_state_dict(build_net(opt).state_dict(), seed=1)
+        eps = [HEAT * e for e in synth.synthetic_noise(orc.noise_shapes(opt, batch, LR_HW, LR_HW, True))]
+
+        def one():
+            return orc.sr_reverse(lr, sd, opt, eps)
     times = []
     with torch.no_grad():
         for _ in range(warmup):
-            orc.sr_reverse(lr, sd, opt, eps)
+            one()
         t_end = time.perf_counter() + budget_s
         while True:
             t0 = time.perf_counter()
-            orc.sr_reverse(lr, sd, opt, eps)
+            one()
             times.append(time.perf_counter() - t0)
             if steps is not None and len(times) >= steps:
                 break
             if steps is None and (time.perf_counter() > t_end or len(times) >= 50):
                 break
     mp = batch * (LR_HW * SCALE) ** 2 / 1e6
-    return mp, times, cores
+    return mp, times, cores, kind
+
+
+def gpu_eager_baseline(dev, lr, steps=5):
+    """SURVEY 2a's comparator: the unmodified reference modules on the SAME B200 through stock PyTorch / cuDNN (TF32
+    convs allowed = PyTorch's default), same batch, device-resident input, CUDA events.  None if not staged."""
+    ref = reference_net(dev)
+    if ref is None:
+        return None
+    torch.backends.cudnn.allow_tf32 = True
+    x = lr.to(dev)
+    with torch.no_grad():
+        for _ in range(2):
+            ref(lr=x, z=None, u=None, eps_std=HEAT, reverse=True, training=False)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            out = ref(lr=x, z=None, u=None, eps_std=HEAT, reverse=True, training=False)
+        b.record()
+        torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    B = x.shape[0]
+    del ref
+    torch.cuda.empty_cache()
+    return {"value": B * (LR_HW * SCALE) ** 2 / 1e6 / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+            "what": "unmodified reference modules (define_G) on this GPU, stock PyTorch {} eager, cuDNN TF32 convs "
+                    "allowed, B={}".format(torch.__version__, B), "finite": bool(torch.isfinite(out).all())}
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = 2
-    mp, times, cores = oracle_inverse_mps(batch, budget_s=0, warmup=max(1, min(args.warmup, 2)), steps=args.steps)
+    batch = B_PER_GPU    # the workload's own batch: one step = one full configs[1] pass on the host cores
+    mp, times, cores, kind = cpu_inverse_mps(batch, budget_s=0, warmup=1, steps=args.steps)
     total = sum(times)
     value = mp * len(times) / total
-    sample = "{} timed passes of B={} (of the B=16 workload), 40x40 LR -> 160x160 HR".format(len(times), batch)
+    sample = "{} timed passes of B={} (the full workload batch), 40x40 LR -> 160x160 HR, T=0.8".format(len(times), batch)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-        "note": "reference is pure Python/torch and /root/reference is absent on the GPU box: this arm times "
-                "oracle/hcflow_oracle.py (same torch CPU ops, bit-exact vs the reference goldens)",
+        "gpu_launches": 0, "same_config": True,
+        "note": ("the UNMODIFIED reference modules (networks.define_G, staged by oracle/build_ref.py) on torch CPU fp32, "
+                 "all host threads" if kind == "reference" else
+                 "reference copy not staged: oracle/hcflow_oracle.py (same torch CPU ops, bit-exact vs the reference goldens)"),
     }
     print(json.dumps(line), flush=True)
 
@@ -147,9 +206,38 @@ def conv_flops(plan, B):
     return total
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch (chained encoder kernel, 80x80 level), one
-# ncu --set full capture per precision mode (profiles/README.md)
-NCU_DRAM_BYTES = {"tf32x3": 5.76e9, "tf32x3_all": 5.76e9, "tf32": 5.42e9, "f16": 5.12e9, "f16x3": 7.28e9}
+def ncu_dram_bytes(precision):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch (chained encoder kernel, 80x80 level) from the
+    newest committed `ncu --set full` summary of this precision mode under profiles/ -> (bytes, file name) or (None, None)."""
+    import glob
+    cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_prof_chain_L0_{}_summary.csv".format(precision))))
+    for path in reversed(cands):
+        tot, unit_scale = 0.0, {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        found = 0
+        with open(path) as f:
+            for line in f:
+                parts = line.strip().split(",")
+                if len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    tot += float(parts[2]) * unit_scale.get(parts[1], 1.0)
+                    found += 1
+        if found == 2:
+            return tot, os.path.basename(path)
+    return None, None
+
+
+def parity_from_report():
+    """Measured parity numbers of the newest committed GPU parity report (written by pytest -m gpu) -- never literals."""
+    import glob
+    cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_parity_report.json")))
+    if not cands:
+        return None
+    with open(cands[-1]) as f:
+        rep = json.load(f)
+    keep = {}
+    for k, v in rep.items():
+        if k.startswith(("e2e_reverse", "stress_reverse", "config", "e2e_forward", "stress_forward")):
+            keep[k] = v
+    return {"file": os.path.basename(cands[-1]), "measured": keep}
 
 
 def per_class_times(eng):
@@ -175,6 +263,73 @@ def per_class_times(eng):
             n, ms, f = by_tag.get(tag, (0, 0.0, 0.0))
             by_tag[tag] = (n + 1, ms + a.elapsed_time(b), f + fl)
     per_class_times.by_tag = by_tag
+    return out
+
+
+def run_configs4(net, opt, dev, rank, world, hd, orc, flush, steps):
+    """configs[4] as BASELINE.json states it: 4x SR, global batch 64 x N sharded over the N ranks (64 per GPU; the
+    reference's batch_size // world_size, codes/data/__init__.py:13-14), inverse pass, plus one forward NLL step whose
+    batch mean (HCFlowNet_SR_arch.py:65 nll.mean()) is the path's only collective: ONE all-reduce of (sum nll_i, count)
+    over NCCL, inside the timed region.  Every rank takes part; times are the max over ranks."""
+    from hcflow_b200 import synth
+    B4, HR = 64, LR_HW * SCALE
+    lr = synth.synthetic_lr(B4, LR_HW, LR_HW, seed=100 + rank)
+    hr = synth.synthetic_hr(B4, HR, HR, seed=100 + rank)
+    unit = synth.synthetic_noise(orc.noise_shapes(opt, B4, LR_HW, LR_HW, True), seed=200 + rank)
+    er = net.engine("reverse", B4, LR_HW, LR_HW, dev)
+    er.ext["lr"].copy_(lr)
+    for i, e in enumerate(unit):
+        er.ext["eps{}".format(i)].copy_(HEAT * e)
+    for _ in range(3):
+        er.run()
+    torch.cuda.synchronize()
+    hd.barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        flush.fill_(1.0)
+        a.record()
+        er.run()
+        b.record()
+    torch.cuda.synchronize()
+    hd.barrier()
+    inv_ms = hd.max_over_ranks(sum(a.elapsed_time(b) for a, b in ev), dev) / steps
+    # forward NLL with the all-reduce of the batch mean
+    ef = net.engine("forward", B4, LR_HW, LR_HW, dev)
+    ef.ext["hr"].copy_(hr)
+    ef.ext["lr"].copy_(lr)
+    ef.ext["dequant"].copy_(torch.rand(hr.shape, generator=torch.Generator().manual_seed(300 + rank)))
+    ln2hw = float(math.log(2.0) * HR * HR)
+
+    def fwd_step():
+        ef.run()
+        per_image = (-ef.logdet) / ln2hw            # fp64 [B4]: the reference's per-image nll before .mean()
+        return hd.batch_mean_nll(per_image)
+    for _ in range(3):
+        nll = fwd_step()
+    torch.cuda.synchronize()
+    hd.barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(steps)]
+    for a, m, b in ev:
+        flush.fill_(1.0)
+        a.record()
+        ef.run()
+        m.record()
+        nll = hd.batch_mean_nll((-ef.logdet) / ln2hw)
+        b.record()
+    torch.cuda.synchronize()
+    hd.barrier()
+    fwd_ms = hd.max_over_ranks(sum(a.elapsed_time(b) for a, _, b in ev), dev) / steps
+    ar_us = hd.max_over_ranks(sorted(m.elapsed_time(b) for _, m, b in ev)[steps // 2], dev) * 1e3
+    mp = world * B4 * HR * HR / 1e6
+    out = {"workload": "configs[4]: 4x SR, global batch {} = 64/GPU x {} GPU(s), 160x160 HR".format(B4 * world, world),
+           "inverse": {"value": mp / (inv_ms / 1e3), "unit": UNIT, "ms_per_step": inv_ms, "steps": steps},
+           "forward_nll": {"value": mp / (fwd_ms / 1e3), "unit": UNIT, "ms_per_step": fwd_ms, "steps": steps,
+                           "batch_mean_nll": float(nll), "allreduce_us_median": ar_us,
+                           "collective": "torch.distributed all_reduce(SUM) of 2 doubles, backend {}".format(
+                               torch.distributed.get_backend() if torch.distributed.is_initialized() else "none (1 rank)")}}
+    net.clear_engines()
+    torch.cuda.empty_cache()
     return out
 
 
@@ -259,6 +414,10 @@ def run_ours(args):
     e2e_ms = hd.max_over_ranks(e0.elapsed_time(e1), dev)
     e2e_value = mp_step * args.steps / (e2e_ms / 1e3)
 
+    cfg4 = None
+    if world > 1 or args.configs4:
+        cfg4 = run_configs4(net, opt, dev, rank, world, hd, orc, flush, steps=max(3, min(args.steps, 10)))
+
     if rank != 0:
         return
     # ---- roofline of the dominant kernel class (eager pass, per-launch events)
@@ -279,15 +438,15 @@ def run_ours(args):
     n, ms, fl = by_tag[top_tag]
     achieved = fl / (ms / 1e3) / 1e12
     # DRAM bytes per launch of that kernel from the committed ncu --set full capture (profiles/README.md)
-    ncu_traffic = NCU_DRAM_BYTES.get(args.precision) if "chain" in top_tag and "enc." in top_tag else None
+    ncu_traffic, ncu_file = ncu_dram_bytes(args.precision) if "chain" in top_tag and "enc." in top_tag else (None, None)
     f16_mode = args.precision in ("f16", "f16x3")
     # the launch is timed inside the step (per-launch events of an eager pass): the sustained figure applies
     peak_used = peaks.get("bf16_tflops_sustained") or peaks["bf16_tflops"]
     roofline = {
         "bound": "tensor", "kernel": "conv_tc_kernel " + top_tag, "achieved": achieved, "peak": peak_used,
         "unit": "TFLOP/s", "frac": achieved / peak_used, "traffic": ncu_traffic, "peak_burst": peaks["bf16_tflops"],
-        "traffic_note": "dram__bytes_read+write per launch, ncu --set full, profiles/r01*_prof_chain_L0_*; "
-                        "algorithmic bytes of that launch = 2.34e9",
+        "traffic_note": "dram__bytes_read+write per launch read from profiles/{} (ncu --set full of this launch); "
+                        "algorithmic bytes of that launch = 2.34e9".format(ncu_file),
         "peak_source": "{} bf16 sustained from MEASURED_PEAKS.json ({})".format(
             peaks["source"], "the kernel computes on fp16 operands: same tensor rate; split layers issue 2 MMAs per useful "
             "K-step" if f16_mode else "the kernel computes in TF32, nominal peak = half of it; tf32x3 issues 2 MMAs per "
@@ -318,10 +477,13 @@ def run_ours(args):
     # ---- CPU baseline (rank 0, N=1 only): the oracle on the host cores, bounded sample
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        mp, times, cores = oracle_inverse_mps(1, budget_s=12.0, warmup=1)
-        cpu = {"value": mp * len(times) / sum(times), "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "{} passes of configs[0] (B=1, 40x40 LR -> 160x160 HR, T=0.8), oracle on torch CPU fp32".format(
-                   len(times))}
+        mp, times, cores, kind = cpu_inverse_mps(1, budget_s=12.0, warmup=1)
+        cpu = {"value": mp * len(times) / sum(times), "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": "{} passes of configs[0] (B=1, 40x40 LR -> 160x160 HR, T=0.8), {} on torch CPU fp32".format(
+                   len(times), "unmodified reference modules" if kind == "reference" else "oracle port")}
+    eager = None
+    if world == 1 and not args.no_eager_baseline:
+        eager = gpu_eager_baseline(dev, lr)
     # ---- the other precision modes, device-resident, short (same inputs, same graph-replay method)
     modes = {args.precision: {"value": value, "ms_per_step": t_ms / args.steps}}
     if world == 1 and not args.no_modes:
@@ -348,7 +510,7 @@ def run_ours(args):
             torch.cuda.synchronize()
             ms3 = sum(a.elapsed_time(b) for a, b in zip(s3, f3)) / n3
             modes[prec] = {"value": B * HR * HR / 1e6 / (ms3 / 1e3), "ms_per_step": ms3}
-            net._engines.clear()
+            net.clear_engines()
             torch.cuda.empty_cache()
         net.set_precision(args.precision)
     line = {
@@ -366,10 +528,12 @@ def run_ours(args):
         "clocks": sampler.summary(),
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "gpu_eager_baseline": eager,
         "modes": modes,
-        "parity": "tests/test_gpu_parity.py: un-clamped HR vs reference goldens max-abs fp32 5e-6, f16x3 7e-5, tf32x3 8e-5, "
-                  "f16 1.7e-3, tf32 1.3e-2 (tolerances 2e-4 / 2e-3 / 2e-3 / 2e-2 / 5e-2)",
+        "parity": parity_from_report(),
     }
+    if cfg4 is not None:
+        line["configs4"] = cfg4
     print(json.dumps(line), flush=True)
 
 
@@ -387,6 +551,8 @@ def main():
                          "as TF32; fp32: CUDA-core kernels")
     ap.add_argument("--no-modes", action="store_true", help="skip the short runs of the other precision modes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the stock-PyTorch run of the reference modules on the GPU")
+    ap.add_argument("--configs4", action="store_true", help="also run configs[4]'s per-GPU shard (B=64) at N=1 (always on for N>1)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches (for ncu)")
     ap.add_argument("--skip-e2e", action="store_true")
     args = ap.parse_args()

@@ -81,6 +81,7 @@ class Seg16(C.Structure):
 
 
 OUT_F32, OUT_HI, OUT_LO = 1, 2, 4
+STATUS_F16_OVERFLOW, STATUS_DEP_TIMEOUT = 1, 2
 ABI_VERSION = 3   # == HCF_ABI_VERSION (include/hcflow_b200.h)
 
 # every symbol include/hcflow_b200.h declares: name -> (restype, argtypes)
@@ -107,6 +108,7 @@ SYMBOLS = {
     "hcf_conv_tc_plan_layers": (C.c_int32, [C.c_void_p]),
     "hcf_conv_tc_run": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hcf_conv_tc_plan_refresh": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hcf_conv_tc_plan_set_status": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hcf_conv_tc_plan_destroy": (None, [C.c_void_p]),
     "hcf_step_inverse": (C.c_int, [C.POINTER(StepArgs), C.c_void_p]),
     "hcf_step_forward_head": (C.c_int, [C.POINTER(StepArgs), C.c_void_p]),

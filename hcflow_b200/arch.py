@@ -13,6 +13,7 @@ Extensions (keyword-only, all optional, ignored by the reference's callers):
   dequant_noise= the U[0,1) tensor used instead of torch.rand of HCFlowNet_SR_arch.py:52
 After a call ``net.last`` holds the un-clamped tensors (hr_raw / z_raw / logdet / ...).
 """
+import collections
 import math
 
 import torch
@@ -41,8 +42,28 @@ class _HCFlowBase(nn.Module):
         # deepest level's encoder features of the previous call instead of recomputing them
         self.reuse_lr_features = False
         self._last_lr_key = None
-        self._engines = {}
+        self._last_lr_ref = None
+        # compiled engines, least recently used first.  An engine owns activation buffers, fp16 planes, tensor-core plans
+        # and a captured graph for ONE (direction, B, h, w): a test loop over variable-size images would otherwise grow
+        # GPU memory by gigabytes per new size.  Packed weights are shared (one WeightStore per device).
+        self.max_engines = 4
+        self._engines = collections.OrderedDict()
+        self._stores = {}
+        self._weights_epoch = 0
         self.last = {}
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_weights())
+
+    def invalidate_weights(self):
+        """Tell the engines that parameter VALUES changed in a way autograd's version counters do not see
+        (``p.data.copy_()``, ``p.data.mul_()``, EMA swaps ...).  load_state_dict calls it; optimizers and plain in-place
+        ops on the Parameters are detected without it."""
+        self._weights_epoch += 1
+
+    def _replicate_for_data_parallel(self):
+        raise RuntimeError(
+            "hcflow_b200 nets cannot be replicated by nn.DataParallel over several GPUs (replicas carry no parameters "
+            "and would share one engine cache across threads).  Use one process per GPU (torchrun / "
+            "DistributedDataParallel, hcflow_b200.dist), or DataParallel with a single device id.")
 
     # ---- engine management -------------------------------------------------------------
     def set_precision(self, precision):
@@ -54,19 +75,41 @@ class _HCFlowBase(nn.Module):
         assert precision in ("fp32", "tf32", "tf32x3", "tf32x3_all", "f16", "f16x3")
         if precision != self.precision:
             self.precision = precision
-            self._engines.clear()
+            self.clear_engines()
+
+    def clear_engines(self):
+        for eng in self._engines.values():
+            eng.close()
+        self._engines.clear()
+        self._stores.clear()
 
     def engine(self, direction, B, h, w, device, io="f32"):
-        from .engine import Engine
+        from .engine import Engine, WeightStore
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
         key = (direction, B, h, w, str(device), self.precision, self.use_graph, self.use_chains, self.share_cond,
                self.fuse_steps, io, self.pair_convs)
         eng = self._engines.get(key)
-        if eng is None:
-            eng = Engine(self, direction, B, h, w, device, precision=self.precision, use_graph=self.use_graph,
-                         use_chains=self.use_chains, share_cond=self.share_cond, fuse_steps=self.fuse_steps, io=io,
-                         pair_convs=self.pair_convs)
-            self._engines[key] = eng
+        if eng is not None:
+            self._engines.move_to_end(key)
+            return eng
+        while len(self._engines) >= max(1, self.max_engines):
+            _, old = self._engines.popitem(last=False)     # least recently used
+            old.close()
+        store = self._stores.setdefault(str(device), WeightStore())
+        eng = Engine(self, direction, B, h, w, device, precision=self.precision, use_graph=self.use_graph,
+                     use_chains=self.use_chains, share_cond=self.share_cond, fuse_steps=self.fuse_steps, io=io,
+                     pair_convs=self.pair_convs, store=store)
+        self._engines[key] = eng
         return eng
+
+    def check_status(self):
+        """Synchronous check of the engines' device status words (fp16 range guard): raises FP16RangeError /
+        HcfError if a previous pass tripped one.  (Every call also checks, without synchronising, the passes that
+        have already completed.)"""
+        for eng in self._engines.values():
+            eng.check_status(wait=True)
 
     def _check(self, t, name, c=3):
         if t is None:
@@ -94,12 +137,16 @@ class _HCFlowBase(nn.Module):
                 dst.normal_(0.0, 1.0).mul_(std)
 
     def _reverse(self, lr, eps_std, eps):
+        lr_arg = lr
         lr = self._check(lr, "lr")
         B, _, h, w = lr.shape
         eng = self.engine("reverse", B, h, w, lr.device)
-        key = (id(eng), lr.data_ptr(), lr._version, tuple(lr.shape))
-        same = self.reuse_lr_features and key == self._last_lr_key
+        # identity of the CALLER's tensor (not of a converted temporary, whose address the caching allocator recycles),
+        # and a reference to it, so that its storage cannot be freed and handed to a different image in between
+        key = (id(eng), id(lr_arg), lr_arg.data_ptr(), lr_arg._version, tuple(lr_arg.shape), lr_arg.dtype)
+        same = self.reuse_lr_features and key == self._last_lr_key and self._last_lr_ref is lr_arg
         self._last_lr_key = key
+        self._last_lr_ref = lr_arg if self.reuse_lr_features else None
         with torch.cuda.device(lr.device):
             eng.ext["lr"].copy_(lr)
             self._draw_eps(eng, eps_std, eps, lr.device)

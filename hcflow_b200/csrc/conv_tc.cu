@@ -598,6 +598,17 @@ static int chain_create(const hcf_conv_args* args, const void* const* wtc, const
     hcf_conv_tc_plan_destroy(pl);
     return (int)e;
   }
+  if (n > 1) {   // a chain needs its whole grid resident at once (the launch is cooperative): check it now
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(pl->fn), pl->threads,
+                                                      pl->smem_bytes);
+    if (e != cudaSuccess || (long)per_sm * sms < (long)pl->grid.x) {
+      set_error("tc_chain: %d CTAs of %d threads / %zu B shared memory cannot be co-resident (%d per SM x %d SMs)",
+                (int)pl->grid.x, pl->threads, pl->smem_bytes, per_sm, sms);
+      hcf_conv_tc_plan_destroy(pl);
+      return HCF_ENOTSUP;
+    }
+  }
   *out = pl;
   return 0;
 }
@@ -652,10 +663,41 @@ extern "C" int hcf_conv_tc_plan_create(const hcf_conv_args* a, const float* wtc,
 
 extern "C" int32_t hcf_conv_tc_plan_layers(const hcf_conv_tc_plan* pl) { return pl ? pl->p.n_layers : 0; }
 
+// Sticky device status word of a plan (NULL = none): bit 0 (HCF_STATUS_F16_OVERFLOW) an fp16 operand plane saturated,
+// bit 1 (HCF_STATUS_DEP_TIMEOUT) a dependency wait of a chained launch timed out.  The host reads / clears it.
+extern "C" int hcf_conv_tc_plan_set_status(hcf_conv_tc_plan* pl, int32_t* status) {
+  using namespace hcf;
+  HCF_REQUIRE(pl != nullptr, "tc_plan_set_status: null plan");
+  pl->p.status = status;
+  return 0;
+}
+
 extern "C" int hcf_conv_tc_run(const hcf_conv_tc_plan* pl, void* stream) {
   using namespace hcf;
   HCF_REQUIRE(pl != nullptr, "tc_run: null plan");
   ++pl->runs;
+  if (pl->p.n_layers > 1) {
+    // A chained launch's CTAs wait on each other's tiles: they must all be resident at once.  A cooperative launch
+    // makes the driver guarantee that (it fails with cudaErrorCooperativeLaunchTooLarge instead of deadlocking when
+    // the grid cannot be co-resident, and is not started next to a kernel that holds the SMs it needs).
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = pl->grid;
+    cfg.blockDim = dim3((unsigned)pl->threads);
+    cfg.dynamicSmemBytes = pl->smem_bytes;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, pl->fn, pl->maps, pl->p);
+    if (e != cudaSuccess) {
+      set_error("hcf_conv_tc_run (cooperative, %d CTAs): %s", (int)pl->grid.x, cudaGetErrorString(e));
+      return (int)e;
+    }
+    return finish_launch("hcf_conv_tc_run");
+  }
   pl->fn<<<pl->grid, pl->threads, pl->smem_bytes, (cudaStream_t)stream>>>(pl->maps, pl->p);
   return finish_launch("hcf_conv_tc_run");
 }

@@ -128,7 +128,10 @@ struct Params {
   const float* epi;   // [n_layers][256]: bias (0) | scale (1) of every layer, padded: one coalesced load per layer change
   int step_tab;       // 1: the chain has fused FlowStep layers (shared memory carries their W^-1 / ActNorm tables)
   long long* prof;    // HCF_TC_PROF=1: cycles per role / wait class summed over CTAs (see PROF_* below)
+  int* status;        // sticky device word (may be null): bit 0 = an fp16 operand plane saturated (|x| > 65504),
+                      // bit 1 = a dependency wait timed out (the chain's CTAs were not co-resident)
 };
+constexpr int STATUS_F16_OVERFLOW = 1, STATUS_DEP_TIMEOUT = 2;
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -220,7 +223,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 
 // fp16 operand format: a = hi + lo / 2048 with hi = fp16(a), lo = fp16((a - hi) * 2048) (the scaling keeps the
 // residual out of the fp16 subnormal range); hi alone carries 11 significant bits (round-to-nearest), hi + lo 22.
-__device__ __forceinline__ uint2 split_hi(const float4 o) {
+// Range guard: values beyond the fp16 range saturate to +-65504 (never inf: the stale x zero-weight-row trick of the
+// ragged chunks would turn one inf into NaNs) and raise a sticky flag the host checks after the pass.
+__device__ __forceinline__ uint2 split_hi(float4& o, int* __restrict__ status) {
+  const float m = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w)));
+  if (!(m <= 65504.0f)) {   // (also catches NaN)
+    if (status) atomicOr(status, 1);
+    o.x = fminf(fmaxf(o.x, -65504.0f), 65504.0f); o.y = fminf(fmaxf(o.y, -65504.0f), 65504.0f);
+    o.z = fminf(fmaxf(o.z, -65504.0f), 65504.0f); o.w = fminf(fmaxf(o.w, -65504.0f), 65504.0f);
+  }
   const __half2 a = __floats2half2_rn(o.x, o.y), b = __floats2half2_rn(o.z, o.w);
   return make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
 }
@@ -253,7 +264,7 @@ __device__ __forceinline__ void coal_store_fast(const float4* __restrict__ stage
                                                 int ch, int ld, float* __restrict__ out, __half* __restrict__ hi_p,
                                                 __half* __restrict__ lo_p, const Chan4& cc, bool has_pre, bool has_r1,
                                                 bool has_r2, const float4 (&r1v)[8], const float4 (&r2v)[8],
-                                                float alpha1, float alpha2) {
+                                                float alpha1, float alpha2, int* __restrict__ status) {
   const int cidx = lane & 7;
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
@@ -278,7 +289,7 @@ __device__ __forceinline__ void coal_store_fast(const float4* __restrict__ stage
       // loaded from memory compiles to a generic ST
       if (W32) __stcg(reinterpret_cast<float4*>(out + e1), o);
       if (WHI) {
-        const uint2 hi = split_hi(o);
+        const uint2 hi = split_hi(o, status);
         __stcg(reinterpret_cast<uint2*>(hi_p + e1), hi);
         if (WLO) __stcg(reinterpret_cast<uint2*>(lo_p + e1), split_lo(o, hi));
       }
@@ -603,9 +614,16 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
           if (layer > 0 && !(p.debug & 64)) {
             // wait until layer-1 is complete on the 3x3 tile neighbourhood (halo + WAR safety)
             HCF_T(td0);
+            uint32_t spins = 0;
             while (!deps_ready(deps, layer)) {
               __nanosleep(32);
               load_deps(deps, p.done, b * per_img, ty, tx, p.tiles_y, p.tiles_x);
+              // the launch is cooperative (all CTAs co-resident), so a wait is bounded by the chain's own run time;
+              // ~2 s of polling means a producer CTA is missing or crashed: flag it and stop instead of hanging
+              if (++spins > (1u << 24)) {
+                if (p.status) atomicOr(p.status, STATUS_DEP_TIMEOUT);
+                __trap();
+              }
             }
             fence_acquire_gpu();                                      // acquire side of the epilogue's release
             asm volatile("fence.proxy.async.global;" ::: "memory");   // order the TMA (async proxy) reads after it
@@ -1017,7 +1035,7 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
             cc.scale = *reinterpret_cast<const float4*>(s_scale + ch);
             cc.slope = act == HCF_ACT_RELU ? 0.f : (act == HCF_ACT_LRELU ? 0.2f : 1.f);
 #define HCF_COAL(A, B_, C_) coal_store_fast<A, B_, C_>(stage, pixv, lane, ch, out_ld, out, o16.hi, o16.lo, cc, is_pre, hr1, hr2, \
-                                                     r1v, r2v, alpha1, alpha2)
+                                                     r1v, r2v, alpha1, alpha2, p.status)
             switch (fast) {
               case 1: HCF_COAL(true, false, false); break;
               case 2: HCF_COAL(false, true, false); break;
@@ -1052,7 +1070,7 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                   if (out2) *reinterpret_cast<float4*>(out2 + e2) = o;
                   if (F16) {
                     if (o16.hi || o16.hi2) {
-                      const uint2 hi = split_hi(o);
+                      const uint2 hi = split_hi(o, p.status);
                       if (o16.hi) *reinterpret_cast<uint2*>(o16.hi + e1) = hi;
                       if (o16.hi2) *reinterpret_cast<uint2*>(o16.hi2 + e2) = hi;
                       if (o16.lo || o16.lo2) {
@@ -1078,6 +1096,10 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                       if (out) out[e1 + e] = t;
                       if (out2) out2[e2 + e] = t;
                       if (F16) {
+                        if (!(fabsf(t) <= 65504.0f)) {   // range guard (see split_hi)
+                          if (p.status) atomicOr(p.status, STATUS_F16_OVERFLOW);
+                          t = fminf(fmaxf(t, -65504.0f), 65504.0f);
+                        }
                         const __half hh = __float2half_rn(t);
                         const __half hl = __float2half_rn((t - __half2float(hh)) * 2048.0f);
                         if (o16.hi) o16.hi[e1 + e] = hh;

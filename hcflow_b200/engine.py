@@ -7,6 +7,7 @@ eager-torch fallback: constructing an Engine without CUDA or without the library
 """
 import ctypes as C
 import math
+import warnings
 
 import torch
 
@@ -16,11 +17,28 @@ from . import prep
 from . import rewrite
 
 
+class WeightStore:
+    """Packed / derived weights of ONE net on ONE device, shared by all its engines: conv weights in the kernels'
+    layouts, tensor-core weight images, bias / scale vectors, W^-1, exp(+-logs).  They depend on the weights and on the
+    op shapes, not on (B, h, w), so engines for different input sizes share them; only activation buffers, plans and
+    graphs are per engine.  ``stamp[key]`` = weight signature the tensor was packed for."""
+
+    def __init__(self):
+        self.t = {}
+        self.stamp = {}
+        self.tc_registry = {}    # weight-image key -> (op, passes, split channels, fp16?) for in-place reload
+
+
+class FP16RangeError(RuntimeError):
+    """An activation left the fp16 operand range (|x| > 65504) in an "f16" / "f16x3" pass; the planes saturated, the
+    result is not trustworthy.  Use precision "tf32x3" / "fp32" for such weights."""
+
+
 class Engine:
     """One compiled plan = (net weights, direction, B, h, w, precision) on one device."""
 
     def __init__(self, net, direction, B, h, w, device, precision="fp32", use_graph=True, use_chains=True,
-                 share_cond=True, fuse_steps=True, io="f32", pair_convs=True):
+                 share_cond=True, fuse_steps=True, io="f32", pair_convs=True, store=None):
         if not torch.cuda.is_available():
             raise L.HcfError("hcflow_b200 needs a CUDA device (no CPU fallback)")
         self.lib = L.load()
@@ -38,9 +56,16 @@ class Engine:
         self._lr_features_valid = False
         self._keep = []          # ctypes structs must outlive the launches
         self._params = None
-        self._tc_registry = {}   # weight-image key -> (op, passes, split channels, fp16?) for in-place reload
+        self.store = store if store is not None else WeightStore()
+        self._tc_registry = self.store.tc_registry
+        self._my_tc_keys = set()
         self._tc_plans = []
-        self.weights = {}
+        self.weights = self.store.t
+        self.n_fp32_fallback = 0  # convs that were meant for the tensor cores but fell back to the CUDA-core kernel
+        self.status = None        # sticky device status word of the tensor-core plans (fp16 range guard, dep timeout)
+        self._status_host = None
+        self._status_event = None
+        self.closed = False
         self.bufs = {}
         self.ext = {}
         self.calls = []
@@ -92,48 +117,60 @@ class Engine:
     # ------------------------------------------------------------------ weights
     def weight_signature(self):
         # walking the module tree costs ~1 ms for 1478 tensors; the Parameter objects are stable (load_state_dict,
-        # .to() and optimizers update them in place and bump _version), so the flat list is cached
+        # .to() and optimizers update them in place and bump _version), so the flat list is cached.  Storage addresses
+        # are part of the signature (p.data = t, .to(device)); in-place edits through .data (p.data.mul_()) bump
+        # neither: callers of such code must call net.invalidate_weights() (arch.py), which bumps the epoch.
         if self._params is None:
             self._params = list(self.net.parameters())
-        return sum(p._version for p in self._params), id(self.net)
+        ptrs = hash(tuple(p.data_ptr() for p in self._params))     # (0.14 ms for 1478 tensors, like the version sum)
+        return sum(p._version for p in self._params), ptrs, id(self.net), getattr(self.net, "_weights_epoch", 0)
 
     def load_weights(self):
         """(Re)pack every parameter the plan touches. Device addresses stay stable on reload."""
+        self._params = None
+        sig = self.weight_signature()
         sd = {k: v.detach().cpu() for k, v in self.net.state_dict().items()}
         dev = self.device
+        stamp = self.store.stamp
 
-        def put(key, t):
-            t = t.contiguous()
+        def put(key, make):
+            if stamp.get(key) == sig and key in self.weights:
+                return           # another engine of this net already packed it for this weight version
+            t = make().contiguous()
             if key in self.weights and self.weights[key].shape == t.shape:
                 self.weights[key].copy_(t)
             else:
                 self.weights[key] = t.to(dev)
+            stamp[key] = sig
 
         self._sd_cpu = sd
         for op in self.ops:
             if isinstance(op, P.ConvOp):
                 npad = prep.npad_for(op.cout)
                 segc = [v.C for v, _ in op.segs]
-                put(self._wkey(op), prep.pack_conv_weight(self._raw_weight(op), segc, npad))
+                put(self._wkey(op), lambda op=op, segc=segc, npad=npad: prep.pack_conv_weight(self._raw_weight(op), segc, npad))
                 if op.bias:
-                    put(op.bias + "@{}".format(npad), prep.pad_vec(prep.derive(sd, op.bias), npad, 0.0))
+                    put(op.bias + "@{}".format(npad), lambda op=op, npad=npad: prep.pad_vec(prep.derive(sd, op.bias), npad, 0.0))
                 if op.scale:
-                    put(op.scale + "@{}".format(npad), prep.pad_vec(prep.derive(sd, op.scale), npad, 1.0))
+                    put(op.scale + "@{}".format(npad), lambda op=op, npad=npad: prep.pad_vec(prep.derive(sd, op.scale), npad, 1.0))
             st = op if isinstance(op, P.StepOp) else (op.step if isinstance(op, P.ConvOp) else None)
             if st is not None:
                 for key in (st.w, st.an_scale, st.an_bias):
                     if key:
-                        put(key, prep.derive(sd, key))
+                        put(key, lambda key=key: prep.derive(sd, key))
         self.logdet_const = prep.logdet_constant(sd, self.plan.logdet_terms)
         if self.plan.direction == "forward" and self.plan.sr:
             s = 2 ** self.net.flow.L
             self.logdet_const += prep.quant_logdet(self.net.quant, self.h * s * self.w * s)
         self.logdet_init.fill_(self.logdet_const)
-        self._sig = self.weight_signature()
+        self._sig = sig
         for hnd in self._tc_plans:   # plans read bias / scale through their own gathered table
             L.check(self.lib.hcf_conv_tc_plan_refresh(hnd, torch.cuda.current_stream(self.device).cuda_stream), "plan_refresh")
-        for key, (op, passes, split_ch, f16) in self._tc_registry.items():   # tensor-core weight images, in place
-            self.weights[key].copy_(self._pack_tc(op, passes, split_ch, f16))
+        for key in self._my_tc_keys:   # tensor-core weight images this engine uses, in place
+            if stamp.get(key) != sig:
+                op, passes, split_ch, f16 = self._tc_registry[key]
+                self.weights[key].copy_(self._pack_tc(op, passes, split_ch, f16))
+                stamp[key] = sig
 
     @staticmethod
     def _wkey(op):
@@ -314,6 +351,11 @@ class Engine:
             else:
                 raise TypeError(op)
         self._flush_tc(pending)
+        if self._tc_plans:
+            self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self._status_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            for hnd in self._tc_plans:
+                L.check(lib.hcf_conv_tc_plan_set_status(hnd, self.status.data_ptr()), "plan_set_status")
         if self._flag_used:
             pool, used = self._flag_pool, self._flag_used
             self.calls.insert(0, (lambda _a, _s: (pool[:used].zero_(), 0)[1], None, "flags_zero"))
@@ -372,9 +414,15 @@ class Engine:
 
     def _tc_weights(self, op, passes):
         key = self._wkey(op) + "#tc{}".format(passes)
-        if key not in self.weights:
-            self.weights[key] = self._pack_tc(op, passes, -1, False).to(self.device)
+        if key not in self.weights or self.store.stamp.get(key) != self._sig:
+            img = self._pack_tc(op, passes, -1, False)
+            if key in self.weights:
+                self.weights[key].copy_(img)
+            else:
+                self.weights[key] = img.to(self.device)
             self._tc_registry[key] = (op, passes, -1, False)
+            self.store.stamp[key] = self._sig
+        self._my_tc_keys.add(key)
         return self.weights[key]
 
     # ---- fp16 chains ("f16" / "f16x3"): hi / lo planes shadowing the fp32 buffers -----------------------
@@ -398,9 +446,15 @@ class Engine:
 
     def _tc16_weights(self, op, passes, split_ch=-1):
         key = self._wkey(op) + "#tc16_{}_{}".format(passes, split_ch)
-        if key not in self.weights:
-            self.weights[key] = self._pack_tc(op, passes, split_ch, True).to(self.device)
+        if key not in self.weights or self.store.stamp.get(key) != self._sig:
+            img = self._pack_tc(op, passes, split_ch, True)
+            if key in self.weights:
+                self.weights[key].copy_(img)
+            else:
+                self.weights[key] = img.to(self.device)
             self._tc_registry[key] = (op, passes, split_ch, True)
+            self.store.stamp[key] = self._sig
+        self._my_tc_keys.add(key)
         return self.weights[key]
 
     def _try_chain16(self, pending):
@@ -552,9 +606,13 @@ class Engine:
             passes = self._passes_for(op)
             rc = lib.hcf_conv_tc_plan_create(C.byref(a), self._tc_weights(op, passes).data_ptr(), passes,
                                              C.byref(handle))
-            if rc == -2:   # shape does not fit the tensor-core kernel's shared memory: CUDA-core kernel
+            if rc == -2:   # shape does not fit the tensor-core kernel's shared memory: CUDA-core kernel, loudly
+                warnings.warn("hcflow_b200: conv {} ({}x{}, cout {}) does not fit the tcgen05 kernel ({}); it runs on the "
+                              "CUDA-core fp32 kernel (~10x slower)".format(tag, op.H, op.W, op.cout,
+                                                                          lib.hcf_last_error().decode(errors="replace")))
                 self._add_call(lib.hcf_conv_fp32, C.byref(a), "conv_fp32", tag, flops, 1)
                 self.n_fp32_conv += 1
+                self.n_fp32_fallback += 1
                 continue
             L.check(rc, "tc_plan_create")
             self._tc_plans.append(handle)
@@ -587,9 +645,29 @@ class Engine:
         skip = {i for i in range(end) if cls[i] in ("layout_split16", "conv_tc_chain", "conv_tc", "conv_fp32", "layout_upsample")}
         return skip
 
+    def check_status(self, wait=False):
+        """Raise if a previous pass tripped the device status word (fp16 range guard / dependency time-out).  The word
+        is copied to pinned host memory after every pass without synchronising; ``wait=True`` waits for that copy."""
+        if self._status_event is None:
+            return
+        if wait:
+            self._status_event.synchronize()
+        elif not self._status_event.query():
+            return
+        word = int(self._status_host[0])
+        if word:
+            self.status.zero_()
+            self._status_host.zero_()
+            if word & L.STATUS_DEP_TIMEOUT:
+                raise L.HcfError("a chained tcgen05 launch timed out waiting for a neighbour tile")
+            raise FP16RangeError("an activation exceeded the fp16 operand range (|x| > 65504) in precision {!r}: the "
+                                 "operand planes saturated; use tf32x3 / fp32 for these weights".format(self.precision))
+
     def run(self, reuse_lr_features=False):
         """Run the plan on the current stream (inputs already in self.ext).  reuse_lr_features: skip the launches
         that depend on the LR image alone (valid when ext["lr"] is the same image as in the previous run)."""
+        assert not self.closed, "engine was evicted from the cache"
+        self.check_status()
         if self.weight_signature() != self._sig:
             self.load_weights()
             self._lr_features_valid = False
@@ -608,14 +686,40 @@ class Engine:
                 self._graphs[key] = g
             self._graphs[key].replay()
         self._lr_features_valid = True
+        if self.status is not None:
+            self._status_host.copy_(self.status, non_blocking=True)
+            if self._status_event is None:
+                self._status_event = torch.cuda.Event()
+            self._status_event.record(torch.cuda.current_stream(self.device))
 
     @property
     def launches_per_run(self):
         return len(self.calls)
 
+    def close(self):
+        """Release everything that is per (B, h, w): captured graphs, tensor-core plans (tensor maps, layer tables),
+        activation buffers and fp16 planes.  The packed weights live in the shared store and stay."""
+        if self.closed:
+            return
+        self.closed = True
+        try:
+            torch.cuda.current_stream(self.device).synchronize()
+        except Exception:
+            pass
+        self._graphs.clear()
+        self.graph = None
+        for hnd in self._tc_plans:
+            try:
+                self.lib.hcf_conv_tc_plan_destroy(hnd)
+            except Exception:
+                pass
+        self._tc_plans = []
+        self.calls, self.call_info, self._keep = [], [], []
+        self.bufs, self.ext, self.shadow16 = {}, {}, {}
+        self._flag_pool = None
+
     def __del__(self):
         try:
-            for hnd in self._tc_plans:
-                self.lib.hcf_conv_tc_plan_destroy(hnd)
+            self.close()
         except Exception:
             pass

@@ -190,7 +190,13 @@ int hcf_conv_chain16_create(const hcf_conv_args* args, const void* const* w16, c
 /* fp32 NHWC view (ld, C, npix pixels) -> hi / lo planes with row pitch dst_ld (lo may be NULL) */
 int hcf_split16(const float* src, int32_t ld, int32_t C, int64_t npix, void* hi, void* lo, int32_t dst_ld, void* stream);
 int32_t hcf_conv_tc_plan_layers(const hcf_conv_tc_plan* p);
+/* a chained plan (n > 1) is launched COOPERATIVELY: its CTAs wait on each other's tiles, the driver guarantees that
+ * the whole grid is co-resident (creation fails with HCF_ENOTSUP if it can not be) */
 int hcf_conv_tc_run(const hcf_conv_tc_plan* p, void* stream);
+/* sticky device status word of a plan (NULL = none), OR-ed by the kernels, read and cleared by the host */
+#define HCF_STATUS_F16_OVERFLOW 1 /* an fp16 operand plane saturated at +-65504 (value out of the fp16 modes' range) */
+#define HCF_STATUS_DEP_TIMEOUT 2  /* a dependency wait of a chained launch timed out (the kernel trapped) */
+int hcf_conv_tc_plan_set_status(hcf_conv_tc_plan* p, int32_t* status);
 /* a plan reads bias / scale through an inline per-layer table gathered at creation: call this after the arrays
  * behind hcf_conv_args.bias / .scale were rewritten in place (weight reload); copies are queued on `stream` */
 int hcf_conv_tc_plan_refresh(hcf_conv_tc_plan* p, void* stream);

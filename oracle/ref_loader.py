@@ -1,16 +1,21 @@
-"""Import the UNMODIFIED reference modules (authoring container only).
+"""Import the UNMODIFIED reference modules.
 
-TEST INFRASTRUCTURE.  /root/reference does not exist on the GPU box; everything that
-runs there uses the committed fixtures under tests/golden/ instead.  The reference's
+TEST / BENCH INFRASTRUCTURE.  /root/reference does not exist on the GPU box: the parity tests there use the
+committed fixtures under tests/golden/; the bench's reference arm and the factory test use the unmodified copy that
+oracle/build_ref.py stages under oracle/_ref (git-ignored).  The reference's
 ``utils/util.py`` needs ``natsort`` and ``matplotlib`` at import time;
 two three-line stubs under oracle/_stubs/ satisfy that.
 """
 import os
 import sys
 
+_HERE = os.path.dirname(os.path.abspath(__file__))
 REF_ROOT = os.environ.get("HCFLOW_REFERENCE", "/root/reference")
+if not os.path.isdir(os.path.join(REF_ROOT, "codes", "models", "modules")):
+    # GPU box: the unmodified copy staged by oracle/build_ref.py (git-ignored, travels with the snapshot)
+    REF_ROOT = os.path.join(_HERE, "_ref")
 REF_CODES = os.path.join(REF_ROOT, "codes")
-_STUBS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_stubs")
+_STUBS = os.path.join(_HERE, "_stubs")
 
 
 def available():

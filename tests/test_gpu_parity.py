@@ -130,6 +130,7 @@ def test_step_kernels_match_oracle(cfg, pre, cond, report):
 
 # ------------------------------------------------------------------------------ end to end vs goldens
 def _net_cuda(cfg, precision="fp32"):
+    """cfg: a bundled config or a stress fixture name (tests/helpers.net_and_weights)"""
     opt, net_cpu, sd = net_and_weights(cfg)
     net = build_net(opt)
     net.load_state_dict(sd, strict=True)
@@ -175,7 +176,7 @@ def test_sr_forward_matches_reference_golden(cfg, report):
     # the quantised fake LR may flip one 1/255 step where z sits within rounding distance of a boundary
     flips = int(((fake_lr.cpu() - g["fwd_fake_lr"]).abs() > 1e-6).sum())
     # log-det alone: subtract the dirac term computed by the oracle on OUR fake_lr
-    dirac = orc.gaussian_logp(lr, -torch.ones_like(lr) * 6, fake_lr.cpu()).double()
+    dirac = orc.gaussian_logp(lr.double(), -torch.ones_like(lr).double() * 6, fake_lr.cpu().double())
     ld = net.last["objective"].cpu() - dirac
     e_ld = float(((ld - g["fwd_logdet"].double()).abs() / g["fwd_logdet"].double().abs()).max())
     report["e2e_forward/" + cfg] = {"z": e_z, "nll_rel": e_nll, "logdet_rel": e_ld, "quant_flips": flips}
@@ -311,7 +312,9 @@ def test_conv_tcgen05_matches_fp64(case, precision, report):
 # "f16" / "f16x3": the chained encoder convs on FP16 operands (round-to-nearest 11-bit operands instead of TF32's
 # truncated 10+1 bits; the split layers of f16x3 carry hi + lo = 22 bits).  CPU emulation of the same operand
 # rounding (oracle + patched conv2d) gives 1.6e-3 / 1.3e-5 max-abs on sr_x4.
-E2E_TOL = {"tf32": 5e-2, "tf32x3": 2e-3, "tf32x3_all": 2e-3, "f16": 2e-2, "f16x3": 2e-3}
+# Tolerances are <= 3x the values measured on B200 (profiles/r02_parity_report.json).  The x3 modes (default f16x3)
+# carry the stated "fp32 tolerance" of this package: 2e-4 max-abs on the un-clamped HR, also on the stress fixtures.
+E2E_TOL = {"tf32": 4e-2, "tf32x3": 2e-4, "tf32x3_all": 2e-4, "f16": 6e-3, "f16x3": 1e-4}
 
 
 @pytest.mark.parametrize("precision", ["tf32", "tf32x3", "tf32x3_all", "f16", "f16x3"])
@@ -454,7 +457,8 @@ def test_conv_chain16_rdb_matches_fp64(shape, mode, passes, tol, report):
 @pytest.mark.parametrize("precision", ["f16", "f16x3"])
 def test_chain16_full_size_is_deterministic_and_close_to_fp32_path(precision, report):
     """Full BASELINE size (B=16, 40x40 -> 160x160): the fp16 chains (dependency counters across 148 CTAs) give the
-    same bits on every run and agree with the tf32x3 path within the mode's end-to-end tolerance."""
+    same bits on every run and agree with the tf32x3 path within the modes' end-to-end tolerances (both are compared with
+    the ORACLE at this size by test_config1_full_size_default_precision_vs_oracle)."""
     opt, net, sd = _net_cuda("sr_x4", "tf32x3")
     B = 16
     lr = synth.synthetic_lr(B, 40, 40, seed=5).cuda()
@@ -472,7 +476,7 @@ def test_chain16_full_size_is_deterministic_and_close_to_fp32_path(precision, re
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
     err = float((outs[0] - want).abs().max())
     report["chain16_full/{}".format(precision)] = {"max_vs_tf32x3": err, "chains16": eng.n_chains16}
-    assert err < E2E_TOL[precision], err
+    assert err < E2E_TOL[precision] + E2E_TOL["tf32x3"], err
 
 
 # ------------------------------------------------------------------------------ coupling sub-net as one chain
@@ -618,7 +622,7 @@ def test_engine_rewrites_agree_with_the_plain_plan(precision, report):
     report["rewrites/{}".format(precision)] = {"max": err, "launches_plain": e0.launches_per_run,
                                                "launches_rewritten": e1.launches_per_run}
     assert e1.launches_per_run < e0.launches_per_run // 3
-    assert err < 2e-3, err
+    assert err < 1e-4, err
 
 
 def test_prior_draw_consumes_the_reference_rng_stream():
@@ -634,7 +638,7 @@ def test_prior_draw_consumes_the_reference_rng_stream():
     assert torch.equal(got, want) and torch.equal(got2, want2)
 
 
-@pytest.mark.parametrize("precision,tol", [("f16x3", 2e-3), ("tf32x3", 2e-3), ("f16", 2e-2)])
+@pytest.mark.parametrize("precision,tol", [("f16x3", 1e-4), ("tf32x3", 2e-4), ("f16", 6e-3)])
 def test_ragged_size_against_oracle(precision, tol, report):
     """LR 12x20 (HR 48x80): every level has partial tiles in both directions (16x8 pixel tiles), B=3 is not a
     multiple of anything -- the chained launches, the fused FlowStep epilogue and the shared-conditioning addend
@@ -719,7 +723,7 @@ def test_weight_reload_refreshes_every_derived_array(precision):
 
 # forward (NLL) pass in the tensor-core modes: z within the modes' operand-rounding budget, log-det (fp64 accumulation
 # of per-pixel terms) to 1e-4 relative.  Measured values are written to the parity report.
-@pytest.mark.parametrize("precision,tol_z,tol_ld", [("f16x3", 2e-3, 1e-4), ("tf32x3", 2e-3, 1e-4), ("f16", 2e-2, 1e-3)])
+@pytest.mark.parametrize("precision,tol_z,tol_ld", [("f16x3", 1e-4, 2e-5), ("tf32x3", 1e-4, 1e-4), ("f16", 1e-4, 1e-3)])
 @pytest.mark.parametrize("cfg", ["sr_x4", "sr_x8"])
 def test_sr_forward_tensor_core_modes_match_reference_golden(cfg, precision, tol_z, tol_ld, report):
     g = load_golden(cfg)
@@ -729,7 +733,7 @@ def test_sr_forward_tensor_core_modes_match_reference_golden(cfg, precision, tol
     with torch.no_grad():
         fake_lr, nll = net(hr=hr.cuda(), lr=lr.cuda(), u=None, reverse=False, training=False, dequant_noise=dq)
     e_z = maxabs(net.last["z_raw"].cpu(), g["fwd_z"])
-    dirac = orc.gaussian_logp(lr, -torch.ones_like(lr) * 6, fake_lr.cpu()).double()
+    dirac = orc.gaussian_logp(lr.double(), -torch.ones_like(lr).double() * 6, fake_lr.cpu().double())
     ld = net.last["objective"].cpu() - dirac
     e_ld = float(((ld - g["fwd_logdet"].double()).abs() / g["fwd_logdet"].double().abs()).max())
     eng = [e for e in net._engines.values()][-1]
@@ -737,3 +741,254 @@ def test_sr_forward_tensor_core_modes_match_reference_golden(cfg, precision, tol
                                                          "fp32_convs": eng.n_fp32_conv}
     assert eng.n_tc > 0
     assert e_z < tol_z and e_ld < tol_ld, (e_z, e_ld)
+
+
+# ------------------------------------------------------------------------------ stress fixtures (O(1) couplings)
+STRESS_TOL = {"fp32": 2e-4, "f16x3": 2e-4, "tf32x3": 2e-4, "tf32x3_all": 2e-4, "f16": 5e-2, "tf32": 2e-1}
+
+
+@pytest.mark.parametrize("precision", ["fp32", "f16x3", "tf32x3", "tf32x3_all", "f16", "tf32"])
+@pytest.mark.parametrize("cfg", ["sr_x4_stress", "sr_x8_stress", "rescaling_x4_stress"])
+def test_stress_fixture_reverse_matches_reference_golden(cfg, precision, report):
+    """The regular fixtures keep every coupling within 2 % of the identity (|h|max 0.02), which hides operand
+    rounding of the coupling sub-nets.  The stress fixtures (UNMODIFIED reference on a shallow flow whose couplings
+    have |h| ~ 0.8 .. 0.9, oracle/make_golden.py) do not: the x3 modes must hold 2e-4 on the un-clamped HR here too."""
+    g = load_golden(cfg)
+    opt, net, sd = _net_cuda(cfg, precision)
+    lr, hr, unit, heat = _inputs(g, opt)
+    with torch.no_grad():
+        out = net(lr=lr.cuda(), eps_std=heat, reverse=True, eps=unit)
+    raw = net.last["hr_raw"].cpu()
+    e = maxabs(raw, g["inv_raw"])
+    report["stress_reverse_{}/{}".format(precision, cfg)] = {
+        "hr_raw_max": e, "hr_raw_mean": float((raw.double() - g["inv_raw"].double()).abs().mean()),
+        "h_absmax": g["h_absmax"], "range": [float(g["inv_raw"].min()), float(g["inv_raw"].max())]}
+    assert e < STRESS_TOL[precision], (cfg, precision, e)
+    assert maxabs(out.cpu(), g["inv_hr"]) < STRESS_TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "f16x3", "tf32x3"])
+@pytest.mark.parametrize("cfg", ["sr_x4_stress", "sr_x8_stress"])
+def test_stress_fixture_forward_matches_reference_golden(cfg, precision, report):
+    g = load_golden(cfg)
+    opt, net, sd = _net_cuda(cfg, precision)
+    lr, hr, unit, heat = _inputs(g, opt)
+    dq = torch.rand(hr.shape, generator=torch.Generator().manual_seed(77), dtype=torch.float32)
+    with torch.no_grad():
+        fake_lr, nll = net(hr=hr.cuda(), lr=lr.cuda(), u=None, reverse=False, training=False, dequant_noise=dq)
+    e_z = maxabs(net.last["z_raw"].cpu(), g["fwd_z"])
+    dirac = orc.gaussian_logp(lr.double(), -torch.ones_like(lr).double() * 6, fake_lr.cpu().double())
+    ld = net.last["objective"].cpu() - dirac
+    e_ld = float(((ld - g["fwd_logdet"].double()).abs() / g["fwd_logdet"].double().abs()).max())
+    report["stress_forward_{}/{}".format(precision, cfg)] = {"z": e_z, "logdet_rel": e_ld}
+    assert e_z < 2e-4 and e_ld < 2e-5, (e_z, e_ld)
+
+
+@pytest.mark.parametrize("precision", ["f16x3", "tf32x3", "f16"])
+def test_rescaling_forward_tensor_core_modes_match_reference_golden(precision, report):
+    """Rescaling encode (HR -> LR, z1, z2) in the tensor-core modes, regular and stress fixture."""
+    for cfg in ("rescaling_x4", "rescaling_x4_stress"):
+        g = load_golden(cfg)
+        opt, net, sd = _net_cuda(cfg, precision)
+        lr, hr, unit, heat = _inputs(g, opt)
+        with torch.no_grad():
+            flr, z1, z2 = net(hr=hr.cuda(), reverse=False, training=False)
+        e = [maxabs(net.last["z_raw"].cpu(), g["fwd_raw_lr"]), maxabs(z1.cpu(), g["fwd_z1"]), maxabs(z2.cpu(), g["fwd_z2"])]
+        eng = [e_ for e_ in net._engines.values()][-1]
+        report["e2e_forward_{}/{}".format(precision, cfg)] = {"raw_lr": e[0], "z1": e[1], "z2": e[2], "tc_convs": eng.n_tc}
+        assert eng.n_tc > 0
+        tol = 2e-2 if precision == "f16" else 2e-4
+        assert e[0] < tol and e[1] < 2.5 * tol and e[2] < 2.5 * tol, (cfg, precision, e)
+
+
+# ------------------------------------------------------------------------------ shift branch of AffineCoupling3shift
+def test_shift_first3_kernel_branch_matches_oracle(report):
+    """AffineCoupling3shift (AffineCouplings.py:130-133 forward, :153-155 reverse): the first 3 channels are shifted
+    by the sub-net of the other C - 3; no scale, no log-det.  hcf_step_inverse / hcf_step_forward_coupling in mode
+    HCF_COUPLING_SHIFT_FIRST3 against oracle.coupling, on the rescaling net's second FlowStep (k odd = shift step)."""
+    from tests import gpu_ops
+    opt, net, sd = net_and_weights("rescaling_x4")
+    layers, _ = orc.layer_list(opt, False)
+    idx = next(i for i, lay in enumerate(layers) if lay[0] == "step" and lay[1] == "shift_first3")
+    pre = "flow.layers.{}".format(idx)
+    n_pass = layers[idx][2]
+    Cc = n_pass + 3
+    B, H, W = 2, 6, 10
+    z = _rand(B, Cc, H, W, seed=51)
+    with torch.no_grad():
+        h = orc.dense_block(z[:, 3:], sd, pre + ".affine.f")
+        assert h.shape[1] == 3
+        want_r, _ = orc.coupling(z, None, sd, pre + ".affine", None, True, "shift_first3", n_pass)
+        want_f, ld = orc.coupling(z, None, sd, pre + ".affine", torch.zeros(B), False, "shift_first3", n_pass)
+        got_r = gpu_ops.step("inverse", z, h, "shift_first3", n_pass, None, torch.ones(Cc), torch.zeros(Cc), ld=Cc + 1)
+        logdet = torch.zeros(B, dtype=torch.float64, device="cuda")
+        got_f = gpu_ops.step("forward_coupling", z, h, "shift_first3", n_pass, None, None, None, logdet=logdet)
+    e_r, e_f = maxabs(got_r, want_r), maxabs(got_f, want_f)
+    report["step_shift_first3"] = {"inverse": e_r, "forward": e_f}
+    assert e_r < 1e-6 and e_f < 1e-6
+    assert float(logdet.abs().max()) == 0.0 and float(ld.abs().max()) == 0.0   # the shift adds no log-det
+    assert maxabs(got_r[:, 3:], z[:, 3:]) == 0.0                                # the conditioning channels pass through
+
+
+# ------------------------------------------------------------------------------ BASELINE configs at their own size
+def _img0_close(raw, want, tol, what):
+    e = maxabs(raw, want)
+    assert e < tol, (what, e)
+    return e
+
+
+def test_config1_full_size_default_precision_vs_oracle(report):
+    """configs[1]: 4x SR, B=16, 40x40 -> 160x160, T=0.8, DEFAULT precision: images 0 and 15 against the oracle run on
+    them alone (images are independent), the whole batch finite and clamped."""
+    opt, net, sd = _net_cuda("sr_x4", "f16x3")
+    B = 16
+    lr = synth.synthetic_lr(B, 40, 40, seed=5)
+    unit = synth.synthetic_noise(orc.noise_shapes(opt, B, 40, 40, True), seed=9)
+    with torch.no_grad():
+        hr = net(lr=lr.cuda(), eps_std=0.8, reverse=True, eps=unit)
+        raw = net.last["hr_raw"].cpu()
+        errs = []
+        for i in (0, 15):
+            _, want = orc.sr_reverse(lr[i:i + 1], sd, opt, [0.8 * e[i:i + 1] for e in unit])
+            errs.append(_img0_close(raw[i:i + 1], want, 1e-4, "configs[1] image {}".format(i)))
+    assert torch.isfinite(raw).all() and float(hr.min()) >= 0.0 and float(hr.max()) <= 1.0
+    report["config1_full_size_f16x3"] = {"img0": errs[0], "img15": errs[1]}
+
+
+def test_config2_x8_full_size_default_precision_vs_oracle(report):
+    """configs[2]: 8x SR, B=32, 20x20 LR <-> 160x160 HR, forward NLL + inverse, default precision; image 0 (inverse) and
+    image 0's z / objective (forward) against the oracle."""
+    opt, net, sd = _net_cuda("sr_x8", "f16x3")
+    B = 32
+    lr = synth.synthetic_lr(B, 20, 20, seed=6)
+    hr_in = synth.synthetic_hr(B, 160, 160, seed=6)
+    unit = synth.synthetic_noise(orc.noise_shapes(opt, B, 20, 20, True), seed=10)
+    dq = torch.rand(hr_in.shape, generator=torch.Generator().manual_seed(78), dtype=torch.float32)
+    with torch.no_grad():
+        net(lr=lr.cuda(), eps_std=0.8, reverse=True, eps=unit)
+        raw = net.last["hr_raw"].cpu()
+        _, want = orc.sr_reverse(lr[:1], sd, opt, [0.8 * e[:1] for e in unit])
+        e_inv = _img0_close(raw[:1], want, 1e-4, "configs[2] inverse image 0")
+        fake_lr, nll = net(hr=hr_in.cuda(), lr=lr.cuda(), reverse=False, dequant_noise=dq)
+        z = net.last["z_raw"].cpu()
+        obj = net.last["objective"].cpu()
+        _, _, z_w, ld_w = orc.sr_forward(hr_in[:1], lr[:1], sd, opt, dq[:1])
+    e_z = _img0_close(z[:1], z_w, 1e-4, "configs[2] forward z image 0")
+    dirac = orc.gaussian_logp(lr[:1].double(), -torch.ones_like(lr[:1]).double() * 6, fake_lr[:1].cpu().double())
+    e_ld = float(((obj[:1] - dirac - ld_w.double()).abs() / ld_w.double().abs()).max())
+    assert torch.isfinite(raw).all() and torch.isfinite(obj).all() and math.isfinite(float(nll))
+    assert e_ld < 2e-5, e_ld
+    report["config2_full_size_f16x3"] = {"inverse_img0": e_inv, "forward_z_img0": e_z, "logdet_rel_img0": e_ld}
+
+
+def test_config3_rescaling_full_size_default_precision_vs_oracle(report):
+    """configs[3]: 4x rescaling round trip, B=64, 256x256 HR tiles, default precision: encode (image 0's LR / z against
+    the oracle), quantise, decode with T=1.0 (image 0 against the oracle on the same quantised LR)."""
+    opt, net, sd = _net_cuda("rescaling_x4", "f16x3")
+    B = 64
+    hr_in = synth.synthetic_hr(B, 256, 256, seed=7)
+    unit = synth.synthetic_noise(orc.noise_shapes(opt, B, 64, 64, False), seed=11)
+    with torch.no_grad():
+        flr, z1, z2 = net(hr=hr_in.cuda(), reverse=False)
+        raw_lr = net.last["z_raw"].cpu()
+        lr_q = orc.quantize(flr.cpu())        # Quantization layer of the round trip (HCFlow_Rescaling_model.py)
+        out = net(lr=lr_q.cuda(), eps_std=1.0, reverse=True, eps=unit)
+        raw = net.last["hr_raw"].cpu()
+        _, z1_w, z2_w, rawlr_w = orc.rescaling_forward(hr_in[:1], sd, opt)
+        _, want = orc.rescaling_reverse(lr_q[:1], sd, opt, [e[:1] for e in unit])
+    e = [_img0_close(raw_lr[:1], rawlr_w, 1e-4, "configs[3] encode LR image 0"),
+         _img0_close(z1[:1].cpu(), z1_w, 2.5e-4, "configs[3] z1"), _img0_close(z2[:1].cpu(), z2_w, 2.5e-4, "configs[3] z2"),
+         _img0_close(raw[:1], want, 1e-4, "configs[3] decode image 0")]
+    assert torch.isfinite(raw).all() and float(out.min()) >= 0.0 and float(out.max()) <= 1.0
+    report["config3_full_size_f16x3"] = {"encode_lr": e[0], "z1": e[1], "z2": e[2], "decode": e[3]}
+
+
+# ------------------------------------------------------------------------------ robustness of the host side
+def test_engine_cache_is_bounded_and_weights_are_shared(report):
+    """A loop over variable-size images (the reference's full-image evaluation) must not grow GPU memory without
+    bound: engines are evicted least-recently-used (their plans / graphs / buffers destroyed) and all engines of a net
+    share ONE set of packed weights."""
+    opt, net, sd = _net_cuda("sr_x4", "f16x3")
+    net.max_engines = 2
+    outs = {}
+    with torch.no_grad():
+        for hw in (8, 12, 16, 8):
+            lr = synth.synthetic_lr(1, hw, hw, seed=hw).cuda()
+            outs.setdefault(hw, []).append(net(lr=lr, eps_std=0.0, reverse=True).clone())
+            assert len(net._engines) <= 2
+    assert torch.equal(outs[8][0], outs[8][1])            # rebuilt after eviction: same bits
+    engs = list(net._engines.values())
+    assert len(engs) == 2 and engs[0].weights is engs[1].weights and len(net._stores) == 1
+    n_weight_bytes = sum(t.numel() * t.element_size() for t in engs[0].weights.values())
+    report["engine_cache"] = {"engines": len(engs), "shared_weight_mb": n_weight_bytes / 1e6}
+
+
+def test_data_edits_need_invalidate_and_are_then_picked_up():
+    """p.data.mul_() bumps neither the version counter nor the address: the documented contract is
+    net.invalidate_weights(); load_state_dict calls it through a post hook."""
+    opt, net, sd = _net_cuda("sr_x4", "f16x3")
+    lr = synth.synthetic_lr(1, 8, 8, seed=2).cuda()
+    with torch.no_grad():
+        a = net(lr=lr, eps_std=0.0, reverse=True).clone()
+        p = dict(net.named_parameters())["flow.level1_condFlow.conv_first.weight"]
+        p.data.mul_(1.5)
+        net.invalidate_weights()
+        b = net(lr=lr, eps_std=0.0, reverse=True).clone()
+        e0 = net._weights_epoch
+        net.load_state_dict(sd, strict=True)
+        assert net._weights_epoch == e0 + 1
+        c = net(lr=lr, eps_std=0.0, reverse=True).clone()
+    assert not torch.equal(a, b) and torch.equal(a, c)
+
+
+def test_fp16_range_guard_raises_instead_of_returning_nans():
+    """Activations beyond the fp16 range saturate the operand planes and trip a sticky device flag: the default mode
+    reports it (FP16RangeError) instead of silently producing inf / NaN; tf32x3 has no such limit."""
+    from hcflow_b200.engine import FP16RangeError
+    opt, net, sd = _net_cuda("sr_x4", "f16x3")
+    big = {k: (v * 3e5 if k == "flow.level1_condFlow.conv_first.weight" else v) for k, v in sd.items()}
+    net.load_state_dict(big, strict=True)
+    lr = synth.synthetic_lr(1, 8, 8, seed=2).cuda()
+    with torch.no_grad():
+        net(lr=lr, eps_std=0.0, reverse=True)
+        with pytest.raises(FP16RangeError):
+            net.check_status()
+        net.load_state_dict(sd, strict=True)
+        out = net(lr=lr, eps_std=0.0, reverse=True)
+        net.check_status()
+    assert torch.isfinite(out).all()
+
+
+def test_single_device_dataparallel_and_reference_model_wrapper_call():
+    """The reference always wraps the net (HCFlow_SR_model.py:33-36): nn.DataParallel over ONE device runs the module
+    itself and must work; replication over several devices is refused with a clear error (one process per GPU is the
+    supported multi-GPU mode)."""
+    opt, net, sd = _net_cuda("sr_x4", "f16x3")
+    lr = synth.synthetic_lr(2, 8, 8, seed=2).cuda()
+    dp = torch.nn.DataParallel(net, device_ids=[0])
+    with torch.no_grad():
+        a = dp(lr=lr, z=None, u=None, eps_std=0.0, reverse=True, training=False)
+        b = net(lr=lr, z=None, u=None, eps_std=0.0, reverse=True, training=False)
+    assert torch.equal(a, b)
+    with pytest.raises(RuntimeError, match="one process per GPU"):
+        net._replicate_for_data_parallel()
+
+
+def test_batch_mean_nll_over_nccl_matches_the_oracle_mean(report):
+    """configs[4]: the batch NLL is the path's only collective.  Two ranks (two GPUs) over NCCL against the oracle's
+    nll.mean() on the concatenated batch -- tools/nccl_nll_check.py under torchrun.  Needs >= 2 GPUs."""
+    import json
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run: gpurun --gpus 2 -- python -m pytest tests -m gpu -k nccl)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(root, "tools", "nccl_nll_check.py")]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
+    out = r.stdout.decode(errors="replace")
+    assert r.returncode == 0, out[-2000:]
+    line = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+    assert line["ok"] and line["backend"] == "nccl" and line["world"] == 2
+    report["nccl_batch_mean_nll"] = line

@@ -212,3 +212,16 @@ def test_tf32_weight_image_layout(cout, kin, ks, passes):
         hi = (ref.contiguous().view(torch.int32) & -8192).view(torch.float32)     # TF32 read = drop 13 mantissa bits
         assert torch.equal(unsw[:, :, N:N + cout], ref - hi)
     assert lib.hcf_conv_tc_weight_bytes(kin + 8, cout, ks, passes) == 0
+
+
+def test_replication_is_refused_and_load_state_dict_invalidates():
+    """CPU side of two ADVICE items: DataParallel replication raises a clear error (replicas carry no parameters),
+    load_state_dict bumps the weight epoch the engines' signature includes."""
+    opt, net, sd = net_and_weights("sr_x4")
+    with pytest.raises(RuntimeError, match="one process per GPU"):
+        net._replicate_for_data_parallel()
+    e0 = net._weights_epoch
+    net.load_state_dict(sd, strict=True)
+    assert net._weights_epoch == e0 + 1
+    net.invalidate_weights()
+    assert net._weights_epoch == e0 + 2

@@ -47,7 +47,7 @@ def main():
             ref = first      # image 0 has the same LR / noise seed prefix only for B=1; used as a finiteness check
         print(json.dumps({"precision": prec, "B": B, "ms": round(ms, 3), "hr_mp_per_s": round(B * 160 * 160 / 1e6 / (ms / 1e3), 2),
                           "finite": bool(torch.isfinite(eng.ext["hr_raw"]).all()), "launches": eng.launches_per_run}), flush=True)
-        net._engines.clear()
+        net.clear_engines()
         del eng
         torch.cuda.empty_cache()
 

@@ -41,7 +41,7 @@ def main():
     torch.cuda.synchronize()
     print("precision {} debug {} eager ms/step {:.3f}".format(prec, os.environ.get("HCF_TC_DEBUG", "0"),
                                                             e0.elapsed_time(e1) / 4), file=sys.stderr)
-    net._engines.clear()
+    net.clear_engines()
     del eng
     gc.collect()
 
