@@ -314,7 +314,7 @@ def test_conv_tcgen05_matches_fp64(case, precision, report):
 # rounding (oracle + patched conv2d) gives 1.6e-3 / 1.3e-5 max-abs on sr_x4.
 # Tolerances are <= 3x the values measured on B200 (profiles/r02_parity_report.json).  The x3 modes (default f16x3)
 # carry the stated "fp32 tolerance" of this package: 2e-4 max-abs on the un-clamped HR, also on the stress fixtures.
-E2E_TOL = {"tf32": 4e-2, "tf32x3": 2e-4, "tf32x3_all": 2e-4, "f16": 6e-3, "f16x3": 1e-4}
+E2E_TOL = {"tf32": 4e-2, "tf32x3": 2e-4, "tf32x3_all": 2e-4, "f16": 6e-3, "f16x3": 8e-5}
 
 
 @pytest.mark.parametrize("precision", ["tf32", "tf32x3", "tf32x3_all", "f16", "f16x3"])
