@@ -80,6 +80,22 @@ class Seg16(C.Structure):
     _fields_ = [("hi", C.c_void_p), ("lo", C.c_void_p), ("ld", C.c_int32), ("_pad", C.c_int32)]
 
 
+class FlowStep(C.Structure):
+    _fields_ = [("w1", C.c_void_p), ("w2", C.c_void_p), ("w3", C.c_void_p),
+                ("bias1", C.c_void_p), ("scale1", C.c_void_p), ("bias2", C.c_void_p), ("scale2", C.c_void_p),
+                ("bias3", C.c_void_p), ("scale3", C.c_void_p),
+                ("w", C.c_void_p), ("an_scale", C.c_void_p), ("an_bias", C.c_void_p),
+                ("pre", C.c_void_p), ("pre_ld", C.c_int32), ("_pad", C.c_int32)]
+
+
+class FlowStepChainArgs(C.Structure):
+    _fields_ = [("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("n_pass", C.c_int32),
+                ("n_steps", C.c_int32), ("split", C.c_int32), ("forward", C.c_int32),
+                ("z", C.c_void_p), ("z_ld", C.c_int32), ("_pad", C.c_int32),
+                ("z16_a", C.c_void_p), ("z16_b", C.c_void_p), ("done", C.c_void_p), ("logdet", C.c_void_p),
+                ("steps", C.POINTER(FlowStep))]
+
+
 OUT_F32, OUT_HI, OUT_LO = 1, 2, 4
 STATUS_F16_OVERFLOW, STATUS_DEP_TIMEOUT = 1, 2
 ABI_VERSION = 3   # == HCF_ABI_VERSION (include/hcflow_b200.h)
@@ -110,6 +126,14 @@ SYMBOLS = {
     "hcf_conv_tc_plan_refresh": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hcf_conv_tc_plan_set_status": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hcf_conv_tc_plan_destroy": (None, [C.c_void_p]),
+    "hcf_flowstep_w1_bytes": (C.c_int64, []),
+    "hcf_flowstep_pack_w1": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "hcf_flowstep_stage_z1": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
+    "hcf_flowstep_chain_create": (C.c_int, [C.POINTER(FlowStepChainArgs), C.POINTER(C.c_void_p)]),
+    "hcf_flowstep_chain_refresh": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hcf_flowstep_chain_set_status": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hcf_flowstep_chain_run": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hcf_flowstep_chain_destroy": (None, [C.c_void_p]),
     "hcf_step_inverse": (C.c_int, [C.POINTER(StepArgs), C.c_void_p]),
     "hcf_step_forward_head": (C.c_int, [C.POINTER(StepArgs), C.c_void_p]),
     "hcf_step_forward_coupling": (C.c_int, [C.POINTER(StepArgs), C.c_void_p]),

@@ -38,6 +38,7 @@ class _HCFlowBase(nn.Module):
         self.share_cond = True   # tensor-core modes: the sub-nets' shared conditioning conv once per level (engine.py)
         self.fuse_steps = True   # tensor-core modes, inverse pass: FlowStep tail in the last sub-net conv's epilogue
         self.pair_convs = True   # tensor-core modes: RDB growth convs in pairs (rewrite.pair_rdb_convs)
+        self.flowchain = True    # fp16 modes: one fused kernel per FlowStep chain (csrc/flowstep_tc.cu)
         # opt-in: when the SAME lr tensor (same storage, same version counter) is sampled again, keep the
         # deepest level's encoder features of the previous call instead of recomputing them
         self.reuse_lr_features = False
@@ -89,7 +90,7 @@ class _HCFlowBase(nn.Module):
         if device.type == "cuda" and device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
         key = (direction, B, h, w, str(device), self.precision, self.use_graph, self.use_chains, self.share_cond,
-               self.fuse_steps, io, self.pair_convs)
+               self.fuse_steps, io, self.pair_convs, self.flowchain)
         eng = self._engines.get(key)
         if eng is not None:
             self._engines.move_to_end(key)
@@ -100,7 +101,7 @@ class _HCFlowBase(nn.Module):
         store = self._stores.setdefault(str(device), WeightStore())
         eng = Engine(self, direction, B, h, w, device, precision=self.precision, use_graph=self.use_graph,
                      use_chains=self.use_chains, share_cond=self.share_cond, fuse_steps=self.fuse_steps, io=io,
-                     pair_convs=self.pair_convs, store=store)
+                     pair_convs=self.pair_convs, store=store, flowchain=self.flowchain)
         self._engines[key] = eng
         return eng
 

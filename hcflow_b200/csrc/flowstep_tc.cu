@@ -84,20 +84,52 @@ struct Params {
 
 struct Maps2 { CUtensorMap m[2]; };
 
+// mbarrier wait with a watchdog: a protocol bug must not hang the GPU (a kernel that never ends takes the box down);
+// after ~4 s of polling the status word gets HCF_STATUS_DEP_TIMEOUT and the kernel traps
+__device__ __forceinline__ void mbar_wait_wd(uint32_t bar, uint32_t parity, int* status) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return;
+    if ((it & 1023u) == 1023u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000ll) {
+        if (status) atomicOr(status, STATUS_DEP_TIMEOUT);
+        __trap();
+      }
+    }
+  }
+}
+#define mbar_wait(bar, parity) mbar_wait_wd((bar), (parity), p.status)
+
 // ------------------------------------------------------------------------------------------------ per-pixel tails
 // h[2j] = shift, h[2j+1] = scale of coupled channel n_pass + j (AffineCouplings.py:52-57, 78-84: h[:, 0::2], h[:, 1::2])
 template <int C>
 __device__ __forceinline__ void mix(const float* __restrict__ s_w, const float (&z)[C], float (&y)[C]) {
 #pragma unroll
   for (int i = 0; i < C; ++i) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // independent accumulators: no C-long dependent FMA chain
+    if (C % 4 == 0) {
 #pragma unroll
-    for (int j = 0; j < C; ++j) {
-      const float w = s_w[i * C + j];
-      if ((j & 3) == 0) a0 = fmaf(w, z[j], a0);
-      else if ((j & 3) == 1) a1 = fmaf(w, z[j], a1);
-      else if ((j & 3) == 2) a2 = fmaf(w, z[j], a2);
-      else a3 = fmaf(w, z[j], a3);
+      for (int j = 0; j < C; j += 4) {               // 16-byte broadcast loads of the row
+        const float4 w4 = *reinterpret_cast<const float4*>(s_w + i * C + j);
+        a0 = fmaf(w4.x, z[j], a0); a1 = fmaf(w4.y, z[j + 1], a1);
+        a2 = fmaf(w4.z, z[j + 2], a2); a3 = fmaf(w4.w, z[j + 3], a3);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < C; ++j) {
+        const float w = s_w[i * C + j];
+        if ((j & 3) == 0) a0 = fmaf(w, z[j], a0);
+        else if ((j & 3) == 1) a1 = fmaf(w, z[j], a1);
+        else if ((j & 3) == 2) a2 = fmaf(w, z[j], a2);
+        else a3 = fmaf(w, z[j], a3);
+      }
     }
     y[i] = (a0 + a1) + (a2 + a3);
   }
@@ -105,10 +137,11 @@ __device__ __forceinline__ void mix(const float* __restrict__ s_w, const float (
 
 // returns the pixel's log-det contribution (forward) or 0
 template <int C>
-__device__ __forceinline__ float tail_pixel(const float (&h)[32], float* __restrict__ zp, int n_pass, bool forward,
+__device__ __forceinline__ float tail_pixel(const float (&h)[32], float* __restrict__ zp, bool forward,
                                             bool has_w, bool has_next, const float* __restrict__ s_w,
                                             const float* __restrict__ s_sc, const float* __restrict__ s_b,
                                             __half* __restrict__ z16p, bool split) {
+  constexpr int n_pass = C / 2;      // AffineCoupling: channels_for_nn = in_channels // 2 (AffineCouplings.py:17-18)
   float z[C];
 #pragma unroll
   for (int i = 0; i < C; ++i) z[i] = __ldcg(zp + i);
@@ -117,10 +150,7 @@ __device__ __forceinline__ float tail_pixel(const float (&h)[32], float* __restr
   for (int i = 0; i < C; ++i) {
     if (i >= n_pass) {
       const int j = i - n_pass;
-      float shift = 0.f, scale = 0.f;
-#pragma unroll
-      for (int k = 0; k < 16; ++k)
-        if (k == j) { shift = h[2 * k]; scale = h[2 * k + 1]; }
+      const float shift = h[2 * j], scale = h[2 * j + 1];
       const float ls = coupling_logscale(scale);
       if (forward) {
         z[i] = (z[i] + shift) * expf(ls);
@@ -229,8 +259,8 @@ __global__ void __launch_bounds__(THREADS, 1) flowstep_kernel(const __grid_const
           cur_step = step;
           const StepDesc* S = p.steps + step;
           const void* src[3] = {ldg_ptr(&S->w1), ldg_ptr(&S->w2), ldg_ptr(&S->w3)};
-          const uint32_t bytes[3] = {split ? (uint32_t)W1_BYTES : (uint32_t)W1_BYTES,   // (one-pass images keep the split geometry's block pitch)
-                                     (uint32_t)(split ? W2_BYTES : W2_BYTES / 2), (uint32_t)p.w3_bytes};
+          // (the W1 image always has the [hi ; lo] block geometry; one-pass plans just never read the lo rows)
+          const uint32_t bytes[3] = {(uint32_t)W1_BYTES, (uint32_t)(split ? W2_BYTES : W2_BYTES / 2), (uint32_t)p.w3_bytes};
           const uint32_t dst[3] = {sbase + OFF_W1, sbase + OFF_W2, sbase + OFF_W3};
           for (int k = 0; k < 3; ++k) {
             mbar_wait(w_empty(k), (w_it & 1u) ^ 1u);
@@ -273,7 +303,7 @@ __global__ void __launch_bounds__(THREADS, 1) flowstep_kernel(const __grid_const
     const uint32_t idesc3m = (1u << 4) | ((NB3 >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t idesc3c = (1u << 4) | (((uint32_t)p.N3 >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t idesc12 = split ? idesc128 : idesc64;
-    const uint32_t NB12_16 = (split ? 128u : 64u) * 8u;            // rows x 128 B in 16-byte units
+    const uint32_t W1_BLOCK16 = 128u * 8u;                         // one tap block of W1 ([hi 64 ; lo 64] rows) in 16-byte units
     int cur_step = -1;
     uint32_t w_it = 0;
     for (int seq = 0, item; (item = item_at(seq)) >= 0; ++seq) {
@@ -293,7 +323,7 @@ __global__ void __launch_bounds__(THREADS, 1) flowstep_kernel(const __grid_const
 #pragma unroll 1
         for (int tap = 0; tap < 9; ++tap) {
           const int dy = tap / 3, dx = tap - dy * 3;
-          const uint64_t bd = b0 + (uint32_t)(tap >> 2) * NB12_16 + (uint32_t)(tap & 3) * 2u;
+          const uint64_t bd = b0 + (uint32_t)(tap >> 2) * W1_BLOCK16 + (uint32_t)(tap & 3) * 2u;
 #pragma unroll
           for (int m = 0; m < 2; ++m) {
             const uint64_t ad = a0 + (uint32_t)((m * 128 + dy * PITCH + dx) * 8);
@@ -515,10 +545,10 @@ __global__ void __launch_bounds__(THREADS, 1) flowstep_kernel(const __grid_const
         __half* z16p = has_next ? p.z16[(step + 1) & 1] + (size_t)pix * 32 : nullptr;
         const bool fw = p.forward != 0, hw = has_w != 0, hn = has_next != 0;
         switch (C) {
-          case 6: lsum = tail_pixel<6>(h, zp, p.n_pass, fw, hw, hn, s_w, s_sc, s_b, z16p, split); break;
-          case 12: lsum = tail_pixel<12>(h, zp, p.n_pass, fw, hw, hn, s_w, s_sc, s_b, z16p, split); break;
-          case 21: lsum = tail_pixel<21>(h, zp, p.n_pass, fw, hw, hn, s_w, s_sc, s_b, z16p, split); break;
-          case 24: lsum = tail_pixel<24>(h, zp, p.n_pass, fw, hw, hn, s_w, s_sc, s_b, z16p, split); break;
+          case 6: lsum = tail_pixel<6>(h, zp, fw, hw, hn, s_w, s_sc, s_b, z16p, split); break;
+          case 12: lsum = tail_pixel<12>(h, zp, fw, hw, hn, s_w, s_sc, s_b, z16p, split); break;
+          case 21: lsum = tail_pixel<21>(h, zp, fw, hw, hn, s_w, s_sc, s_b, z16p, split); break;
+          case 24: lsum = tail_pixel<24>(h, zp, fw, hw, hn, s_w, s_sc, s_b, z16p, split); break;
           default: break;   // (the host only creates plans for these channel counts)
         }
       }
@@ -606,9 +636,8 @@ extern "C" int hcf_flowstep_chain_create(const hcf_flowstep_chain_args* a, hcf_f
   HCF_REQUIRE(out != nullptr, "flowstep_chain: null out");
   *out = nullptr;
   HCF_REQUIRE(a && a->steps && a->n_steps >= 1 && a->B >= 1 && a->H >= 1 && a->W >= 1, "flowstep_chain: bad args");
-  if (!(a->C == 6 || a->C == 12 || a->C == 21 || a->C == 24) || a->n_pass < 1 || a->n_pass > 16 || a->n_pass >= a->C ||
-      2 * (a->C - a->n_pass) > 32) {
-    set_error("flowstep_chain: C = %d / n_pass = %d not supported (C in {6,12,21,24}, sub-net cout <= 32)", a->C, a->n_pass);
+  if (!(a->C == 6 || a->C == 12 || a->C == 21 || a->C == 24) || a->n_pass != a->C / 2 || 2 * (a->C - a->n_pass) > 32) {
+    set_error("flowstep_chain: C = %d / n_pass = %d not supported (C in {6,12,21,24}, n_pass = C / 2)", a->C, a->n_pass);
     return HCF_ENOTSUP;
   }
   HCF_REQUIRE(a->z && a->z_ld >= a->C && a->z16_a && a->z16_b && aligned16(a->z16_a) && aligned16(a->z16_b) && a->done,

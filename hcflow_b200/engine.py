@@ -38,7 +38,7 @@ class Engine:
     """One compiled plan = (net weights, direction, B, h, w, precision) on one device."""
 
     def __init__(self, net, direction, B, h, w, device, precision="fp32", use_graph=True, use_chains=True,
-                 share_cond=True, fuse_steps=True, io="f32", pair_convs=True, store=None):
+                 share_cond=True, fuse_steps=True, io="f32", pair_convs=True, store=None, flowchain=True):
         if not torch.cuda.is_available():
             raise L.HcfError("hcflow_b200 needs a CUDA device (no CPU fallback)")
         self.lib = L.load()
@@ -60,6 +60,8 @@ class Engine:
         self._tc_registry = self.store.tc_registry
         self._my_tc_keys = set()
         self._tc_plans = []
+        self._fs_plans = []
+        self.n_flowchains = 0
         self.weights = self.store.t
         self.n_fp32_fallback = 0  # convs that were meant for the tensor cores but fell back to the CUDA-core kernel
         self.status = None        # sticky device status word of the tensor-core plans (fp16 range guard, dep timeout)
@@ -79,6 +81,7 @@ class Engine:
         self.share_cond = share_cond   # the coupling sub-nets' shared conditioning part once per level (TC modes)
         self.fuse_steps = fuse_steps   # FlowStep tail in the last sub-net conv's epilogue (TC modes, inverse pass)
         self.pair_convs = pair_convs   # RDB growth convs in pairs: N = 64 accumulators, partial sums through `pre`
+        self.flowchain = flowchain     # fp16 modes: whole FlowSteps as work items of the fused-FlowStep kernel
         self._step_structs = {}  # id(conv op) -> L.ConvStep
         self._flag_pool = None   # dependency counters of all chained launches: one buffer, zeroed once per pass
         self._flag_used = 0
@@ -144,7 +147,7 @@ class Engine:
             stamp[key] = sig
 
         self._sd_cpu = sd
-        for op in self.ops:
+        for op in self._flat_ops():
             if isinstance(op, P.ConvOp):
                 npad = prep.npad_for(op.cout)
                 segc = [v.C for v, _ in op.segs]
@@ -169,8 +172,21 @@ class Engine:
         for key in self._my_tc_keys:   # tensor-core weight images this engine uses, in place
             if stamp.get(key) != sig:
                 op, passes, split_ch, f16 = self._tc_registry[key]
-                self.weights[key].copy_(self._pack_tc(op, passes, split_ch, f16))
+                self.weights[key].copy_(self._pack_fs_w1(op) if f16 == "fsw1" else self._pack_tc(op, passes, split_ch, f16))
                 stamp[key] = sig
+        for hnd in self._fs_plans:
+            L.check(self.lib.hcf_flowstep_chain_refresh(hnd, torch.cuda.current_stream(self.device).cuda_stream), "flowstep_refresh")
+
+    def _flat_ops(self):
+        """self.ops with every FlowChainOp expanded into the convs / StepOps whose parameters it uses"""
+        for op in self.ops:
+            if isinstance(op, P.FlowChainOp):
+                for c1, c2, c3, tail, head in op.steps:
+                    for o in (head, c1, c2, c3, tail):
+                        if o is not None:
+                            yield o
+            else:
+                yield op
 
     @staticmethod
     def _wkey(op):
@@ -182,7 +198,8 @@ class Engine:
     def _rewrite_ops(self):
         """The plan as the tensor-core modes execute it (rewrite.py): materialised up-sampled segments, shared
         conditioning convs, fused FlowStep tails; the extra buffers are allocated here."""
-        ops, extra = rewrite.rewrite_ops(self.plan.ops, self.precision, self.share_cond, self.fuse_steps, self.pair_convs)
+        ops, extra = rewrite.rewrite_ops(self.plan.ops, self.precision, self.share_cond, self.fuse_steps, self.pair_convs,
+                                         flowchain=self.flowchain and self.use_chains and self.share_cond and self.fuse_steps)
         for name, b in extra.items():
             if name not in self.bufs:
                 self.bufs[name] = torch.zeros(self.B, b.H, b.W, b.C, dtype=torch.float32, device=self.device)
@@ -247,23 +264,12 @@ class Engine:
                     pending = []
                     self._add_call(lib.hcf_conv_fp32, C.byref(a), "conv_fp32", tag, flops, 1)
                     self.n_fp32_conv += 1
+            elif isinstance(op, P.FlowChainOp):
+                self._flush_tc(pending)
+                pending = []
+                self._lower_flowchain(op)
             elif isinstance(op, P.StepOp):
-                a = L.StepArgs()
-                a.npix, a.pix_per_img = B * op.H * op.W, op.H * op.W
-                a.z, a.z_ld = self._vptr(op.z)
-                a.C = op.z.C
-                if op.h is not None:
-                    a.h, a.h_ld = self._vptr(op.h)
-                a.mode = 0 if op.mode == "affine" else 1
-                a.n_pass = op.n_pass
-                a.w = self.weights[op.w].data_ptr() if op.w else None
-                a.an_scale = self.weights[op.an_scale].data_ptr() if op.an_scale else None
-                a.an_bias = self.weights[op.an_bias].data_ptr() if op.an_bias else None
-                a.logdet = self.logdet.data_ptr() if self.plan.uses_logdet else None
-                fn = {"inverse": lib.hcf_step_inverse, "forward_head": lib.hcf_step_forward_head,
-                      "forward_coupling": lib.hcf_step_forward_coupling}[op.variant]
-                self._keep.append(a)
-                self._add_call(fn, C.byref(a), "step_" + op.variant)
+                self._lower_step(op)
             elif isinstance(op, P.PriorOp):
                 a = L.PriorArgs()
                 a.B, a.H, a.W, a.Cz = B, op.H, op.W, op.z.C
@@ -351,15 +357,115 @@ class Engine:
             else:
                 raise TypeError(op)
         self._flush_tc(pending)
-        if self._tc_plans:
+        if self._tc_plans or self._fs_plans:
             self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
             self._status_host = torch.zeros(1, dtype=torch.int32).pin_memory()
             for hnd in self._tc_plans:
                 L.check(lib.hcf_conv_tc_plan_set_status(hnd, self.status.data_ptr()), "plan_set_status")
+            for hnd in self._fs_plans:
+                L.check(lib.hcf_flowstep_chain_set_status(hnd, self.status.data_ptr()), "flowstep_set_status")
         if self._flag_used:
             pool, used = self._flag_pool, self._flag_used
             self.calls.insert(0, (lambda _a, _s: (pool[:used].zero_(), 0)[1], None, "flags_zero"))
             self.call_info.insert(0, {"cls": "flags_zero", "tag": "flags_zero", "flops": 0.0, "convs": 0})
+
+    def _lower_step(self, op):
+        lib, B = self.lib, self.B
+        a = L.StepArgs()
+        a.npix, a.pix_per_img = B * op.H * op.W, op.H * op.W
+        a.z, a.z_ld = self._vptr(op.z)
+        a.C = op.z.C
+        if op.h is not None:
+            a.h, a.h_ld = self._vptr(op.h)
+        a.mode = 0 if op.mode == "affine" else 1
+        a.n_pass = op.n_pass
+        a.w = self.weights[op.w].data_ptr() if op.w else None
+        a.an_scale = self.weights[op.an_scale].data_ptr() if op.an_scale else None
+        a.an_bias = self.weights[op.an_bias].data_ptr() if op.an_bias else None
+        a.logdet = self.logdet.data_ptr() if self.plan.uses_logdet else None
+        fn = {"inverse": lib.hcf_step_inverse, "forward_head": lib.hcf_step_forward_head,
+              "forward_coupling": lib.hcf_step_forward_coupling}[op.variant]
+        self._keep.append(a)
+        self._add_call(fn, C.byref(a), "step_" + op.variant)
+
+    # ---- fused FlowStep chains (csrc/flowstep_tc.cu) -------------------------------------------------------
+    def _pack_fs_w1(self, op):
+        """conv1's z1 input channels -> the fused-FlowStep kernel's tap-block image (host tensor)"""
+        w = self._raw_weight(op).contiguous()           # [64, n_pass, 3, 3] (w_in slice of the shared-conditioning rewrite)
+        assert w.shape[0] == 64 and w.shape[2] == 3 and w.shape[1] <= 16, tuple(w.shape)
+        img = torch.zeros(self.lib.hcf_flowstep_w1_bytes() // 2, dtype=torch.float16)
+        L.check(self.lib.hcf_flowstep_pack_w1(w.data_ptr(), w.shape[1], img.data_ptr()), "flowstep_pack_w1")
+        return img
+
+    def _fs_w1(self, op):
+        key = self._wkey(op) + "#fsw1"
+        if key not in self.weights or self.store.stamp.get(key) != self._sig:
+            img = self._pack_fs_w1(op)
+            if key in self.weights:
+                self.weights[key].copy_(img)
+            else:
+                self.weights[key] = img.to(self.device)
+            self._tc_registry[key] = (op, 0, 0, "fsw1")
+            self.store.stamp[key] = self._sig
+        self._my_tc_keys.add(key)
+        return self.weights[key]
+
+    def _lower_flowchain(self, op):
+        """One persistent cooperative launch for len(op.steps) FlowSteps: z1 staging, (forward: the first step's
+        ActNorm + W head as its own small launch,) then the fused kernel."""
+        lib, B = self.lib, self.B
+        split = 1 if self.precision == "f16x3" else 0
+        passes = 3 if split else 1
+        n = len(op.steps)
+        steps = (L.FlowStep * n)()
+
+        def vec(key, npad):
+            return self.weights[key + "@{}".format(npad)].data_ptr()
+        flops = 0.0
+        for i, (c1, c2, c3, tail, head) in enumerate(op.steps):
+            s = steps[i]
+            s.w1 = self._fs_w1(c1).data_ptr()
+            s.w2 = self._tc16_weights(c2, passes, -1 if split else 0).data_ptr()
+            s.w3 = self._tc16_weights(c3, passes, -1 if split else 0).data_ptr()
+            s.bias1, s.scale1 = vec(c1.bias, prep.npad_for(c1.cout)), vec(c1.scale, prep.npad_for(c1.cout))
+            s.bias2, s.scale2 = vec(c2.bias, prep.npad_for(c2.cout)), vec(c2.scale, prep.npad_for(c2.cout))
+            s.bias3, s.scale3 = vec(c3.bias, prep.npad_for(c3.cout)), vec(c3.scale, prep.npad_for(c3.cout))
+            tab = head if op.forward else tail          # whose W / ActNorm vectors this step contributes
+            s.w = self.weights[tab.w].data_ptr() if tab.w else None
+            s.an_scale = self.weights[tab.an_scale].data_ptr()
+            s.an_bias = self.weights[tab.an_bias].data_ptr()
+            if c1.pre is not None:
+                s.pre, s.pre_ld = self._vptr(c1.pre)
+            for c in (c1, c2, c3):
+                flops += 2.0 * B * c.H * c.W * c.ks * c.ks * sum(v.C for v, _ in c.segs) * c.cout
+        a = L.FlowStepChainArgs()
+        a.B, a.H, a.W, a.C, a.n_pass, a.n_steps, a.split, a.forward = B, op.H, op.W, op.z.C, op.n_pass, n, split, int(op.forward)
+        a.z, a.z_ld = self._vptr(op.z)
+        name = "fsz16_{}x{}".format(op.H, op.W)
+        if name not in self.shadow16:    # ping-pong staging of z1: [hi 16 | lo 16] fp16 per pixel, shared by a level's chains
+            self.shadow16[name] = tuple(torch.zeros(B, op.H, op.W, 32, dtype=torch.float16, device=self.device) for _ in range(2))
+        za, zb = self.shadow16[name]
+        a.z16_a, a.z16_b = za.data_ptr(), zb.data_ptr()
+        tiles = B * ((op.H + 15) // 16) * ((op.W + 7) // 8)
+        done = self._alloc_flags(tiles)
+        a.done = done.data_ptr()
+        a.logdet = self.logdet.data_ptr() if (op.forward and self.plan.uses_logdet) else None
+        a.steps = steps
+        handle = C.c_void_p()
+        L.check(lib.hcf_flowstep_chain_create(C.byref(a), C.byref(handle)), "flowstep_chain_create")
+        self._keep += [a, steps, done]
+        self._fs_plans.append(handle)
+        if op.forward:
+            self._lower_step(op.steps[0][4])             # ActNorm + W of the first step; the others ride in the tails
+        zptr, zld = self._vptr(op.z)
+        npix = B * op.H * op.W
+
+        def stage(_a, stream, zptr=zptr, zld=zld, n_pass=op.n_pass, dst=za.data_ptr()):
+            return lib.hcf_flowstep_stage_z1(zptr, zld, n_pass, npix, dst, stream)
+        self._add_call(stage, None, "layout_stage_z1")
+        self._add_call(lib.hcf_flowstep_chain_run, handle, "conv_tc_flowstep", "{}@{}x{}".format(op.tag, op.H, op.W), flops, 3 * n)
+        self.n_tc += 3 * n
+        self.n_flowchains += 1
 
     def _alloc_flags(self, n):
         if self._flag_pool is None:
@@ -714,6 +820,12 @@ class Engine:
             except Exception:
                 pass
         self._tc_plans = []
+        for hnd in self._fs_plans:
+            try:
+                self.lib.hcf_flowstep_chain_destroy(hnd)
+            except Exception:
+                pass
+        self._fs_plans = []
         self.calls, self.call_info, self._keep = [], [], []
         self.bufs, self.ext, self.shadow16 = {}, {}, {}
         self._flag_pool = None

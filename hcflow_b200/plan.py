@@ -118,6 +118,22 @@ class DiracLogpOp:
 
 
 @dataclass
+class FlowChainOp:
+    """engine-level rewrite only (rewrite.group_flowsteps): consecutive FlowSteps with FCN sub-nets on the same z,
+    executed by ONE fused-FlowStep launch (csrc/flowstep_tc.cu).  ``steps``: per step (conv1, conv2, conv3, tail StepOp,
+    head StepOp or None); ``orig``: the ops it replaces, in order (tests/plan_emulator.py interprets those)."""
+    kind = "flowchain"
+    H: int
+    W: int
+    z: View
+    n_pass: int
+    forward: bool
+    steps: list
+    orig: list
+    tag: str = ""
+
+
+@dataclass
 class Plan:
     direction: str
     sr: bool

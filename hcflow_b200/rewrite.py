@@ -68,7 +68,12 @@ def share_conditioning(ops, bufs, max_cout=128):
             uops.append(P.ConvOp(H, W, [(cond, 0)], 3, cout * len(mem),
                                  tuple((ops[m].weight, zc, zc + cc) for m in mem), None, None, P.ACT_NONE,
                                  P.View(ubuf, g * cout, cout * len(mem)), tag="fcn.ucond"))
-        inserts[idxs[0]] = uops
+        # in front of the first step -- and of its forward ActNorm / W head, so that [head, conv1, conv2, conv3, coupling]
+        # stays contiguous (group_flowsteps); the shared convs depend on the encoder feature only
+        at = idxs[0]
+        if at > 0 and isinstance(ops[at - 1], P.StepOp) and ops[at - 1].variant == "forward_head":
+            at -= 1
+        inserts[at] = uops
         for j, m in enumerate(idxs):
             o = ops[m]
             ops[m] = P.ConvOp(o.H, o.W, [o.segs[0]], o.ks, o.cout, o.weight, o.bias, o.scale, o.act, o.out, tag=o.tag,
@@ -144,7 +149,83 @@ def fuse_steps(ops):
     return fused
 
 
-def rewrite_ops(plan_ops, precision, share_cond=True, fuse=True, pair=True):
+FLOWCHAIN_C = (6, 12, 21, 24)   # csrc/flowstep_tc.cu
+
+
+def _fcn_triplet(ops, i):
+    """ops[i:i+3] = conv1 (3x3 over z1 only, optional pre addend), conv2 (1x1), conv3 (3x3) of one FCN sub-net?"""
+    if i + 2 >= len(ops):
+        return None
+    c1, c2, c3 = ops[i], ops[i + 1], ops[i + 2]
+    if not all(isinstance(c, P.ConvOp) for c in (c1, c2, c3)):
+        return None
+    ok = (c1.tag == "fcn.conv1" and c2.tag == "fcn.conv2" and c3.tag == "fcn.conv3"
+          and len(c1.segs) == 1 and c1.segs[0][1] == 0 and c1.ks == 3 and c1.cout == 64 and c1.act == P.ACT_RELU
+          and c1.bias and c1.scale and c1.res1 is None and c1.res2 is None and c1.out2 is None and c1.raw2 is None
+          and len(c2.segs) == 1 and c2.segs[0][0] == c1.out and c2.ks == 1 and c2.cout == 64 and c2.act == P.ACT_RELU
+          and c2.bias and c2.scale and c2.pre is None
+          and len(c3.segs) == 1 and c3.segs[0][0] == c2.out and c3.ks == 3 and c3.cout <= 32 and c3.act == P.ACT_NONE
+          and c3.bias and c3.scale and c3.pre is None and c3.res1 is None and c3.out2 is None
+          and (c1.H, c1.W) == (c2.H, c2.W) == (c3.H, c3.W)
+          and (c1.pre is None or (c1.pre.C == 64 and c1.pre.off % 4 == 0 and c1.pre.buf.C % 4 == 0)))
+    return (c1, c2, c3) if ok else None
+
+
+def group_flowsteps(ops):
+    """Runs of FlowSteps whose sub-net is an FCN over z1 alone (after share_conditioning the conditional steps
+    qualify too) become ONE FlowChainOp each: the fused-FlowStep kernel runs a whole step per work item.
+      reverse:  [conv1, conv2, conv3 + fused StepOp("inverse")] per step           (after fuse_steps)
+      forward:  [StepOp("forward_head"), conv1, conv2, conv3, StepOp("forward_coupling")] per step"""
+    out, i = [], 0
+    while i < len(ops):
+        steps, orig, j = [], [], i
+        z = None
+        forward = None
+        while True:
+            head = None
+            k = j
+            if k < len(ops) and isinstance(ops[k], P.StepOp) and ops[k].variant == "forward_head":
+                head = ops[k]
+                k += 1
+            tri = _fcn_triplet(ops, k)
+            if tri is None:
+                break
+            c1, c2, c3 = tri
+            if head is not None:
+                tail = ops[k + 3] if k + 3 < len(ops) else None
+                if not (isinstance(tail, P.StepOp) and tail.variant == "forward_coupling" and tail.h == c3.out
+                        and tail.z == head.z and c3.step is None):
+                    break
+                fw, end = True, k + 4
+            else:
+                tail = c3.step
+                if tail is None or tail.variant != "inverse":
+                    break
+                fw, end = False, k + 3
+            zz = tail.z
+            if not (tail.mode == "affine" and zz.C in FLOWCHAIN_C and tail.n_pass == zz.C // 2
+                    and c3.cout == 2 * (zz.C - tail.n_pass) and c1.segs[0][0] == zz.sub(0, tail.n_pass)
+                    and (tail.H, tail.W) == (c1.H, c1.W)):
+                break
+            if steps and (zz != z or fw != forward):
+                break
+            z, forward = zz, fw
+            steps.append((c1, c2, c3, tail, head))
+            orig.extend(ops[j:end])
+            j = end
+        if steps:
+            c1 = steps[0][0]
+            out.append(P.FlowChainOp(c1.H, c1.W, z, steps[0][3].n_pass, forward, steps, orig,
+                                     tag="flowsteps[{}{}]x{}".format("cond" if c1.pre is not None else "main",
+                                                                    ",fwd" if forward else "", len(steps))))
+            i = j
+        else:
+            out.append(ops[i])
+            i += 1
+    return out
+
+
+def rewrite_ops(plan_ops, precision, share_cond=True, fuse=True, pair=True, flowchain=True):
     """-> (ops, {name: Buf} of the extra fp32 buffers the rewritten ops use)."""
     ops = list(plan_ops)
     bufs = {}
@@ -159,6 +240,8 @@ def rewrite_ops(plan_ops, precision, share_cond=True, fuse=True, pair=True):
         ops = share_conditioning(ops, bufs, 64 if precision in SPLIT_FCN_MODES else 128)
     if fuse:
         ops = fuse_steps(ops)
+    if flowchain and precision in ("f16", "f16x3"):
+        ops = group_flowsteps(ops)
     return ops, bufs
 
 
@@ -172,6 +255,8 @@ def _overlap(a, b):
 
 
 def op_reads(op):
+    if isinstance(op, P.FlowChainOp):
+        return [op.z] + [st[0].pre for st in op.steps if st[0].pre is not None]
     if isinstance(op, P.ConvOp):
         return ([v for v, _ in op.segs] + [v for v in (op.res1, op.res2, op.pre) if v is not None]
                 + ([op.step.z] if op.step is not None else []))
@@ -185,6 +270,8 @@ def op_reads(op):
 
 
 def op_writes(op):
+    if isinstance(op, P.FlowChainOp):
+        return [op.z]
     if isinstance(op, P.ConvOp):
         if op.step is not None:    # h is consumed in the epilogue, z is updated in place
             return [op.step.z]

@@ -187,6 +187,60 @@ typedef struct {
 int hcf_conv_chain16_create(const hcf_conv_args* args, const void* const* w16, const int32_t* layer_passes,
                             const int32_t* layer_split, const int32_t* out_flags, int32_t n, int32_t* done_flags, const hcf_shadow16* shadows,
                             int32_t n_shadows, const hcf_seg16* seg16, hcf_conv_tc_plan** out);
+/* ---- fused FlowStep chains (csrc/flowstep_tc.cu): ONE work item = one whole FlowStep (FlowStep.py:40-64) with an FCN
+ * coupling sub-net (Basic.py:426-447: conv3x3 -> ActNorm, ReLU -> conv1x1 -> ActNorm, ReLU -> conv3x3 * exp(3 logs)) on
+ * one 16x8-pixel tile, the sub-net's hidden activations never leave the SM; n_steps consecutive FlowSteps on the same z
+ * are one persistent cooperative launch.  Replaces, per step: 3 F.conv2d + 2 ActNorm + the coupling / invconv / ActNorm
+ * elementwise ops of AffineCouplings.py:28-87, Permutations.py:94-108, ActNorms.py:45-94.  C in {6, 12, 21, 24},
+ * n_pass = C / 2 channels condition the sub-net (hidden width 64), fp16 operands (split = 1: hi + lo on both operands). */
+typedef struct {
+  const void* w1;       /* conv1 over z1: image of hcf_flowstep_pack_w1 (device) */
+  const void* w2;       /* conv2 1x1 64->64: hcf_conv_tc16_pack_weights(kin 64, cout 64, ks 1, split_kin 64 or 0) */
+  const void* w3;       /* conv3 3x3 64->2(C - n_pass): hcf_conv_tc16_pack_weights(kin 64, cout, ks 3, split_kin 64 or 0) */
+  const float* bias1;   /* device vectors: ActNorm of conv1 (bias, exp(logs)), of conv2, and conv3's bias / exp(3 logs); */
+  const float* scale1;  /* >= 64 entries (conv3: >= ceil16(cout)) */
+  const float* bias2;
+  const float* scale2;
+  const float* bias3;
+  const float* scale3;
+  const float* w;        /* per-pixel C x C matrix of THIS step (inverse: W^-1, forward: W), NULL = no permutation */
+  const float* an_scale; /* ActNorm of THIS step: inverse exp(-logs), forward exp(logs) */
+  const float* an_bias;
+  const float* pre;      /* conditional steps: the W_u * u part of conv1, fp32 NHWC [B,H,W,pre_ld >= 64]; may be NULL */
+  int32_t pre_ld;
+  int32_t _pad;
+} hcf_flowstep;
+
+typedef struct {
+  int32_t B, H, W;
+  int32_t C, n_pass;
+  int32_t n_steps;
+  int32_t split;      /* 1: all three convs with hi + lo operands (x3 modes); 0: one fp16 pass */
+  int32_t forward;    /* 0: inverse tails (coupling^-1, W^-1, ActNorm^-1 of each step);
+                         1: forward tails (coupling of step s + log-det, then ActNorm + W of step s + 1); the caller
+                            applies the FIRST step's ActNorm + W beforehand (hcf_step_forward_head) */
+  float* z;           /* [B,H,W,z_ld] fp32, C channels, updated in place */
+  int32_t z_ld;
+  int32_t _pad;
+  void* z16_a;        /* two staging buffers [B,H,W,32] fp16 (hi 16 | lo 16 channels per pixel), ping-pong between steps; */
+  void* z16_b;        /* A must hold z[:, :n_pass] before the run (hcf_flowstep_stage_z1) */
+  int32_t* done;      /* per-tile step counters, B * ceil(H/16) * ceil(W/8) int32, zeroed before every run */
+  double* logdet;     /* forward: per-image log-det accumulators [B] (sum of the coupling log-scales is added); may be NULL */
+  const hcf_flowstep* steps;
+} hcf_flowstep_chain_args;
+
+typedef struct hcf_flowstep_plan hcf_flowstep_plan;
+int64_t hcf_flowstep_w1_bytes(void);
+/* w: [64][n_pass][3][3] fp32 (host), the z1 input channels of the sub-net's first conv */
+int hcf_flowstep_pack_w1(const float* w, int32_t n_pass, void* image);
+int hcf_flowstep_stage_z1(const float* z, int32_t z_ld, int32_t n_pass, int64_t npix, void* z16, void* stream);
+int hcf_flowstep_chain_create(const hcf_flowstep_chain_args* a, hcf_flowstep_plan** out);
+/* re-gathers the per-step bias / scale / W / ActNorm tables after the arrays behind them were rewritten in place */
+int hcf_flowstep_chain_refresh(hcf_flowstep_plan* p, void* stream);
+int hcf_flowstep_chain_set_status(hcf_flowstep_plan* p, int32_t* status);
+int hcf_flowstep_chain_run(const hcf_flowstep_plan* p, void* stream);
+void hcf_flowstep_chain_destroy(hcf_flowstep_plan* p);
+
 /* fp32 NHWC view (ld, C, npix pixels) -> hi / lo planes with row pitch dst_ld (lo may be NULL) */
 int hcf_split16(const float* src, int32_t ld, int32_t C, int64_t npix, void* hi, void* lo, int32_t dst_ld, void* stream);
 int32_t hcf_conv_tc_plan_layers(const hcf_conv_tc_plan* p);

@@ -175,7 +175,10 @@ class Emulator:
             hr = self.ext["hr"]
             const += prep.quant_logdet(self.quant, hr.shape[2] * hr.shape[3])
         self.logdet.fill_(const)
-        for op in self.ops:
+        flat = []
+        for op in self.ops:     # a fused FlowStep chain computes exactly what the ops it replaces compute
+            flat.extend(op.orig if isinstance(op, P.FlowChainOp) else [op])
+        for op in flat:
             if isinstance(op, P.ConvOp):
                 self._conv(op)
             elif isinstance(op, P.StepOp):

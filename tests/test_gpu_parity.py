@@ -992,3 +992,50 @@ def test_batch_mean_nll_over_nccl_matches_the_oracle_mean(report):
     line = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
     assert line["ok"] and line["backend"] == "nccl" and line["world"] == 2
     report["nccl_batch_mean_nll"] = line
+
+
+# ------------------------------------------------------------------------------ fused FlowStep kernel (flowstep_tc.cu)
+FS_CASES = [
+    # name, cfg, step prefixes in forward order, conditional?, (B, H, W)
+    ("main_c24", "sr_x4", ["flow.layers.{}".format(i) for i in (16, 17, 18)], False, (2, 40, 40)),
+    ("main_c12_ragged", "sr_x4", ["flow.layers.{}".format(i) for i in (1, 2, 3, 4)], False, (1, 21, 13)),
+    ("cond_c21", "sr_x4", ["flow.level1_condFlow.additional_flow_steps.{}".format(i) for i in (0, 1, 2)], True, (2, 24, 24)),
+    ("cond_c6_single_tile", "sr_x4", ["flow.level0_condFlow.additional_flow_steps.{}".format(i) for i in (0, 1)], True, (1, 16, 8)),
+    ("stress_cond_c21", "sr_x4_stress", ["flow.level1_condFlow.additional_flow_steps.{}".format(i) for i in (0, 1, 2, 3)], True, (1, 33, 20)),
+    ("stress_main_c12", "sr_x4_stress", ["flow.layers.{}".format(i) for i in (1, 2, 3, 4)], False, (3, 32, 16)),
+]
+
+
+@pytest.mark.parametrize("split", [True, False], ids=["split", "one_pass"])
+@pytest.mark.parametrize("forward", [False, True], ids=["inverse", "forward"])
+@pytest.mark.parametrize("case", FS_CASES, ids=[c[0] for c in FS_CASES])
+def test_fused_flowstep_kernel_matches_oracle(case, forward, split, report):
+    """hcf_flowstep_chain_* alone, through the C ABI: n consecutive FlowSteps (whole sub-net + tail per work item, halo
+    recompute, ping-pong z1 staging, inter-tile step counters) against oracle.flow_step applied n times.  Inverse runs
+    the steps in reverse order (FlowNet_SR_x4.py:106-109).  Tolerance: split 5e-5 (values O(1..5); measured in the
+    report), one fp16 pass 2e-2."""
+    from tests import gpu_ops
+    name, cfg, pres, cond, (B, H, W) = case
+    opt, net, sd = net_and_weights(cfg)
+    Cc = sd[pres[0] + ".actnorm.bias"].shape[1]
+    z = _rand(B, Cc, H, W, seed=61)
+    u = _rand(B, 128, H, W, seed=62, scale=0.3) if cond else None
+    order = pres if forward else list(reversed(pres))
+    with torch.no_grad():
+        want = z.clone()
+        ld = torch.zeros(B) if forward else None
+        for pre in order:
+            want, ld = orc.flow_step(want, u, sd, pre, ld, not forward, "affine", Cc // 2)
+        logdet = torch.zeros(B, dtype=torch.float64, device="cuda") if forward else None
+        got = gpu_ops.flowstep_chain(z, sd, order, forward, split, u=u, logdet=logdet)
+    err = maxabs(got, want)
+    rec = {"z": err, "range": float(want.abs().max())}
+    if forward:
+        from hcflow_b200 import prep
+        const = prep.logdet_constant(sd, [(pre, (pre + ".permute.weight") in sd, H * W) for pre in order])
+        rec["logdet_abs"] = float(((logdet.cpu() + const) - ld.double()).abs().max())
+        rec["logdet"] = float(ld.abs().max())
+    report["flowstep_kernel/{}/{}/{}".format(name, "fwd" if forward else "inv", "split" if split else "one")] = rec
+    assert err < (5e-5 if split else 2e-2), (name, err)
+    if forward:
+        assert rec["logdet_abs"] < (2e-3 if split else 0.5) * max(1.0, rec["logdet"] / 1000.0), rec

@@ -99,7 +99,7 @@ def test_fp16_chain_layout_of_the_x4_encoder_and_flowstep_chains():
     assert (rewrite.OUT_F32, rewrite.OUT_HI, rewrite.OUT_LO) == (_lib.OUT_F32, _lib.OUT_HI, _lib.OUT_LO)
     opt, net, sd = net_and_weights("sr_x4")
     plan = P.build_plan(net, "reverse", 2, 16, 16)
-    ops, _ = rewrite.rewrite_ops(plan.ops, "f16x3")
+    ops, _ = rewrite.rewrite_ops(plan.ops, "f16x3", flowchain=False)   # (the generic chained-conv lowering of FlowSteps)
     # runs of consecutive convs on one grid = the chains the engine builds
     runs, cur = [], []
     for i, o in enumerate(ops):
@@ -164,3 +164,44 @@ def test_rewritten_forward_plan_matches_golden(cfg):
     H, W = hr.shape[2], hr.shape[3]
     nll = float(((-em.logdet) / (math.log(2.0) * H * W)).mean())
     assert abs(nll - float(g["fwd_nll"])) < 1e-4 * abs(float(g["fwd_nll"]))
+
+
+@pytest.mark.parametrize("direction", ["reverse", "forward"])
+@pytest.mark.parametrize("cfg", ["sr_x4", "sr_x8", "rescaling_x4", "sr_x4_stress"])
+def test_flowstep_chains_are_grouped_and_still_reproduce_the_golden(cfg, direction):
+    """rewrite.group_flowsteps (fp16 modes): every FlowStep with an FCN sub-net over z1 becomes part of a FlowChainOp --
+    the work list of the fused-FlowStep kernel (csrc/flowstep_tc.cu) -- and the plan still computes the reference's
+    outputs (the emulator interprets a chain through the ops it replaces)."""
+    import math
+    from hcflow_b200 import rewrite
+    g = load_golden(cfg)
+    opt, net, sd = net_and_weights(cfg)
+    lr, hr, eps = _inputs(g, opt)
+    plan = P.build_plan(net, direction, g["B"], g["h"], g["w"])
+    ops, extra = rewrite.rewrite_ops(plan.ops, "f16x3")
+    chains = [o for o in ops if isinstance(o, P.FlowChainOp)]
+    assert chains and all(c.forward == (direction == "forward") for c in chains)
+    n_steps_plan = sum(isinstance(o, P.StepOp) and o.variant in ("inverse", "forward_coupling") for o in plan.ops)
+    n_in_chains = sum(len(c.steps) for c in chains)
+    if cfg.startswith("sr_x4"):
+        assert n_in_chains == n_steps_plan                      # x4: every FlowStep runs in the fused kernel
+        assert not any(isinstance(o, P.StepOp) for o in ops)
+    else:
+        assert 0 < n_in_chains < n_steps_plan                   # x8: C = 48 steps; rescaling: dense sub-nets stay generic
+    for c in chains:
+        assert c.z.C in rewrite.FLOWCHAIN_C and c.n_pass == c.z.C // 2
+        for c1, c2, c3, tail, head in c.steps:
+            assert c1.segs[0][0] == c.z.sub(0, c.n_pass) and (head is not None) == c.forward
+    em = Emulator(net, plan, ops=ops, extra_bufs=extra)
+    if direction == "reverse":
+        out = em.run(lr=lr, **{"eps{}".format(i): e for i, e in enumerate(eps)})
+        assert maxabs(out["hr_raw"], g["inv_raw"]) < 2e-4
+    elif is_sr(opt):
+        dq = torch.rand(hr.shape, generator=torch.Generator().manual_seed(77), dtype=torch.float32)
+        out = em.run(hr=hr, lr=lr, dequant=dq)
+        assert maxabs(out["z_raw"], g["fwd_z"]) < 2e-4
+        nll = float(((-em.logdet) / (math.log(2.0) * hr.shape[2] * hr.shape[3])).mean())
+        assert abs(nll - float(g["fwd_nll"])) < 1e-4 * abs(float(g["fwd_nll"]))
+    else:
+        out = em.run(hr=hr)
+        assert maxabs(out["fake_lr"], g["fwd_fake_lr"]) < 2e-4
