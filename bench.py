@@ -458,7 +458,7 @@ def run_ours(args):
     }
     # the fused FlowStep launches (north_star: per fused FlowStep, fraction of the HBM roofline): algorithmic bytes of
     # SURVEY 8d's table (x4 inverse, per image: conditional / main FlowSteps of both levels = 14.1 + 4.0 + 46.6 + 8.0 MB)
-    fs = [(t, v) for t, v in by_tag.items() if "fcn." in t]
+    fs = [(t, v) for t, v in by_tag.items() if "fcn." in t or t.startswith("flowsteps")]
     if fs:
         fs_ms = sum(v[1] for _, v in fs)
         fs_bytes = B * (680 * 13 * 1600 + 192 * 13 * 1600 + 560 * 13 * 6400 + 96 * 13 * 6400)
@@ -466,10 +466,13 @@ def run_ours(args):
             "bound": "hbm", "launches": len(fs), "ms": round(fs_ms, 3), "algorithmic_bytes": fs_bytes,
             "achieved": fs_bytes / (fs_ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": fs_bytes / (fs_ms / 1e3) / 1e9 / peaks["hbm_gbs"],
-            "note": "52 FlowSteps (shared-conditioning convs, sub-nets, fused ActNorm / 1x1 / coupling tails) in 4 chained "
-                    "launches; ncu: 0.83 GB DRAM traffic for the 80x80 conditional chain (0.75 GB algorithmic), 14 MB for the "
-                    "main chain (L2-resident); tensor pipe 13 % / 4 %: these launches are latency-bound, not HBM-bound "
-                    "(profiles/r01b_prof_flowchains_L0_f16x3_summary.csv)"}
+            "flops": sum(v[2] for _, v in fs), "tflops": sum(v[2] for _, v in fs) / (fs_ms / 1e3) / 1e12,
+            "frac_tensor": sum(v[2] for _, v in fs) / (fs_ms / 1e3) / 1e12 / peak_used,
+            "by_launch": {t: round(v[1], 3) for t, v in fs},
+            "note": "52 FlowSteps: per level one launch of shared-conditioning convs (W_u * u of all 13 conditional steps) and two "
+                    "fused-FlowStep launches (csrc/flowstep_tc.cu: one work item = sub-net + ActNorm / 1x1 / coupling tail of one "
+                    "step on one tile); algorithmic bytes = SURVEY 8d's per-FlowStep figures; ncu summaries under "
+                    "profiles/r02_prof_flowstep_*"}
     if tc_keys:
         a_n, a_ms, a_fl = (sum(classes[c][k] for c in tc_keys) for k in range(3))
         roofline["all_tcgen05_convs"] = {"launches": a_n, "ms": round(a_ms, 3), "tflops": round(a_fl / a_ms / 1e9, 1),

@@ -8,6 +8,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhcflow_b200.so")
+if os.environ.get("HCFLOW_LIB"):   # e.g. the wait-profiler build (HCF_BUILD_PROF=1), kept beside the product library
+    LIB_PATH = os.environ["HCFLOW_LIB"]
 
 c_float_p = C.c_void_p  # device pointers travel as integers
 

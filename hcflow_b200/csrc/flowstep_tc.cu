@@ -60,7 +60,7 @@ constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;          // + base alignment sl
 static_assert(OFF_HHI % 1024 == 0 && OFF_HLO % 1024 == 0 && OFF_W1 % 1024 == 0 && OFF_W2 % 1024 == 0 && OFF_W3 % 1024 == 0,
               "operand tiles must be 1024-byte aligned (128B swizzle atoms)");
 static_assert(SMEM_BYTES <= SMEM_LIMIT, "flowstep kernel: shared memory budget");
-constexpr int THREADS = 320;
+constexpr int THREADS = 448;    // producer, MMA issuer, 2 x 4 epilogue warps (one group per M tile), 4 tail warps
 
 struct StepDesc {
   const __half* w1; const __half* w2; const __half* w3;
@@ -80,6 +80,7 @@ struct Params {
   int* done;
   int* status;
   double* logdet;
+  long long* prof;                  // HCF_TC_PROF=1 (prof build): cycles per role / wait class summed over CTAs
 };
 
 struct Maps2 { CUtensorMap m[2]; };
@@ -106,6 +107,18 @@ __device__ __forceinline__ void mbar_wait_wd(uint32_t bar, uint32_t parity, int*
   }
 }
 #define mbar_wait(bar, parity) mbar_wait_wd((bar), (parity), p.status)
+
+// 32 accumulator columns of this thread's TMEM lane, WITHOUT the wait (several loads share one tcgen05.wait::ld)
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
 
 // ------------------------------------------------------------------------------------------------ per-pixel tails
 // h[2j] = shift, h[2j+1] = scale of coupled channel n_pass + j (AffineCouplings.py:52-57, 78-84: h[:, 0::2], h[:, 1::2])
@@ -137,14 +150,14 @@ __device__ __forceinline__ void mix(const float* __restrict__ s_w, const float (
 
 // returns the pixel's log-det contribution (forward) or 0
 template <int C>
-__device__ __forceinline__ float tail_pixel(const float (&h)[32], float* __restrict__ zp, bool forward,
+__device__ __forceinline__ float tail_pixel(const float (&h)[32], const float (&zq)[MAXC], float* __restrict__ zp, bool forward,
                                             bool has_w, bool has_next, const float* __restrict__ s_w,
                                             const float* __restrict__ s_sc, const float* __restrict__ s_b,
                                             __half* __restrict__ z16p, bool split) {
   constexpr int n_pass = C / 2;      // AffineCoupling: channels_for_nn = in_channels // 2 (AffineCouplings.py:17-18)
   float z[C];
 #pragma unroll
-  for (int i = 0; i < C; ++i) z[i] = __ldcg(zp + i);
+  for (int i = 0; i < C; ++i) z[i] = zq[i];
   float lsum = 0.f;
 #pragma unroll
   for (int i = 0; i < C; ++i) {
@@ -196,6 +209,21 @@ __device__ __forceinline__ float tail_pixel(const float (&h)[32], float* __restr
   return lsum;
 }
 
+// in-kernel wait profile (HCF_BUILD_PROF=1 build + HCF_TC_PROF=1): where each role's cycles go, per work item
+enum { FP_P_TOTAL = 0, FP_P_WEIGHTS, FP_P_DEPS, FP_P_Z1EMPTY, FP_M_TOTAL, FP_M_Z1FULL, FP_M_ISSUE1, FP_M_A2READY, FP_M_ISSUE2,
+       FP_M_A3READY, FP_M_ACC3EMPTY, FP_M_ISSUE3, FP_M_WFULL, FP_E_TOTAL, FP_E_ACC1, FP_E_BODY1, FP_E_ACC2, FP_E_BODY2, FP_E_TABLES,
+       FP_T_TOTAL, FP_T_DEPSEQ, FP_T_ACC3, FP_T_BODY, FP_T_PUBLISH, FP_LAUNCHES, FP_N };
+#ifdef HCF_TC_PROF_BUILD
+#define FS_T(var) const long long var = prof_on ? clock64() : 0ll
+#define FS_ACC(slot, a, b) do { if (prof_on) pacc[slot] += (b) - (a); } while (0)
+#define FS_FLUSH(lo, hi) do { if (prof_on) for (int i_ = (lo); i_ <= (hi); ++i_) \
+    atomicAdd((unsigned long long*)p.prof + i_, (unsigned long long)pacc[i_]); } while (0)
+#else
+#define FS_T(var) do { } while (0)
+#define FS_ACC(slot, a, b) do { } while (0)
+#define FS_FLUSH(lo, hi) do { } while (0)
+#endif
+
 // ------------------------------------------------------------------------------------------------ kernel
 __global__ void __launch_bounds__(THREADS, 1) flowstep_kernel(const __grid_constant__ Maps2 maps, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -216,7 +244,7 @@ __global__ void __launch_bounds__(THREADS, 1) flowstep_kernel(const __grid_const
     asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.m[1]) : "memory");
     mbar_init(z1_full, 1); mbar_init(z1_empty, 1);
     for (int k = 0; k < 3; ++k) { mbar_init(w_full(k), 1); mbar_init(w_empty(k), 1); }
-    mbar_init(acc1_full, 1); mbar_init(a2_ready, 128); mbar_init(acc2_full, 1); mbar_init(a3_ready, 128);
+    mbar_init(acc1_full, 1); mbar_init(a2_ready, 256); mbar_init(acc2_full, 1); mbar_init(a3_ready, 256);
     mbar_init(acc3_full, 1); mbar_init(acc3_empty, 128);
     asm volatile("st.shared.b32 [%0], %1;" ::"r"(dep_seq), "r"(0u) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -238,6 +266,12 @@ __global__ void __launch_bounds__(THREADS, 1) flowstep_kernel(const __grid_const
   };
   const bool split = p.split != 0;
   const uint32_t NB3 = (uint32_t)p.N3 * (split ? 2u : 1u);
+#ifdef HCF_TC_PROF_BUILD
+  const bool prof_on = p.prof != nullptr;
+  long long pacc[FP_N];
+#pragma unroll
+  for (int i = 0; i < FP_N; ++i) pacc[i] = 0;
+#endif
 
   if (warp == 0) {
     // =============================================================== producer
@@ -250,10 +284,12 @@ __global__ void __launch_bounds__(THREADS, 1) flowstep_kernel(const __grid_const
         const int b = tile / per_img, r = tile % per_img;
         load_deps(deps, p.done, b * per_img, r / p.tiles_x, r % p.tiles_x, p.tiles_y, p.tiles_x);
       }
+      FS_T(tp0);
       for (int seq = 0, item; (item = item_at(seq)) >= 0; ++seq) {
         const int step = item / p.n_tiles, tile = item - step * p.n_tiles;
         const int b = tile / per_img, r = tile % per_img;
         const int ty = r / p.tiles_x, tx = r % p.tiles_x;
+        FS_T(tw0);
         if (step != cur_step) {
           // the step's weight images: issued BEFORE the dependency wait (they depend on nothing)
           cur_step = step;
@@ -269,6 +305,8 @@ __global__ void __launch_bounds__(THREADS, 1) flowstep_kernel(const __grid_const
           }
           ++w_it;
         }
+        FS_T(tw1);
+        FS_ACC(FP_P_WEIGHTS, tw0, tw1);
         if (step > 0) {
           uint32_t spins = 0;
           while (!deps_ready(deps, step)) {
@@ -282,6 +320,8 @@ __global__ void __launch_bounds__(THREADS, 1) flowstep_kernel(const __grid_const
           fence_acquire_gpu();
           asm volatile("fence.proxy.async.global;" ::: "memory");
         }
+        FS_T(tw2);
+        FS_ACC(FP_P_DEPS, tw1, tw2);
         asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"(dep_seq), "r"((uint32_t)seq + 1u) : "memory");
         const int nitem = item_at(seq + 1);
         if (nitem >= 0) {
@@ -289,10 +329,16 @@ __global__ void __launch_bounds__(THREADS, 1) flowstep_kernel(const __grid_const
           const int nb = nt / per_img, nr = nt % per_img;
           load_deps(deps, p.done, nb * per_img, nr / p.tiles_x, nr % p.tiles_x, p.tiles_y, p.tiles_x);
         }
+        FS_T(tw3);
         mbar_wait(z1_empty, ((uint32_t)seq & 1u) ^ 1u);
+        FS_T(tw4);
+        FS_ACC(FP_P_Z1EMPTY, tw3, tw4);
         mbar_expect_tx(z1_full, Z1_BYTES);
         tma_load_4d(sbase + OFF_Z1, &maps.m[step & 1], z1_full, 0, tx * TW - 2, ty * TH - 2, b);
       }
+      FS_T(tp1);
+      FS_ACC(FP_P_TOTAL, tp0, tp1);
+      FS_FLUSH(FP_P_TOTAL, FP_P_Z1EMPTY);
     }
   } else if (warp == 1) {
     // =============================================================== MMA issuer
@@ -306,6 +352,7 @@ __global__ void __launch_bounds__(THREADS, 1) flowstep_kernel(const __grid_const
     const uint32_t W1_BLOCK16 = 128u * 8u;                         // one tap block of W1 ([hi 64 ; lo 64] rows) in 16-byte units
     int cur_step = -1;
     uint32_t w_it = 0;
+    FS_T(tm0);
     for (int seq = 0, item; (item = item_at(seq)) >= 0; ++seq) {
       const int step = item / p.n_tiles;
       const int nitem = item_at(seq + 1);
@@ -314,8 +361,13 @@ __global__ void __launch_bounds__(THREADS, 1) flowstep_kernel(const __grid_const
       if (new_step) { cur_step = step; ++w_it; }
       const uint32_t par = (uint32_t)seq & 1u, wpar = (w_it - 1u) & 1u;
       // ---------------- conv1: 9 taps x K=16 (hi) [+ lo] on two M tiles -> cols [m*128, m*128+128)
+      FS_T(ta0);
       mbar_wait(z1_full, par);
+      FS_T(ta1);
       if (new_step) mbar_wait(w_full(0), wpar);
+      FS_T(ta2);
+      FS_ACC(FP_M_Z1FULL, ta0, ta1);
+      FS_ACC(FP_M_WFULL, ta1, ta2);
       tc_fence_after();
       if (elect_one()) {
         const uint64_t a0 = dense + ((sbase + OFF_Z1) >> 4);
@@ -337,8 +389,12 @@ __global__ void __launch_bounds__(THREADS, 1) flowstep_kernel(const __grid_const
         if (last_of_step) umma_commit(w_empty(0));
       }
       __syncwarp();
+      FS_T(ta3);
+      FS_ACC(FP_M_ISSUE1, ta2, ta3);
       // ---------------- conv2: 1x1, K = 64
       mbar_wait(a2_ready, par);
+      FS_T(ta4);
+      FS_ACC(FP_M_A2READY, ta3, ta4);
       if (new_step) mbar_wait(w_full(1), wpar);
       tc_fence_after();
       if (elect_one()) {
@@ -358,9 +414,15 @@ __global__ void __launch_bounds__(THREADS, 1) flowstep_kernel(const __grid_const
         if (last_of_step) umma_commit(w_empty(1));
       }
       __syncwarp();
+      FS_T(ta5);
+      FS_ACC(FP_M_ISSUE2, ta4, ta5);
       // ---------------- conv3: 3x3 over the h2 halo tile -> cols [256, 256 + NB3)
       mbar_wait(a3_ready, par);
+      FS_T(ta6);
+      FS_ACC(FP_M_A3READY, ta5, ta6);
       mbar_wait(acc3_empty, par ^ 1u);
+      FS_T(ta7);
+      FS_ACC(FP_M_ACC3EMPTY, ta6, ta7);
       if (new_step) mbar_wait(w_full(2), wpar);
       tc_fence_after();
       if (elect_one()) {
@@ -382,94 +444,113 @@ __global__ void __launch_bounds__(THREADS, 1) flowstep_kernel(const __grid_const
         if (last_of_step) umma_commit(w_empty(2));
       }
       __syncwarp();
+      FS_T(ta8);
+      FS_ACC(FP_M_ISSUE3, ta7, ta8);
     }
-  } else if (warp < 6) {
-    // =============================================================== epilogues 1 and 2 (thread = linear tile pixel)
+    FS_T(tm1);
+    FS_ACC(FP_M_TOTAL, tm0, tm1);
+    if (lane == 0) FS_FLUSH(FP_M_TOTAL, FP_M_WFULL);
+  } else if (warp < 10) {
+    // =============================================================== epilogues 1 and 2 (thread = linear tile pixel;
+    // warps 2-5 drain M tile 0, warps 6-9 M tile 1)
     const int q4 = warp & 3;                       // TMEM lane quarter of this warp
     const int t = q4 * 32 + lane;                  // row within an M tile
+    const int m = (warp - 2) >> 2;                 // M tile of this warp's group
+    const int q = m * 128 + t;                     // linear pixel of the [18] x pitch-12 region
+    const bool store = q < HPIX;
+    const bool warp_live = (m * 128 + q4 * 32) < HPIX;   // (the last warp of M tile 1 holds padding rows only)
     float* s_epi = reinterpret_cast<float*>(gbase + OFF_TAB);
+    uint8_t* rowh = gbase + OFF_HHI + q * 128;
+    uint8_t* rowl = gbase + OFF_HLO + q * 128;
+    const int rr = q / PITCH, cc = q - rr * PITCH;
     int cur_step = -1;
     const float* pre = nullptr;
     int pre_ld = 0;
+    FS_T(te0);
     for (int seq = 0, item; (item = item_at(seq)) >= 0; ++seq) {
       const int step = item / p.n_tiles, tile = item - step * p.n_tiles;
       const int b = tile / per_img, r = tile % per_img;
       const int y0 = (r / p.tiles_x) * TH, x0 = (r % p.tiles_x) * TW;
       const uint32_t par = (uint32_t)seq & 1u;
+      FS_T(tb0);
       if (step != cur_step) {
         cur_step = step;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         const int et = threadIdx.x - 64;
         s_epi[et] = __ldg(p.tabs + (size_t)step * TAB_FLOATS + et);
-        s_epi[128 + et] = __ldg(p.tabs + (size_t)step * TAB_FLOATS + 128 + et);
         pre = ldg_ptr(&(p.steps + step)->pre);
         pre_ld = __ldg(&(p.steps + step)->pre_ld);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      // the two rows of this thread: q = m * 128 + t -> region pixel (q / 12, q % 12), image pixel (y0 - 1 + ., x0 - 1 + .)
-      bool inimg[2];
-      uint32_t gpix[2];
+      FS_T(tb1);
+      FS_ACC(FP_E_TABLES, tb0, tb1);
+      // region pixel (rr, cc) -> image pixel (y0 - 1 + rr, x0 - 1 + cc)
+      const int gy = y0 - 1 + rr, gx = x0 - 1 + cc;
+      const bool inimg = store && cc < 10 && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
+      const float* prep = (pre != nullptr && inimg) ? pre + (size_t)((b * p.H + gy) * p.W + gx) * pre_ld : nullptr;
+      // the W_u * u addend of conv1 (conditional steps): the first half of the row is fetched BEFORE the accumulator
+      // wait, the second half while the first is processed (thread = pixel: 256 contiguous bytes per thread)
+      float4 pa[8];
+      if (prep) {
 #pragma unroll
-      for (int m = 0; m < 2; ++m) {
-        const int q = m * 128 + t;
-        const int rr = q / PITCH, cc = q - rr * PITCH;
-        const int gy = y0 - 1 + rr, gx = x0 - 1 + cc;
-        inimg[m] = q < HPIX && cc < 10 && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
-        gpix[m] = inimg[m] ? (uint32_t)((b * p.H + gy) * p.W + gx) : 0u;
+        for (int j = 0; j < 8; ++j) pa[j] = __ldg(reinterpret_cast<const float4*>(prep) + j);
       }
 #pragma unroll 1
       for (int stage = 0; stage < 2; ++stage) {
+        FS_T(tb2);
         mbar_wait(stage == 0 ? acc1_full : acc2_full, par);
+        FS_T(tb3);
+        FS_ACC(stage == 0 ? FP_E_ACC1 : FP_E_ACC2, tb2, tb3);
         tc_fence_after();
         const float* s_bias = s_epi + stage * 128;
         const float* s_scale = s_bias + 64;
+        const bool keep = stage == 0 ? true : inimg;       // h2 outside the image is conv3's zero padding
+        const bool add = stage == 0 && prep != nullptr;
+        if (warp_live) {
 #pragma unroll 1
-        for (int m = 0; m < 2; ++m) {
-          const int q = m * 128 + t;
-          const bool store = q < HPIX;
-          const bool keep = stage == 0 ? true : inimg[m];       // h2 outside the image is conv3's zero padding
-          const float* prep = (stage == 0 && pre != nullptr && inimg[m]) ? pre + (size_t)gpix[m] * pre_ld : nullptr;
-          uint8_t* rowh = gbase + OFF_HHI + q * 128;
-          uint8_t* rowl = gbase + OFF_HLO + q * 128;
-#pragma unroll 1
-          for (int cg = 0; cg < 4; ++cg) {                      // 16 channels at a time
-            float v[16];
-            const uint32_t tcol = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(m * 128 + cg * 16);
-            tmem_ld16(tcol, v);
-            if (split) {
-              float lo[16];
-              tmem_ld16(tcol + 64u, lo);
+          for (int half = 0; half < 2; ++half) {                // 32 channels at a time: ONE TMEM round trip
+            float v[32];
+            {
+              const uint32_t tcol = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(m * 128 + half * 32);
+              uint32_t rv[32], rl[32];
+              tmem_ld32_nowait(tcol, rv);
+              if (split) tmem_ld32_nowait(tcol + 64u, rl);
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = fmaf(lo[j], 1.0f / 2048.0f, v[j]);
+              for (int j = 0; j < 32; ++j)
+                v[j] = split ? fmaf(__uint_as_float(rl[j]), 1.0f / 2048.0f, __uint_as_float(rv[j])) : __uint_as_float(rv[j]);
             }
-            if (prep) {
+            if (add) {
 #pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) {
-                const float4 a = __ldcg(reinterpret_cast<const float4*>(prep + cg * 16 + j4 * 4));
-                v[4 * j4] += a.x; v[4 * j4 + 1] += a.y; v[4 * j4 + 2] += a.z; v[4 * j4 + 3] += a.w;
+              for (int j = 0; j < 8; ++j) {
+                v[4 * j] += pa[j].x; v[4 * j + 1] += pa[j].y; v[4 * j + 2] += pa[j].z; v[4 * j + 3] += pa[j].w;
+              }
+              if (half == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) pa[j] = __ldg(reinterpret_cast<const float4*>(prep) + 8 + j);
               }
             }
-            uint32_t hi[8], lo8[8];
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-              float a = fmaxf((v[j] + s_bias[cg * 16 + j]) * s_scale[cg * 16 + j], 0.f);
-              float c = fmaxf((v[j + 1] + s_bias[cg * 16 + j + 1]) * s_scale[cg * 16 + j + 1], 0.f);
-              if (!keep) { a = 0.f; c = 0.f; }
-              a = fminf(a, 65504.0f); c = fminf(c, 65504.0f);
-              const __half2 hh = __floats2half2_rn(a, c);
-              const float2 hf = __half22float2(hh);
-              const __half2 ll = __floats2half2_rn((a - hf.x) * 2048.0f, (c - hf.y) * 2048.0f);
-              hi[j >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
-              lo8[j >> 1] = *reinterpret_cast<const uint32_t*>(&ll);
-            }
-            if (store) {
-              // 128B swizzle: 16-byte chunk index XOR (row & 7); this group's chunks are 2 cg and 2 cg + 1
-              const int c0 = ((2 * cg) ^ (q & 7)) * 16, c1 = ((2 * cg + 1) ^ (q & 7)) * 16;
-              *reinterpret_cast<uint4*>(rowh + c0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              *reinterpret_cast<uint4*>(rowh + c1) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-              if (split) {
-                *reinterpret_cast<uint4*>(rowl + c0) = make_uint4(lo8[0], lo8[1], lo8[2], lo8[3]);
-                *reinterpret_cast<uint4*>(rowl + c1) = make_uint4(lo8[4], lo8[5], lo8[6], lo8[7]);
+            for (int c8 = 0; c8 < 4; ++c8) {                    // one 16-byte chunk (8 channels) per plane at a time
+              uint32_t hi[4], lo4[4];
+#pragma unroll
+              for (int j = 0; j < 8; j += 2) {
+                const int ch = half * 32 + c8 * 8 + j;
+                float a = fmaxf((v[c8 * 8 + j] + s_bias[ch]) * s_scale[ch], 0.f);
+                float c = fmaxf((v[c8 * 8 + j + 1] + s_bias[ch + 1]) * s_scale[ch + 1], 0.f);
+                if (!keep) { a = 0.f; c = 0.f; }
+                a = fminf(a, 65504.0f); c = fminf(c, 65504.0f);
+                const __half2 hh = __floats2half2_rn(a, c);
+                const float2 hf = __half22float2(hh);
+                const __half2 ll = __floats2half2_rn((a - hf.x) * 2048.0f, (c - hf.y) * 2048.0f);
+                hi[j >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+                lo4[j >> 1] = *reinterpret_cast<const uint32_t*>(&ll);
+              }
+              if (store) {
+                // 128B swizzle: 16-byte chunk index XOR (row & 7)
+                const int co = (((half * 4 + c8) ^ (q & 7))) * 16;
+                *reinterpret_cast<uint4*>(rowh + co) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                if (split) *reinterpret_cast<uint4*>(rowl + co) = make_uint4(lo4[0], lo4[1], lo4[2], lo4[3]);
               }
             }
           }
@@ -477,8 +558,13 @@ __global__ void __launch_bounds__(THREADS, 1) flowstep_kernel(const __grid_const
         fence_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
         tc_fence_before();
         mbar_arrive(stage == 0 ? a2_ready : a3_ready);
+        FS_T(tb4);
+        FS_ACC(stage == 0 ? FP_E_BODY1 : FP_E_BODY2, tb3, tb4);
       }
     }
+    FS_T(te1);
+    FS_ACC(FP_E_TOTAL, te0, te1);
+    if (threadIdx.x == 64) FS_FLUSH(FP_E_TOTAL, FP_E_TABLES);
   } else {
     // =============================================================== tail (thread = output pixel)
     const int q4 = warp & 3;
@@ -490,6 +576,7 @@ __global__ void __launch_bounds__(THREADS, 1) flowstep_kernel(const __grid_const
     float* s_b = s_sc + MAXC;
     int cur_step = -1, has_w = 0, has_next = 0;
     const int C = p.C;
+    FS_T(tt0);
     for (int seq = 0, item; (item = item_at(seq)) >= 0; ++seq) {
       const int step = item / p.n_tiles, tile = item - step * p.n_tiles;
       const int b = tile / per_img, r = tile % per_img;
@@ -499,14 +586,34 @@ __global__ void __launch_bounds__(THREADS, 1) flowstep_kernel(const __grid_const
       if (step != cur_step) {
         cur_step = step;
         asm volatile("bar.sync 2, 128;" ::: "memory");
-        const int et = threadIdx.x - 192;
+        const int et = threadIdx.x - 320;
         const float* src = p.tabs + (size_t)step * TAB_FLOATS + 256;
         for (int i = et; i < 64 + TAIL_FLOATS; i += 128) s_tab[i] = __ldg(src + i);
         has_w = __ldg(&(p.steps + step)->has_w);
         has_next = __ldg(&(p.steps + step)->has_next);
         asm volatile("bar.sync 2, 128;" ::: "memory");
       }
+      // the producer acquired this item's inputs (dependency counters + fence) before conv1 could run; z of this tile
+      // was last written by this tile's previous step, which is ordered before that acquire.  z is fetched now, long
+      // before the accumulator is ready
+      FS_T(tc0);
+      {
+        uint32_t seen;
+        do {
+          asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(seen) : "r"(dep_seq) : "memory");
+        } while (seen <= (uint32_t)seq);
+      }
+      FS_T(tc1);
+      FS_ACC(FP_T_DEPSEQ, tc0, tc1);
+      const uint32_t pix = in ? (uint32_t)((b * p.H + gy) * p.W + gx) : 0u;
+      float* zp = p.z + (size_t)pix * p.z_ld;
+      float zq[MAXC];
+#pragma unroll
+      for (int i = 0; i < MAXC; ++i) zq[i] = (in && i < C) ? __ldcg(zp + i) : 0.f;
+      FS_T(tc2);
       mbar_wait(acc3_full, par);
+      FS_T(tc3);
+      FS_ACC(FP_T_ACC3, tc2, tc3);
       tc_fence_after();
       float h[32];
 #pragma unroll
@@ -530,25 +637,15 @@ __global__ void __launch_bounds__(THREADS, 1) flowstep_kernel(const __grid_const
       }
       tc_fence_before();
       mbar_arrive(acc3_empty);
-      // the producer acquired this item's inputs (dependency counters + fence) before conv1 could run; z of this tile
-      // was last written by this tile's previous step, which is ordered before that acquire
-      {
-        uint32_t seen;
-        do {
-          asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(seen) : "r"(dep_seq) : "memory");
-        } while (seen <= (uint32_t)seq);
-      }
       float lsum = 0.f;
       if (in) {
-        const uint32_t pix = (uint32_t)((b * p.H + gy) * p.W + gx);
-        float* zp = p.z + (size_t)pix * p.z_ld;
         __half* z16p = has_next ? p.z16[(step + 1) & 1] + (size_t)pix * 32 : nullptr;
         const bool fw = p.forward != 0, hw = has_w != 0, hn = has_next != 0;
         switch (C) {
-          case 6: lsum = tail_pixel<6>(h, zp, fw, hw, hn, s_w, s_sc, s_b, z16p, split); break;
-          case 12: lsum = tail_pixel<12>(h, zp, fw, hw, hn, s_w, s_sc, s_b, z16p, split); break;
-          case 21: lsum = tail_pixel<21>(h, zp, fw, hw, hn, s_w, s_sc, s_b, z16p, split); break;
-          case 24: lsum = tail_pixel<24>(h, zp, fw, hw, hn, s_w, s_sc, s_b, z16p, split); break;
+          case 6: lsum = tail_pixel<6>(h, zq, zp, fw, hw, hn, s_w, s_sc, s_b, z16p, split); break;
+          case 12: lsum = tail_pixel<12>(h, zq, zp, fw, hw, hn, s_w, s_sc, s_b, z16p, split); break;
+          case 21: lsum = tail_pixel<21>(h, zq, zp, fw, hw, hn, s_w, s_sc, s_b, z16p, split); break;
+          case 24: lsum = tail_pixel<24>(h, zq, zp, fw, hw, hn, s_w, s_sc, s_b, z16p, split); break;
           default: break;   // (the host only creates plans for these channel counts)
         }
       }
@@ -559,8 +656,20 @@ __global__ void __launch_bounds__(THREADS, 1) flowstep_kernel(const __grid_const
         if (lane == 0) atomicAdd(p.logdet + b, s);
       }
       // publish: every tail thread's stores happen before the barrier; one thread releases them at gpu scope
+      FS_T(tc4);
+      FS_ACC(FP_T_BODY, tc3, tc4);
       asm volatile("bar.sync 2, 128;" ::: "memory");
       if (t == 0) red_release_add(p.done + tile, 1);
+      FS_T(tc5);
+      FS_ACC(FP_T_PUBLISH, tc4, tc5);
+    }
+    FS_T(tt1);
+    FS_ACC(FP_T_TOTAL, tt0, tt1);
+    if (t == 0) {
+      FS_FLUSH(FP_T_TOTAL, FP_T_PUBLISH);
+#ifdef HCF_TC_PROF_BUILD
+      if (prof_on && blockIdx.x == 0) atomicAdd((unsigned long long*)p.prof + FP_LAUNCHES, 1ull);
+#endif
     }
   }
   tc_fence_before();
@@ -593,6 +702,7 @@ struct hcf_flowstep_plan {
   hcf::fs::StepDesc* d_steps;
   float* d_tabs;
   std::vector<hcf_flowstep>* src;     // the caller's per-step pointers (for refresh)
+  long long* d_prof;
   dim3 grid;
 };
 
@@ -716,6 +826,10 @@ extern "C" int hcf_flowstep_chain_create(const hcf_flowstep_chain_args* a, hcf_f
     hcf_flowstep_chain_destroy(pl);
     return HCF_EINVAL;
   }
+  if (getenv("HCF_TC_PROF")) {
+    if (cudaMalloc(&pl->d_prof, sizeof(long long) * fs::FP_N) == cudaSuccess) cudaMemset(pl->d_prof, 0, sizeof(long long) * fs::FP_N);
+    p.prof = pl->d_prof;
+  }
   const int sms = tc::num_sms();
   pl->grid = dim3((unsigned)(p.n_tiles < sms ? p.n_tiles : sms));
   e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fs::flowstep_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -800,6 +914,24 @@ extern "C" int hcf_flowstep_chain_run(const hcf_flowstep_plan* pl, void* stream)
 
 extern "C" void hcf_flowstep_chain_destroy(hcf_flowstep_plan* pl) {
   if (!pl) return;
+  if (pl->d_prof) {   // HCF_TC_PROF=1: average cycles per work item, by role and wait class
+    long long h[hcf::fs::FP_N];
+    cudaDeviceSynchronize();
+    if (cudaMemcpy(h, pl->d_prof, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      static const char* names[hcf::fs::FP_N] = {"P.total", "P.weights", "P.deps", "P.z1_empty", "M.total", "M.z1_full", "M.issue1",
+                                                 "M.a2_ready", "M.issue2", "M.a3_ready", "M.acc3_empty", "M.issue3", "M.w_full",
+                                                 "E.total", "E.acc1", "E.body1", "E.acc2", "E.body2", "E.tables", "T.total",
+                                                 "T.dep_seq", "T.acc3", "T.body", "T.publish", "launches"};
+      const double items = (double)pl->p.n_items / pl->grid.x;
+      const double launches = h[hcf::fs::FP_LAUNCHES] > 0 ? (double)h[hcf::fs::FP_LAUNCHES] : 1.0;
+      fprintf(stderr, "[hcf prof] flowstep chain steps=%d tiles=%d C=%d fwd=%d items/CTA=%.1f launches=%.0f; cycles per item:",
+              pl->p.n_steps, pl->p.n_tiles, pl->p.C, pl->p.forward, items, launches);
+      for (int i = 0; i < hcf::fs::FP_LAUNCHES; ++i)
+        fprintf(stderr, " %s=%.0f", names[i], (double)h[i] / pl->grid.x / launches / items);
+      fprintf(stderr, "\n");
+    }
+    cudaFree(pl->d_prof);
+  }
   if (pl->d_steps) cudaFree(pl->d_steps);
   if (pl->d_tabs) cudaFree(pl->d_tabs);
   delete pl->src;
