@@ -74,6 +74,7 @@ struct Params {
   int C, n_pass, N3, split, forward;
   int w3_bytes;
   float* z; int z_ld;
+  int z_vec;                        // z rows allow 16-byte accesses over ceil4(C) channels
   __half* z16[2];
   const StepDesc* steps;
   const float* tabs;                // [n_steps][TAB_FLOATS]
@@ -153,7 +154,7 @@ template <int C>
 __device__ __forceinline__ float tail_pixel(const float (&h)[32], const float (&zq)[MAXC], float* __restrict__ zp, bool forward,
                                             bool has_w, bool has_next, const float* __restrict__ s_w,
                                             const float* __restrict__ s_sc, const float* __restrict__ s_b,
-                                            __half* __restrict__ z16p, bool split) {
+                                            __half* __restrict__ z16p, bool split, bool vec) {
   constexpr int n_pass = C / 2;      // AffineCoupling: channels_for_nn = in_channels // 2 (AffineCouplings.py:17-18)
   float z[C];
 #pragma unroll
@@ -196,14 +197,34 @@ __device__ __forceinline__ float tail_pixel(const float (&h)[32], const float (&
 #pragma unroll
     for (int i = 0; i < C; ++i) y[i] = y[i] * s_sc[i] - s_b[i];
   }
+  if (vec) {          // 16-byte stores for the full groups of four channels, scalar stores for the remainder
 #pragma unroll
-  for (int i = 0; i < C; ++i) {
-    __stcg(zp + i, y[i]);
-    if (z16p && i < n_pass) {    // the next step's conv1 operand: [hi 16 | lo 16] halves per pixel
-      const float v = fminf(fmaxf(y[i], -65504.0f), 65504.0f);
-      const __half hh = __float2half_rn(v);
-      z16p[i] = hh;
-      if (split) z16p[16 + i] = __float2half_rn((v - __half2float(hh)) * 2048.0f);
+    for (int i = 0; i + 3 < C; i += 4)
+      __stcg(reinterpret_cast<float4*>(zp + i), make_float4(y[i], y[i + 1], y[i + 2], y[i + 3]));
+#pragma unroll
+    for (int i = C / 4 * 4; i < C; ++i) __stcg(zp + i, y[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < C; ++i) __stcg(zp + i, y[i]);
+  }
+  if (z16p) {         // the next step's conv1 operand: [hi 16 | lo 16] halves per pixel, four 16-byte stores
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+      const float a = i < n_pass ? fminf(fmaxf(y[i < C ? i : 0], -65504.0f), 65504.0f) : 0.f;
+      const float c = i + 1 < n_pass ? fminf(fmaxf(y[i + 1 < C ? i + 1 : 0], -65504.0f), 65504.0f) : 0.f;
+      const __half2 hh = __floats2half2_rn(a, c);
+      const float2 hf = __half22float2(hh);
+      const __half2 ll = __floats2half2_rn((a - hf.x) * 2048.0f, (c - hf.y) * 2048.0f);
+      hi[i >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+      lo[i >> 1] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    uint4* d = reinterpret_cast<uint4*>(z16p);
+    __stcg(d, make_uint4(hi[0], hi[1], hi[2], hi[3]));
+    __stcg(d + 1, make_uint4(hi[4], hi[5], hi[6], hi[7]));
+    if (split) {
+      __stcg(d + 2, make_uint4(lo[0], lo[1], lo[2], lo[3]));
+      __stcg(d + 3, make_uint4(lo[4], lo[5], lo[6], lo[7]));
     }
   }
   return lsum;
@@ -607,9 +628,21 @@ __global__ void __launch_bounds__(THREADS, 1) flowstep_kernel(const __grid_const
       FS_ACC(FP_T_DEPSEQ, tc0, tc1);
       const uint32_t pix = in ? (uint32_t)((b * p.H + gy) * p.W + gx) : 0u;
       float* zp = p.z + (size_t)pix * p.z_ld;
+      // z of this pixel: 16-byte accesses when the view allows it (a warp's scalar access to 32 pixel rows costs one
+      // sector per lane and channel: measured, the tail was bound by exactly that -- 48 scattered stores per pixel)
+      const bool vec = p.z_vec != 0;
       float zq[MAXC];
+      if (vec) {
 #pragma unroll
-      for (int i = 0; i < MAXC; ++i) zq[i] = (in && i < C) ? __ldcg(zp + i) : 0.f;
+        for (int i = 0; i < MAXC; i += 4) {
+          float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (in && i < C) t4 = __ldcg(reinterpret_cast<const float4*>(zp + i));
+          zq[i] = t4.x; zq[i + 1] = t4.y; zq[i + 2] = t4.z; zq[i + 3] = t4.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) zq[i] = (in && i < C) ? __ldcg(zp + i) : 0.f;
+      }
       FS_T(tc2);
       mbar_wait(acc3_full, par);
       FS_T(tc3);
@@ -642,10 +675,10 @@ __global__ void __launch_bounds__(THREADS, 1) flowstep_kernel(const __grid_const
         __half* z16p = has_next ? p.z16[(step + 1) & 1] + (size_t)pix * 32 : nullptr;
         const bool fw = p.forward != 0, hw = has_w != 0, hn = has_next != 0;
         switch (C) {
-          case 6: lsum = tail_pixel<6>(h, zq, zp, fw, hw, hn, s_w, s_sc, s_b, z16p, split); break;
-          case 12: lsum = tail_pixel<12>(h, zq, zp, fw, hw, hn, s_w, s_sc, s_b, z16p, split); break;
-          case 21: lsum = tail_pixel<21>(h, zq, zp, fw, hw, hn, s_w, s_sc, s_b, z16p, split); break;
-          case 24: lsum = tail_pixel<24>(h, zq, zp, fw, hw, hn, s_w, s_sc, s_b, z16p, split); break;
+          case 6: lsum = tail_pixel<6>(h, zq, zp, fw, hw, hn, s_w, s_sc, s_b, z16p, split, vec); break;
+          case 12: lsum = tail_pixel<12>(h, zq, zp, fw, hw, hn, s_w, s_sc, s_b, z16p, split, vec); break;
+          case 21: lsum = tail_pixel<21>(h, zq, zp, fw, hw, hn, s_w, s_sc, s_b, z16p, split, vec); break;
+          case 24: lsum = tail_pixel<24>(h, zq, zp, fw, hw, hn, s_w, s_sc, s_b, z16p, split, vec); break;
           default: break;   // (the host only creates plans for these channel counts)
         }
       }
@@ -777,6 +810,7 @@ extern "C" int hcf_flowstep_chain_create(const hcf_flowstep_chain_args* a, hcf_f
   p.forward = a->forward ? 1 : 0;
   p.w3_bytes = 9 * p.N3 * (p.split ? 2 : 1) * 128;
   p.z = a->z; p.z_ld = a->z_ld;
+  p.z_vec = (aligned16(a->z) && a->z_ld % 4 == 0 && (a->C + 3) / 4 * 4 <= a->z_ld) ? 1 : 0;
   p.z16[0] = reinterpret_cast<__half*>(a->z16_a);
   p.z16[1] = reinterpret_cast<__half*>(a->z16_b);
   p.done = a->done;
