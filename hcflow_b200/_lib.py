@@ -136,6 +136,22 @@ SYMBOLS = {
     "hcf_flowstep_chain_set_status": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hcf_flowstep_chain_run": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hcf_flowstep_chain_destroy": (None, [C.c_void_p]),
+    "hcf_conv_wgrad": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                 C.c_int32, C.c_void_p, C.c_void_p]),
+    "hcf_channel_sum": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
+    "hcf_affine_act_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "hcf_affine_act_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_int64, C.c_int32, C.c_void_p]),
+    "hcf_coupling_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                   C.c_void_p]),
+    "hcf_coupling_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                   C.c_int64, C.c_int32, C.c_void_p]),
+    "hcf_gauss_logp_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
+    "hcf_gauss_logp_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_int64, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hcf_axpby": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_float, C.c_void_p, C.c_int64, C.c_void_p]),
+    "hcf_quantize8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "hcf_downsample_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "hcf_step_inverse": (C.c_int, [C.POINTER(StepArgs), C.c_void_p]),
     "hcf_step_forward_head": (C.c_int, [C.POINTER(StepArgs), C.c_void_p]),
     "hcf_step_forward_coupling": (C.c_int, [C.POINTER(StepArgs), C.c_void_p]),

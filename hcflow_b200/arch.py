@@ -194,6 +194,15 @@ class HCFlowNet_SR(_HCFlowBase):
         return self._forward_nll(hr, lr, dequant_noise)
 
     def _forward_nll(self, hr, lr, dequant_noise):
+        if torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or (hr is not None and hr.requires_grad)):
+            # training (HCFlow_SR_model.py:184-203 optimize_parameters): the same ops as torch.autograd.Function
+            # extensions with CUDA forward + backward kernels (hcflow_b200/autograd.py); the fused engine is inference-only
+            from . import autograd as ag
+            if hr is None or lr is None:
+                raise ValueError("hr and lr are required")
+            if not hr.is_cuda:
+                raise RuntimeError("hcflow_b200 runs on CUDA tensors only (no CPU fallback)")
+            return ag.sr_forward_nll(self, hr.to(torch.float32), lr.to(torch.float32), dequant_noise)
         hr = self._check(hr, "hr")
         lr = self._check(lr, "lr")
         B, _, H, W = hr.shape

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhcflow_b200.so")
-SOURCES = ["api.cu", "conv_fp32.cu", "conv_tc.cu", "flow_ops.cu", "flowstep_tc.cu", "layout_ops.cu"]
+SOURCES = ["api.cu", "conv_fp32.cu", "conv_tc.cu", "flow_ops.cu", "flowstep_tc.cu", "grad_ops.cu", "layout_ops.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

@@ -30,7 +30,7 @@ def pack_conv_weight(w, seg_channels, npad):
     cout, cin, ks, _ = w.shape
     assert sum(seg_channels) == cin, (seg_channels, cin)
     kpad = sum(seg_pad(c) for c in seg_channels)
-    out = torch.zeros(ks * ks, kpad, npad, dtype=torch.float32)
+    out = torch.zeros(ks * ks, kpad, npad, dtype=torch.float32, device=w.device)   # (device-agnostic: the training path packs on the GPU)
     wt = w.detach().float().permute(2, 3, 1, 0).reshape(ks * ks, cin, cout)  # [tap, cin, cout]
     src = 0
     dst = 0

@@ -69,16 +69,18 @@ def synthetic_state_dict(template, seed=1):
 # stress fixtures (tests/golden/*_stress.pt, oracle/make_golden.py): flow depth and scales chosen so that the coupling
 # outputs reach |h| ~ 0.8 .. 0.9 (a trained flow's order of magnitude) while the un-clamped HR stays O(10)
 STRESS = {
-    "sr_x4_stress": {"cfg": "sr_x4", "K": 8, "after": [4, 4], "s_weight": 100.0, "s_bias": 5.0},
-    "sr_x8_stress": {"cfg": "sr_x8", "K": 8, "after": [4, 4, 4], "s_weight": 100.0, "s_bias": 5.0},
-    "rescaling_x4_stress": {"cfg": "rescaling_x4", "K": None, "after": None, "s_weight": 8.0, "s_bias": 3.0},
+    "sr_x4_stress": {"cfg": "sr_x4", "K": 8, "after": [4, 4], "s_weight": 100.0, "s_bias": 5.0, "s_prior_mean": 5.0},
+    "sr_x8_stress": {"cfg": "sr_x8", "K": 8, "after": [4, 4, 4], "s_weight": 100.0, "s_bias": 5.0, "s_prior_mean": 5.0},
+    "rescaling_x4_stress": {"cfg": "rescaling_x4", "K": None, "after": None, "s_weight": 8.0, "s_bias": 3.0, "s_prior_mean": 3.0},
 }
 
 
-def stress_state_dict(sd, s_weight, s_bias=1.0, s_prior=1.0):
+def stress_state_dict(sd, s_weight, s_bias=1.0, s_prior=1.0, s_prior_mean=1.0):
     """Stress variant of a synthetic state dict: the coupling sub-nets' last conv (zero-initialised in the reference,
     0.002 * N(0,1) here) scaled by ``s_weight`` (its bias / logs by ``s_bias``) so that the coupling outputs h become
-    O(1) like a trained flow's, the prior conv's weights by ``s_prior``.  Only usable on a SHALLOW flow
+    O(1) like a trained flow's, the prior conv's weights by ``s_prior`` and its MEAN rows (output channels 0::2,
+    ConditionalFlow.py:62) by ``s_prior_mean`` on top, so that the encoder feature's rounding reaches z through an O(1)
+    prior mean as well.  Only usable on a SHALLOW flow
     (options.shrink_config): 52 steps with O(1) couplings diverge."""
     out = {}
     for k, v in sd.items():
@@ -86,7 +88,11 @@ def stress_state_dict(sd, s_weight, s_bias=1.0, s_prior=1.0):
         if (".affine.f.conv3." in k and "actnorm" not in k) or ".affine.f.conv5." in k:
             out[k] = v * (s_weight if leaf == "weight" else s_bias)
         elif k.endswith("_condFlow.f.weight"):
-            out[k] = v * s_prior
+            w = v * s_prior
+            if s_prior_mean != 1.0:
+                w = w.clone()
+                w[0::2] = w[0::2] * s_prior_mean
+            out[k] = w
         else:
             out[k] = v
     return out

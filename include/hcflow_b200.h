@@ -355,6 +355,43 @@ int hcf_upsample_nearest(const hcf_squeeze_args* a, int32_t shift, void* stream)
 int hcf_gauss_logp_const(const float* x, const float* mean, float logs, int32_t B, int32_t n,
                          double* logdet, void* stream);
 
+/* ---- training path (csrc/grad_ops.cu): the backward halves of the hot-path ops, surfaced as torch.autograd.Function
+ * extensions by hcflow_b200/autograd.py.  They replace what torch autograd records for the reference's modules in
+ * HCFlow_SR_model.py:184-218 (optimize_parameters: nll.backward()): conv2d backward (Basic.py:14-72, 360-383), ActNorm
+ * (ActNorms.py:45-94), the affine coupling (AffineCouplings.py:28-87), GaussianDiag.logp (Basic.py:79-93), the residual
+ * scale-adds (Basic.py:383, 398), F.interpolate's adjoint (FlowNet_SR_x4.py:98) and Quant (Basic.py:186-198).
+ * All tensors are dense fp32 NHWC ([npix, C] row-major) unless a row pitch is given.  dx of a conv is hcf_conv_fp32 on
+ * dy with the flipped / transposed weights. */
+/* dw[co][ci][ky][kx] = sum_pix dy[pix, co] * x[pix shifted by (ky, kx), ci]  (zero padding); dw is overwritten */
+int hcf_conv_wgrad(const float* x, int32_t x_ld, const float* dy, int32_t dy_ld, int32_t B, int32_t H, int32_t W, int32_t Cin,
+                   int32_t Cout, int32_t ks, float* dw, void* stream);
+/* out[c] = sum over pixels of y[pix, c] (a conv's bias gradient) */
+int hcf_channel_sum(const float* y, int32_t ld, int32_t C, int64_t npix, float* out, void* stream);
+/* y = act((x + bias[c]) * scale[c]); bias / scale may be NULL; act = HCF_ACT_* */
+int hcf_affine_act_fwd(const float* x, const float* bias, const float* scale, int32_t act, float* y, int64_t npix, int32_t C,
+                       void* stream);
+/* dx = dy * act'(.) * scale; dbias[c] = sum dx; dscale[c] = sum dy * act'(.) * (x + bias) (either may be NULL) */
+int hcf_affine_act_bwd(const float* dy, const float* x, const float* bias, const float* scale, int32_t act, float* dx,
+                       float* dbias, float* dscale, int64_t npix, int32_t C, void* stream);
+/* affine coupling on the nc coupled channels, h = [shift0, scale0, shift1, ...] (2 nc channels):
+ * forward out = (z2 + shift) * exp(ls), lsum[img] += sum ls (lsum may be NULL); inverse out = z2 * exp(-ls) - shift */
+int hcf_coupling_fwd(const float* z2, const float* h, int32_t nc, int32_t inverse, float* out, double* lsum, int64_t npix,
+                     int32_t pix_per_img, void* stream);
+int hcf_coupling_bwd(const float* dout, const float* dlsum, const float* z2, const float* h, int32_t nc, int32_t inverse,
+                     float* dz2, float* dh, int64_t npix, int32_t pix_per_img, void* stream);
+/* out[img] += sum -0.5 (2 logs + (x - mean)^2 / exp(2 logs) + ln 2 pi); logs == NULL: the constant logs_const */
+int hcf_gauss_logp_fwd(const float* x, const float* mean, const float* logs, float logs_const, int32_t B, int64_t per_img,
+                       double* out, void* stream);
+/* g[img] = d loss / d out[img] (fp32); dx / dmean / dlogs may be NULL */
+int hcf_gauss_logp_bwd(const float* g, const float* x, const float* mean, const float* logs, float logs_const, int32_t B,
+                       int64_t per_img, float* dx, float* dmean, float* dlogs, void* stream);
+/* y = alpha a + beta b (b may be NULL) */
+int hcf_axpby(const float* a, float alpha, const float* b, float beta, float* y, int64_t n, void* stream);
+/* y = round(clamp(x, 0, 1) * 255) / 255 */
+int hcf_quantize8(const float* x, float* y, int64_t n, void* stream);
+/* adjoint of nearest up-sampling by 2^shift: dst [B,H,W,C] = block sums of src [B, H << shift, W << shift, C] */
+int hcf_downsample_sum(const float* src, float* dst, int32_t B, int32_t H, int32_t W, int32_t C, int32_t shift, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

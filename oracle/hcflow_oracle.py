@@ -76,9 +76,21 @@ def haar_reverse(x, haar_weights):
     return F.conv_transpose2d(out, haar_weights.to(x.dtype), None, stride=2, groups=C)
 
 
+class _Quant(torch.autograd.Function):
+    """Basic.py:186-198: clamp to [0,1], round to 8 bit; the backward passes the gradient straight through."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return (torch.clamp(x, 0, 1) * 255.0).round() / 255.0
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
 def quantize(x):
-    """Basic.py:186-192: clamp to [0,1], round to 8 bit."""
-    return (torch.clamp(x, 0, 1) * 255.0).round() / 255.0
+    """Basic.py:186-202 (Quantization module = Quant.apply)."""
+    return _Quant.apply(x)
 
 
 def gaussian_logp(mean, logs, x):

@@ -108,7 +108,7 @@ def main():
         net = build_reference(networks, opt)
         sd = synth.synthetic_state_dict(net.state_dict(), seed=1)
         if stress:
-            sd = synth.stress_state_dict(sd, stress["s_weight"], stress["s_bias"])
+            sd = synth.stress_state_dict(sd, stress["s_weight"], stress["s_bias"], s_prior_mean=stress["s_prior_mean"])
         net.load_state_dict(sd, strict=True)
         mark_inited(net)
         scale = opt["scale"]

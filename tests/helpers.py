@@ -29,7 +29,7 @@ def net_and_weights(cfg, seed=1):
         net = build_net(opt)
         sd = synth.synthetic_state_dict(net.state_dict(), seed=seed)
         if stress:
-            sd = synth.stress_state_dict(sd, stress["s_weight"], stress["s_bias"])
+            sd = synth.stress_state_dict(sd, stress["s_weight"], stress["s_bias"], s_prior_mean=stress["s_prior_mean"])
         net.load_state_dict(sd, strict=True)
         net.eval()
         _CACHE[key] = (opt, net, sd)

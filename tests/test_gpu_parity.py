@@ -1039,3 +1039,91 @@ def test_fused_flowstep_kernel_matches_oracle(case, forward, split, report):
     assert err < (5e-5 if split else 2e-2), (name, err)
     if forward:
         assert rec["logdet_abs"] < (2e-3 if split else 0.5) * max(1.0, rec["logdet"] / 1000.0), rec
+
+
+# ------------------------------------------------------------------------------ training path (autograd.Function extensions)
+def _small_train_net(cfg="sr_x4", stress=False):
+    from hcflow_b200 import options as popt2
+    opt = popt2.shrink_config(popt2.load_config(cfg), K=4, after=[2, 2] if cfg == "sr_x4" else [2, 2, 2], rrdb_nb=[1, 1])
+    net = build_net(opt)
+    sd = synth.synthetic_state_dict(net.state_dict(), seed=3)
+    if stress:
+        sd = synth.stress_state_dict(sd, 50.0, 5.0, s_prior_mean=5.0)
+    net.load_state_dict(sd, strict=True)
+    return opt, net, sd
+
+
+@pytest.mark.parametrize("stress", [False, True], ids=["regular", "stress"])
+@pytest.mark.parametrize("cfg", ["sr_x4", "sr_x8"])
+def test_nll_gradients_match_the_oracle_autograd(cfg, stress, report):
+    """SURVEY 8f-1 / north_star "torch.autograd.Function extensions": d nll / d theta for EVERY parameter, and d nll / d hr,
+    through the CUDA forward + backward kernels (hcflow_b200/autograd.py) against torch autograd over the oracle on the
+    CPU (the reference's optimize_parameters path, HCFlow_SR_model.py:195-203) on a shrunk net (K=4, one RRDB per trunk).
+    Tolerance: per tensor max|g - g_ref| <= 2e-3 * max|g_ref| + 1e-6 (fp32 sums in different orders; measured in the
+    report), nll to 1e-5 relative."""
+    opt, net, sd = _small_train_net(cfg, stress)
+    s = opt["scale"]
+    B, h = 2, 8 if cfg == "sr_x4" else 4
+    lr = synth.synthetic_lr(B, h, h, seed=71)
+    hr = synth.synthetic_hr(B, h * s, h * s, seed=72)
+    dq = torch.rand(hr.shape, generator=torch.Generator().manual_seed(73), dtype=torch.float32)
+    # oracle
+    sd_r = {k: v.clone().requires_grad_(v.is_floating_point() and "haar" not in k) for k, v in sd.items()}
+    hr_r = hr.clone().requires_grad_(True)
+    _, nll_ref, _, _ = orc.sr_forward(hr_r, lr, sd_r, opt, dq)
+    nll_ref.backward()
+    # CUDA
+    net = net.cuda().train()
+    hr_c = hr.cuda().requires_grad_(True)
+    fake_lr, nll = net(hr=hr_c, lr=lr.cuda(), u=None, reverse=False, training=True, dequant_noise=dq)
+    assert nll.requires_grad and fake_lr.shape == (B, 3, h, h)
+    nll.backward()
+    e_nll = abs(float(nll.detach()) - float(nll_ref.detach())) / abs(float(nll_ref.detach()))
+    worst, worst_key, n_checked = 0.0, None, 0
+    for k, p in net.named_parameters():
+        if not p.requires_grad:
+            continue
+        g_ref = sd_r[k].grad
+        assert p.grad is not None and g_ref is not None, k
+        scale_ = float(g_ref.abs().max())
+        err = float((p.grad.cpu() - g_ref).abs().max())
+        rel = err / (scale_ + 1e-12)
+        n_checked += 1
+        if err > 2e-3 * scale_ + 1e-6 and rel > worst:
+            worst, worst_key = rel, k
+        elif worst_key is None and rel > worst:
+            worst = rel
+    e_hr = float((hr_c.grad.cpu() - hr_r.grad).abs().max()) / float(hr_r.grad.abs().max())
+    report["autograd_nll/{}/{}".format(cfg, "stress" if stress else "regular")] = {
+        "nll_rel": e_nll, "worst_param_grad_rel": worst, "d_hr_rel": e_hr, "params_checked": n_checked, "nll": float(nll.detach())}
+    assert worst_key is None, (worst_key, worst)
+    assert e_nll < 1e-5 and e_hr < 2e-3, (e_nll, e_hr)
+    assert n_checked > 100
+
+
+def test_training_step_reduces_the_nll():
+    """A few Adam steps through the autograd path on the shrunk net: the reference's optimize_parameters loop
+    (HCFlow_SR_model.py:195-203) runs on this package and the loss goes down; afterwards the inference engine sees the
+    updated weights (version counters) and reproduces the training-path NLL."""
+    opt, net, sd = _small_train_net("sr_x4")
+    net = net.cuda().train()
+    B, h = 2, 8
+    lr = synth.synthetic_lr(B, h, h, seed=81).cuda()
+    hr = synth.synthetic_hr(B, 4 * h, 4 * h, seed=82).cuda()
+    dq = torch.rand(hr.shape, generator=torch.Generator().manual_seed(83), dtype=torch.float32)
+    optim = torch.optim.Adam(net.parameters(), lr=2e-4)
+    losses = []
+    for it in range(4):
+        optim.zero_grad()
+        _, nll = net(hr=hr, lr=lr, u=None, reverse=False, training=True, dequant_noise=dq)
+        nll.backward()
+        optim.step()
+        losses.append(float(nll))
+    assert all(math.isfinite(v) for v in losses) and losses[-1] < losses[0], losses
+    net.eval()
+    net.set_precision("fp32")
+    with torch.no_grad():
+        _, nll_eval = net(hr=hr, lr=lr, reverse=False, dequant_noise=dq)
+    with torch.enable_grad():
+        _, nll_train = net(hr=hr, lr=lr, reverse=False, dequant_noise=dq)
+    assert abs(float(nll_eval) - float(nll_train)) < 1e-4 * abs(float(nll_train)), (float(nll_eval), float(nll_train))

@@ -70,6 +70,8 @@ POLICIES = {
     "f16x3_fcn3": lambda k: _pol_f16x3(k, (3,)),
     "f16x3_fcn": lambda k: _pol_f16x3(k, (1, 2, 3)),
     "split_all": lambda k: "split",
+    # what if conv5 of the RDBs ran one pass (everything else as f16x3_fcn)?
+    "fcn_split_conv5_one": lambda k: ("one" if ".RDB" in k else _pol_f16x3(k, (1, 2, 3))),
 }
 _FCN_KEYS = set()
 
@@ -111,6 +113,7 @@ def main():
     ap.add_argument("--stress", type=float, default=1.0)
     ap.add_argument("--stress-bias", type=float, default=None)
     ap.add_argument("--stress-prior", type=float, default=1.0)
+    ap.add_argument("--stress-prior-mean", type=float, default=1.0, help="scale only the MEAN rows (0::2) of the prior conv")
     ap.add_argument("--K", type=int, default=None)
     ap.add_argument("--after", default=None)
     ap.add_argument("--nb", default=None)
@@ -127,6 +130,12 @@ def main():
     net = build_net(opt)
     sd = synth.synthetic_state_dict(net.state_dict(), seed=1)
     sd = scale_zero_convs(sd, args.stress, args.stress_bias, args.stress_prior)
+    if args.stress_prior_mean != 1.0:
+        for k in list(sd):
+            if k.endswith("_condFlow.f.weight"):
+                w = sd[k].clone()
+                w[0::2] *= args.stress_prior_mean
+                sd[k] = w
     for k in sd:
         if k.endswith(".conv1.actnorm.bias"):
             _FCN_KEYS.add(k[:-len(".conv1.actnorm.bias")])
