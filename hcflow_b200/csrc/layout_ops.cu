@@ -259,3 +259,133 @@ extern "C" int hcf_copy_view(const hcf_squeeze_args* a, void* stream) {
                                                                      a->src_ld, a->dst_ld);
   return finish_launch("hcf_copy_view");
 }
+
+// ================================================================================================ SURVEY 8f-4
+// Tiled inference (codes/data/util.py:489-514 test_patchwise): E += patch, W += 1 over the patch's window; E /= W.
+// Evaluation metrics on the device (codes/utils/util.py:902-982 calculate_psnr / ssim / calculate_psnr_ssim,
+// codes/data/util.py:209-230 bgr2ycbcr): fp64 like the reference's numpy code.
+namespace hcf {
+
+// patches [n, C, ph, pw] (NCHW, the module's output layout) accumulated into E [C, H, W] at (y0[i], x0[i]); cnt [H, W]
+__global__ void tile_accumulate_kernel(const float* __restrict__ patches, int n, int C, int ph, int pw, const int* __restrict__ y0,
+                                       const int* __restrict__ x0, float* __restrict__ E, float* __restrict__ cnt, int H, int W) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)n * C * ph * pw;
+  if (i >= total) return;
+  const int x = (int)(i % pw);
+  long long r = i / pw;
+  const int y = (int)(r % ph); r /= ph;
+  const int c = (int)(r % C);
+  const int k = (int)(r / C);
+  const int gy = y0[k] + y, gx = x0[k] + x;
+  if (gy < 0 || gy >= H || gx < 0 || gx >= W) return;
+  atomicAdd(E + ((long long)c * H + gy) * W + gx, patches[i]);
+  if (c == 0) atomicAdd(cnt + (long long)gy * W + gx, 1.0f);
+}
+__global__ void tile_normalize_kernel(float* __restrict__ E, const float* __restrict__ cnt, int C, long long hw) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)C * hw) return;
+  E[i] = E[i] / cnt[i % hw];
+}
+
+// pixel value on the reference's [0, 255] scale: images are HWC, uint8 or float in [0, 1]
+__device__ __forceinline__ double px255(const void* img, int f32, long long idx) {
+  return f32 ? (double)reinterpret_cast<const float*>(img)[idx] * 255.0 : (double)reinterpret_cast<const unsigned char*>(img)[idx];
+}
+// channel `ch` of pixel (y, x); ch == -1: the Y channel of a BGR image, (24.966 B + 128.553 G + 65.481 R) / 255 + 16
+__device__ __forceinline__ double chan255(const void* img, int f32, int W, int C, int y, int x, int ch) {
+  const long long base = ((long long)y * W + x) * C;
+  if (ch >= 0) return px255(img, f32, base + ch);
+  return (24.966 * px255(img, f32, base) + 128.553 * px255(img, f32, base + 1) + 65.481 * px255(img, f32, base + 2)) / 255.0 + 16.0;
+}
+__device__ __forceinline__ void block_add(double v, double* out) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __shared__ double part[8];
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) part[w] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += part[i];
+    atomicAdd(out, t);
+  }
+  __syncthreads();
+}
+// sum of squared differences of channel ch over the cropped image
+__global__ void __launch_bounds__(256) sqdiff_kernel(const void* a, const void* b, int f32, int H, int W, int C, int crop, int ch,
+                                                     double* out) {
+  const int h = H - 2 * crop, w = W - 2 * crop;
+  double s = 0.0;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < (long long)h * w; i += (long long)gridDim.x * 256) {
+    const int y = crop + (int)(i / w), x = crop + (int)(i % w);
+    const double d = chan255(a, f32, W, C, y, x, ch) - chan255(b, f32, W, C, y, x, ch);
+    s += d * d;
+  }
+  block_add(s, out);
+}
+// sum of the SSIM map (11x11 Gaussian window, sigma 1.5, 'valid' region) of channel ch over the cropped image
+__global__ void __launch_bounds__(256) ssim_kernel(const void* a, const void* b, int f32, int H, int W, int C, int crop, int ch,
+                                                   const double* __restrict__ win, double* out) {
+  const int h = H - 2 * crop - 10, w = W - 2 * crop - 10;
+  double s = 0.0;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < (long long)h * w; i += (long long)gridDim.x * 256) {
+    const int y = crop + (int)(i / w), x = crop + (int)(i % w);
+    double m1 = 0, m2 = 0, s11 = 0, s22 = 0, s12 = 0;
+    for (int dy = 0; dy < 11; ++dy)
+      for (int dx = 0; dx < 11; ++dx) {
+        const double wgt = win[dy * 11 + dx];
+        const double p = chan255(a, f32, W, C, y + dy, x + dx, ch), q = chan255(b, f32, W, C, y + dy, x + dx, ch);
+        m1 += wgt * p; m2 += wgt * q;
+        s11 += wgt * p * p; s22 += wgt * q * q; s12 += wgt * p * q;
+      }
+    const double C1 = (0.01 * 255) * (0.01 * 255), C2 = (0.03 * 255) * (0.03 * 255);
+    const double v1 = s11 - m1 * m1, v2 = s22 - m2 * m2, cov = s12 - m1 * m2;
+    s += ((2 * m1 * m2 + C1) * (2 * cov + C2)) / ((m1 * m1 + m2 * m2 + C1) * (v1 + v2 + C2));
+  }
+  block_add(s, out);
+}
+
+}  // namespace hcf
+
+extern "C" int hcf_tile_accumulate(const float* patches, int32_t n, int32_t C, int32_t ph, int32_t pw, const int32_t* y0,
+                                   const int32_t* x0, float* E, float* cnt, int32_t H, int32_t W, void* stream) {
+  using namespace hcf;
+  HCF_REQUIRE(patches && y0 && x0 && E && cnt && n > 0 && C > 0 && ph > 0 && pw > 0 && H > 0 && W > 0, "tile_accumulate: bad args");
+  const long long total = (long long)n * C * ph * pw;
+  tile_accumulate_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(patches, n, C, ph, pw, y0, x0, E, cnt, H, W);
+  return finish_launch("hcf_tile_accumulate");
+}
+
+extern "C" int hcf_tile_normalize(float* E, const float* cnt, int32_t C, int32_t H, int32_t W, void* stream) {
+  using namespace hcf;
+  HCF_REQUIRE(E && cnt && C > 0 && H > 0 && W > 0, "tile_normalize: bad args");
+  const long long hw = (long long)H * W;
+  tile_normalize_kernel<<<(unsigned)((C * hw + 255) / 256), 256, 0, (cudaStream_t)stream>>>(E, cnt, C, hw);
+  return finish_launch("hcf_tile_normalize");
+}
+
+// out[0..C-1]: sum of squared differences per channel, out[C..2C-1]: SSIM-map sums per channel, out[2C]: squared
+// differences of the Y channel, out[2C+1]: SSIM-map sum of Y (C == 3 only; BGR order), all on the [0, 255] scale.
+// a, b: HWC images, uint8 (is_f32 = 0) or float in [0, 1] (is_f32 = 1); win: 121 doubles (the 11x11 Gaussian window).
+extern "C" int hcf_image_metrics(const void* a, const void* b, int32_t is_f32, int32_t H, int32_t W, int32_t C, int32_t crop,
+                                 const double* win, double* out, void* stream) {
+  using namespace hcf;
+  HCF_REQUIRE(a && b && win && out && H - 2 * crop > 10 && W - 2 * crop > 10 && C >= 1 && C <= 4 && crop >= 0,
+              "image_metrics: bad args (the cropped image must be larger than the 11x11 SSIM window)");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(double) * (2 * C + 2), st);
+  if (e != cudaSuccess) { set_error("image_metrics: %s", cudaGetErrorString(e)); return (int)e; }
+  const int h = H - 2 * crop, w = W - 2 * crop;
+  int g1 = (int)(((long long)h * w + 255) / 256), g2 = (int)(((long long)(h - 10) * (w - 10) + 255) / 256);
+  g1 = g1 > 1024 ? 1024 : g1; g2 = g2 > 4096 ? 4096 : g2;
+  for (int c = 0; c < C; ++c) {
+    sqdiff_kernel<<<g1, 256, 0, st>>>(a, b, is_f32, H, W, C, crop, c, out + c);
+    ssim_kernel<<<g2, 256, 0, st>>>(a, b, is_f32, H, W, C, crop, c, win, out + C + c);
+  }
+  if (C == 3) {
+    sqdiff_kernel<<<g1, 256, 0, st>>>(a, b, is_f32, H, W, C, crop, -1, out + 2 * C);
+    ssim_kernel<<<g2, 256, 0, st>>>(a, b, is_f32, H, W, C, crop, -1, win, out + 2 * C + 1);
+  }
+  return finish_launch("hcf_image_metrics");
+}

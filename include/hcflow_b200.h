@@ -392,6 +392,19 @@ int hcf_quantize8(const float* x, float* y, int64_t n, void* stream);
 /* adjoint of nearest up-sampling by 2^shift: dst [B,H,W,C] = block sums of src [B, H << shift, W << shift, C] */
 int hcf_downsample_sum(const float* src, float* dst, int32_t B, int32_t H, int32_t W, int32_t C, int32_t shift, void* stream);
 
+/* ---- tiled inference and evaluation metrics on the device.
+ * test_patchwise (codes/data/util.py:489-514): E[.., y0:y0+ph, x0:x0+pw] += patch, W += 1, E /= W.
+ * patches: [n, C, ph, pw] fp32 (the module's NCHW output); y0 / x0: device int32 [n]; E: [C, H, W]; cnt: [H, W]. */
+int hcf_tile_accumulate(const float* patches, int32_t n, int32_t C, int32_t ph, int32_t pw, const int32_t* y0,
+                        const int32_t* x0, float* E, float* cnt, int32_t H, int32_t W, void* stream);
+int hcf_tile_normalize(float* E, const float* cnt, int32_t C, int32_t H, int32_t W, void* stream);
+/* calculate_psnr_ssim's raw sums (codes/utils/util.py:902-982, codes/data/util.py:209-230), fp64, [0, 255] scale:
+ * out[0..C-1] squared-difference sums per channel, out[C..2C-1] SSIM-map sums per channel (11x11 Gaussian window `win`,
+ * 121 doubles, 'valid' region), out[2C], out[2C+1] the same for the Y channel of a BGR image (C == 3).
+ * a, b: HWC images, uint8 (is_f32 = 0) or float in [0, 1] (is_f32 = 1), cropped by `crop` pixels on every side. */
+int hcf_image_metrics(const void* a, const void* b, int32_t is_f32, int32_t H, int32_t W, int32_t C, int32_t crop,
+                      const double* win, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1127,3 +1127,71 @@ def test_training_step_reduces_the_nll():
     with torch.enable_grad():
         _, nll_train = net(hr=hr, lr=lr, reverse=False, dequant_noise=dq)
     assert abs(float(nll_eval) - float(nll_train)) < 1e-4 * abs(float(nll_train)), (float(nll_eval), float(nll_train))
+
+
+# ------------------------------------------------------------------------------ tiling + metrics on the device
+def _reference_module(name):
+    """a module of the UNMODIFIED reference (staged under oracle/_ref by oracle/build_ref.py), or None"""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        return None
+    ref_loader.load()
+    import importlib
+    return importlib.import_module(name)
+
+
+def test_tiled_inference_matches_the_reference_test_patchwise(report):
+    """hcflow_b200.tiling.sample_patchwise against the reference's own test_patchwise (codes/data/util.py:489-514) driving
+    the oracle on the CPU: LR 40x56 in 24x24 patches with 8 pixels overlap (six windows, the last row / column aligned to
+    the border), heat 0 (deterministic).  Same windows, same averaging of the overlaps."""
+    from hcflow_b200 import tiling
+    opt, net, sd = _net_cuda("sr_x4", "f16x3")
+    B, h, w, P, OV = 1, 40, 56, 24, 8
+    lr = synth.synthetic_lr(B, h, w, seed=91)
+    zero_eps = lambda n: [torch.zeros(n, c_, hh, ww) for (_, c_, hh, ww) in orc.noise_shapes(opt, n, P, P, True)]
+    model = lambda x: orc.sr_reverse(x, sd, opt, zero_eps(x.shape[0]))[0]
+    du = _reference_module("data.util")
+    with torch.no_grad():
+        if du is not None:
+            want = du.test_patchwise(model, lr, patchsize=P, overlapsize=OV, sf=4)
+            how = "reference test_patchwise"
+        else:   # restatement of codes/data/util.py:501-514
+            stride = P - OV
+            ys = list(range(0, h - P, stride)) + [h - P]
+            xs = list(range(0, w - P, stride)) + [w - P]
+            E, Wt = torch.zeros(B, 3, 4 * h, 4 * w), torch.zeros(B, 3, 4 * h, 4 * w)
+            for y in ys:
+                for x in xs:
+                    E[..., 4 * y:4 * (y + P), 4 * x:4 * (x + P)].add_(model(lr[..., y:y + P, x:x + P]))
+                    Wt[..., 4 * y:4 * (y + P), 4 * x:4 * (x + P)].add_(1)
+            want = E / Wt
+            how = "restated loop"
+        got = tiling.sample_patchwise(net, lr.cuda(), patchsize=P, overlapsize=OV, eps_std=0.0, tile_batch=4).cpu()
+    assert tiling.patch_origins(h, P, OV) == [0, 16] and tiling.patch_origins(w, P, OV) == [0, 16, 32]
+    err = maxabs(got, want)
+    report["tiled_inference"] = {"max": err, "against": how, "windows": 6}
+    assert got.shape == (B, 3, 160, 224) and err < 8e-5, err
+
+
+def test_device_psnr_ssim_matches_the_reference_function(report):
+    """hcflow_b200.metrics.psnr_ssim against util.calculate_psnr_ssim (codes/utils/util.py:958-982: numpy + cv2 on the
+    host), uint8 and float inputs, with and without border crop."""
+    import numpy as np
+    from hcflow_b200 import metrics
+    uu = _reference_module("utils.util")
+    if uu is None:
+        pytest.skip("reference copy not staged (oracle/build_ref.py)")
+    rng = np.random.RandomState(5)
+    H, W = 64, 80
+    gt = rng.randint(0, 256, size=(H, W, 3)).astype(np.uint8)
+    sr = np.clip(gt.astype(np.int32) + rng.randint(-12, 13, size=(H, W, 3)), 0, 255).astype(np.uint8)
+    rec = {}
+    for crop in (0, 4):
+        want = uu.calculate_psnr_ssim(gt / 255., sr / 255., crop)      # (test_HCFlow.py:143-149 passes img / 255.)
+        got8 = metrics.psnr_ssim(torch.from_numpy(gt).cuda(), torch.from_numpy(sr).cuda(), crop)
+        gotf = metrics.psnr_ssim(torch.from_numpy(gt).cuda().float() / 255., torch.from_numpy(sr).cuda().float() / 255., crop)
+        for name, g in (("u8", got8), ("f32", gotf)):
+            errs = [abs(a - b) for a, b in zip(g, want)]
+            rec["{}_crop{}".format(name, crop)] = errs
+            assert errs[0] < 1e-4 and errs[2] < 1e-4 and errs[1] < 1e-6 and errs[3] < 1e-6, (name, crop, g, want)
+    report["device_psnr_ssim"] = rec
