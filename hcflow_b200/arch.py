@@ -138,6 +138,11 @@ class _HCFlowBase(nn.Module):
                 dst.normal_(0.0, 1.0).mul_(std)
 
     def _reverse(self, lr, eps_std, eps):
+        if self.SR and torch.is_grad_enabled() and lr is not None and lr.is_cuda and (
+                any(p.requires_grad for p in self.parameters()) or lr.requires_grad):
+            # inverse-path loss of the reference's training loop (HCFlow_SR_model.py:207-218): differentiable graph
+            from . import autograd as ag
+            return ag.sr_reverse(self, lr, eps_std, eps)
         lr_arg = lr
         lr = self._check(lr, "lr")
         B, _, h, w = lr.shape

@@ -79,7 +79,7 @@ class Conv2dFn(Function):
         if ctx.needs_input_grad[1]:
             B, H, W, Cin = x.shape
             Cout = w.shape[0]
-            dw = torch.empty_like(w)
+            dw = torch.empty(w.shape, dtype=torch.float32, device=w.device)   # (contiguous: torch.inverse returns column-major)
             with torch.cuda.device(x.device):
                 L.check(lib.hcf_conv_wgrad(x.data_ptr(), Cin, dy.data_ptr(), Cout, B, H, W, Cin, Cout, ctx.ks, dw.data_ptr(),
                                            _st(x)), "conv_wgrad")
@@ -302,6 +302,56 @@ class UpsampleFn(Function):
         return dx, None
 
 
+class UnsqueezeFn(Function):
+    """unsqueeze2d (Basic.py:143-157): [B,H,W,4C] -> [B,2H,2W,C]; backward = squeeze2d."""
+
+    @staticmethod
+    def forward(ctx, x):
+        lib = L.load()
+        x = _chk(x.contiguous())
+        B, H, W, C4 = x.shape
+        y = torch.empty(B, 2 * H, 2 * W, C4 // 4, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            L.check(lib.hcf_unsqueeze2d(C.byref(_sq_args(x, y, B, C4 // 4, H, W)), _st(x)), "unsqueeze2d")
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = L.load()
+        dy = dy.contiguous()
+        B, H2, W2, Cc = dy.shape
+        dx = torch.empty(B, H2 // 2, W2 // 2, 4 * Cc, dtype=torch.float32, device=dy.device)
+        with torch.cuda.device(dy.device):
+            L.check(lib.hcf_squeeze2d(C.byref(_sq_args(dy, dx, B, Cc, H2 // 2, W2 // 2)), _st(dy)), "squeeze2d")
+        return dx
+
+
+class GaussSampleFn(Function):
+    """GaussianDiag.sample with the noise given (Basic.py:96-100): mean + exp(logs) * eps."""
+
+    @staticmethod
+    def forward(ctx, mean, logs, eps):
+        lib = L.load()
+        mean, logs, eps = _chk(mean.contiguous()), _chk(logs.contiguous()), _chk(eps.contiguous())
+        out = torch.empty_like(mean)
+        with torch.cuda.device(mean.device):
+            L.check(lib.hcf_gauss_sample(mean.data_ptr(), logs.data_ptr(), eps.data_ptr(), None, out.data_ptr(), None, mean.numel(),
+                                         _st(mean)), "gauss_sample")
+        ctx.save_for_backward(logs, eps)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = L.load()
+        logs, eps = ctx.saved_tensors
+        g = g.contiguous()
+        dlogs = torch.empty_like(logs)
+        with torch.cuda.device(g.device):
+            L.check(lib.hcf_gauss_sample(None, logs.data_ptr(), eps.data_ptr(), g.data_ptr(), None, dlogs.data_ptr(), g.numel(),
+                                         _st(g)), "gauss_sample")
+        return g, dlogs, None
+
+
 # ------------------------------------------------------------------------------------------------ module-level graph
 def _conv(x, mod_w, bias=None, scale=None, act=ACT_NONE):
     y = Conv2dFn.apply(x, mod_w)
@@ -411,3 +461,58 @@ def sr_forward_nll(net, hr, lr, dequant_noise=None):
     objective = logdet + GaussLogpFn.apply(fake_lr, lr_nhwc, None, -6.0)      # logp(mean=lr, logs=-6, x=fake_lr)
     nll = ((-objective) / float(math.log(2.0) * pixels)).mean().to(torch.float32)
     return torch.clamp(fake_lr.permute(0, 3, 1, 2), 0, 1), nll
+
+
+def _flow_step_reverse(z, u, step):
+    """FlowStep.reverse_flow (FlowStep.py:53-64): coupling^-1 -> invconv^-1 -> ActNorm^-1."""
+    B, H, W, Cc = z.shape
+    aff = step.affine
+    assert aff.mode == "affine", "training path: AffineCoupling only (the SR nets)"
+    n = aff.n_pass
+    z1, z2 = z[..., :n].contiguous(), z[..., n:].contiguous()
+    h = _fcn(z1 if u is None else _cat((z1, u)), aff.f)
+    z2, _ = CouplingFn.apply(z2, h, H * W, True)
+    z = _cat((z1, z2))
+    if step.permute is not None:
+        # the reference inverts in fp64 on every call (Permutations.py:74); torch.inverse is differentiable
+        winv = torch.inverse(step.permute.weight.double()).float()
+        z = Conv2dFn.apply(z, winv.view(Cc, Cc, 1, 1))
+    # x * exp(-logs) - bias  ==  (x + (-bias * exp(logs))) * exp(-logs)      (ActNorms.py:90-93)
+    logs, bias = step.actnorm.logs, step.actnorm.bias
+    return AffineActFn.apply(z, -bias * torch.exp(logs), torch.exp(-logs), ACT_NONE)
+
+
+def sr_reverse(net, lr, eps_std=0.0, eps=None):
+    """HCFlowNet_SR.reverse_flow_diracLR with autograd (HCFlowNet_SR_arch.py:70-75 -> FlowNet_SR_x4.py:106-123): the
+    inverse-path loss of optimize_parameters (HCFlow_SR_model.py:207-218) back-propagates through it.  lr [B,3,h,w] CUDA;
+    eps: unit-normal tensors per level (deepest first), else drawn with torch like the reference.  Returns clamp(fake_hr)."""
+    flow = net.flow
+    assert flow.SR, "training path is implemented for HCFlowNet_SR"
+    std = 0.0 if eps_std is None else float(eps_std)
+    z = lr.to(torch.float32).permute(0, 2, 3, 1).contiguous()
+    feats, draw = {}, 0
+    for lay in reversed(list(flow.layers)):
+        if isinstance(lay, M.SqueezeLayer):
+            z = UnsqueezeFn.apply(z)
+        elif isinstance(lay, M.FlowStep):
+            z = _flow_step_reverse(z, None, lay)
+        elif isinstance(lay, M.Split):
+            level = lay.level
+            cf = flow.cond_flow(level)
+            u = _cat([z] + [UpsampleFn.apply(feats[l], l - level) for l in range(level + 1, flow.L)])
+            feat = _cond_feature(u, cf)
+            feats[level] = feat
+            hp = _conv(feat, cf.f.weight, cf.f.bias, torch.exp(cf.f.logs * 3.0), ACT_NONE)
+            mean, logs = hp[..., 0::2].contiguous(), hp[..., 1::2].contiguous()
+            if eps is not None:
+                e = eps[draw].to(lr.device, torch.float32).permute(0, 2, 3, 1).contiguous() * std
+            else:
+                e = torch.empty_like(mean.permute(0, 3, 1, 2)).normal_(0.0, 1.0).mul_(std).permute(0, 2, 3, 1).contiguous()
+            draw += 1
+            a = GaussSampleFn.apply(mean, logs, e)
+            for st in reversed(list(cf.additional_flow_steps)):
+                a = _flow_step_reverse(a, feat, st)
+            z = _cat((z, a))
+        else:
+            raise NotImplementedError(type(lay).__name__)
+    return torch.clamp(z.permute(0, 3, 1, 2), 0, 1)

@@ -212,6 +212,16 @@ __global__ void gauss_logp_bwd_kernel(const float* __restrict__ g, const float* 
   if (dlogs) dlogs[k] = (d * d * iv - 1.f) * gb;
 }
 
+// prior sample (Basic.py:96-100, ConditionalFlow.py:62-64): out = mean + exp(logs) * eps;  dmean = g, dlogs = g * exp(logs) * eps
+__global__ void gauss_sample_kernel(const float* __restrict__ mean, const float* __restrict__ logs, const float* __restrict__ eps,
+                                    const float* __restrict__ g, float* __restrict__ out, float* __restrict__ dlogs, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float e = expf(logs[i]) * eps[i];
+  if (g) dlogs[i] = g[i] * e;          // backward (dmean = g needs no kernel)
+  else out[i] = mean[i] + e;           // forward
+}
+
 // ------------------------------------------------------------------------------------------------ small elementwise ops
 __global__ void axpby_kernel(const float* __restrict__ a, float alpha, const float* __restrict__ b, float beta,
                              float* __restrict__ y, long long n) {
@@ -330,6 +340,14 @@ extern "C" int hcf_gauss_logp_bwd(const float* g, const float* x, const float* m
   gauss_logp_bwd_kernel<<<HCF_GRID1(n, 256), 256, 0, (cudaStream_t)stream>>>(g, x, mean, logs, logs_const, per_img, n, dx, dmean,
                                                                              dlogs);
   return finish_launch("hcf_gauss_logp_bwd");
+}
+
+extern "C" int hcf_gauss_sample(const float* mean, const float* logs, const float* eps, const float* g, float* out, float* dlogs,
+                                int64_t n, void* stream) {
+  using namespace hcf;
+  HCF_REQUIRE(logs && eps && n > 0 && ((g && dlogs) || (!g && mean && out)), "gauss_sample: bad args");
+  gauss_sample_kernel<<<HCF_GRID1(n, 256), 256, 0, (cudaStream_t)stream>>>(mean, logs, eps, g, out, dlogs, n);
+  return finish_launch("hcf_gauss_sample");
 }
 
 extern "C" int hcf_axpby(const float* a, float alpha, const float* b, float beta, float* y, int64_t n, void* stream) {

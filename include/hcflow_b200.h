@@ -385,6 +385,9 @@ int hcf_gauss_logp_fwd(const float* x, const float* mean, const float* logs, flo
 /* g[img] = d loss / d out[img] (fp32); dx / dmean / dlogs may be NULL */
 int hcf_gauss_logp_bwd(const float* g, const float* x, const float* mean, const float* logs, float logs_const, int32_t B,
                        int64_t per_img, float* dx, float* dmean, float* dlogs, void* stream);
+/* prior sample: g == NULL: out = mean + exp(logs) * eps;  g != NULL (backward): dlogs = g * exp(logs) * eps */
+int hcf_gauss_sample(const float* mean, const float* logs, const float* eps, const float* g, float* out, float* dlogs, int64_t n,
+                     void* stream);
 /* y = alpha a + beta b (b may be NULL) */
 int hcf_axpby(const float* a, float alpha, const float* b, float beta, float* y, int64_t n, void* stream);
 /* y = round(clamp(x, 0, 1) * 255) / 255 */

@@ -1195,3 +1195,40 @@ def test_device_psnr_ssim_matches_the_reference_function(report):
             rec["{}_crop{}".format(name, crop)] = errs
             assert errs[0] < 1e-4 and errs[2] < 1e-4 and errs[1] < 1e-6 and errs[3] < 1e-6, (name, crop, g, want)
     report["device_psnr_ssim"] = rec
+
+
+@pytest.mark.parametrize("heat", [0.0, 0.9])
+def test_inverse_path_l1_gradients_match_the_oracle_autograd(heat, report):
+    """The second half of optimize_parameters (HCFlow_SR_model.py:207-218): fake_H = netG(lr, eps_std, reverse=True),
+    L1(fake_H, real_H).backward() -- gradients of every parameter through the differentiable inverse path (CUDA forward +
+    backward kernels) against torch autograd over the oracle."""
+    opt, net, sd = _small_train_net("sr_x4")
+    B, h = 2, 8
+    lr = synth.synthetic_lr(B, h, h, seed=75)
+    hr = synth.synthetic_hr(B, 4 * h, 4 * h, seed=76)
+    unit = synth.synthetic_noise(orc.noise_shapes(opt, B, h, h, True), seed=77)
+    sd_r = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    fake_ref, _ = orc.sr_reverse(lr, sd_r, opt, [heat * e for e in unit])
+    loss_ref = (fake_ref - hr).abs().mean()
+    loss_ref.backward()
+    net = net.cuda().train()
+    fake = net(lr=lr.cuda(), z=None, u=None, eps_std=heat, reverse=True, eps=unit)
+    assert fake.requires_grad
+    loss = (fake - hr.cuda()).abs().mean()
+    loss.backward()
+    worst, bad = 0.0, []
+    n = 0
+    for k, p in net.named_parameters():
+        g_ref = sd_r[k].grad
+        if g_ref is None:
+            continue
+        n += 1
+        sc = float(g_ref.abs().max())
+        err = float((p.grad.cpu() - g_ref).abs().max())
+        worst = max(worst, err / (sc + 1e-12)) if sc > 1e-9 else worst
+        if err > 5e-3 * sc + 1e-7:
+            bad.append((k, err, sc))
+    report["autograd_inverse_l1/heat{}".format(heat)] = {"loss_rel": abs(float(loss.detach()) - float(loss_ref.detach())) / float(loss_ref.detach()),
+                                                         "worst_param_grad_rel": worst, "params_checked": n}
+    assert not bad, bad[:8]
+    assert maxabs(fake.detach().cpu(), fake_ref.detach()) < 2e-4 and n > 100
