@@ -555,7 +555,9 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      uint32_t a_it = 0, b_it = 0, p_it = 0;
+      uint32_t p_it = 0;
+      int sA = 0, sB = 0;           // ring positions as (slot, phase) counters (see the MMA warp)
+      uint32_t phA = 0, phB = 0;
       // per-layer fields stay in registers; a CTA sees the same layer for ~n_tiles/gridDim.x items in a row
       int cur_layer = -1, kchunks = 0, se0 = 0, se1 = 0, m0 = 0, m1 = 0, m2 = 0, slab_taps = 1, slabs = 1;
       int l0 = 0, l1 = 0, l2 = 0, lparts = 1, ltaps = KS * KS, lsplit = 0, co0 = 0, co1 = 0, co2 = 0;
@@ -590,9 +592,8 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
           wimg = reinterpret_cast<const uint8_t*>(ldg_ptr(&L->wimg));
         }
         auto issue_b = [&](int kc, int sl) {
-          const int sB = b_it % p.sb;
           HCF_T(tb0);
-          mbar_wait(emptyB(sB), ((b_it / p.sb) & 1u) ^ 1u);
+          mbar_wait(emptyB(sB), phB ^ 1u);
           HCF_T(tb1);
           HCF_ACC(PROF_P_EMPTYB, tb0, tb1);
           if (p.debug & 4) {
@@ -605,7 +606,7 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
             mbar_expect_tx(fullB(sB), b_slab);
             bulk_load(b_base + sB * slot_bytes, wimg + chunk_off + (size_t)sl * b_slab, b_slab, fullB(sB));
           }
-          ++b_it;
+          if (++sB == p.sb) { sB = 0; phB ^= 1u; }
         };
         // (issuing the first chunk's weight slabs BEFORE the dependency wait was measured slower: with a two-slot B
         //  ring the activation tile then queues behind the wait for a free slot)
@@ -642,9 +643,8 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
         }
         ++p_it;
         for (int kc = 0; kc < kchunks; ++kc) {
-          const int sA = a_it % p.sa;
           HCF_T(ta0);
-          mbar_wait(emptyA(sA), ((a_it / p.sa) & 1u) ^ 1u);
+          mbar_wait(emptyA(sA), phA ^ 1u);
           HCF_T(ta1);
           HCF_ACC(PROF_P_EMPTYA, ta0, ta1);
           if (p.debug & 4) {
@@ -661,8 +661,8 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
               tma_load_4d(smem_base + sA * A_STAGE + A_PART, map_ptr(li), fullA(sA), cch, x0 - HALO, y0 - HALO, b);
             }
           }
-          ++a_it;
           for (int sl = (kc == 0 ? n_pre : 0); sl < slabs; ++sl) issue_b(kc, sl);
+          if (++sA == p.sa) { sA = 0; phA ^= 1u; }
         }
       }
       HCF_T(tp1);
@@ -679,7 +679,11 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
     // costs its full latency).
     const uint64_t a_tmpl = make_desc(0, HALO_W * ROW_BYTES);
     const uint64_t b_tmpl = make_desc(0, 8u * ROW_BYTES);
-    uint32_t a_it = 0, b_it = 0, t_it = 0;
+    uint32_t t_it = 0;
+    // ring positions as (slot, phase) counters: `it % depth` / `it / depth` with a run-time depth are two integer
+    // divisions (~60 instructions) per chunk and per slab on the one warp whose scalar latency idles the tensor pipe
+    int sA = 0, sB = 0;
+    uint32_t phA = 0, phB = 0;
     int cur_layer = -1, kchunks = 0, slab_taps = 1, slabs = 1, tap0 = 0;
     uint32_t parts = 1, nb = 0, nb_n = 0, idesc_n = 0, idesc = 0, n_cols = 0;
     int split_kc = 0, e0 = 0, e1 = 0, lk0 = 4, lk1 = 4, lk2 = 4;
@@ -715,8 +719,6 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
       const uint32_t d0 = tmem_base + acc * MT * p.nb_max;
       uint32_t accum = 0u;   // first MMA of the item overwrites the accumulator
       for (int kc = 0; kc < kchunks; ++kc) {
-        const int sA = a_it % p.sa;
-        const uint32_t phA = (a_it / p.sa) & 1u;
         HCF_T(tfa0);
         mbar_wait(fullA(sA), phA);
         HCF_T(tfa1);
@@ -732,9 +734,8 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
         const uint32_t nb_kc = split ? nb : nb_n;
         const uint32_t idesc_kc = split ? idesc : idesc_n;
         for (int sl = 0; sl < slabs; ++sl) {
-          const int sB = b_it % p.sb;
           HCF_T(tfb0);
-          mbar_wait(fullB(sB), (b_it / p.sb) & 1u);
+          mbar_wait(fullB(sB), phB);
           tc_fence_after();
           HCF_T(tfb1);
           HCF_ACC(PROF_M_FULLB, tfb0, tfb1);
@@ -777,9 +778,9 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
           HCF_T(tis1);
           HCF_ACC(PROF_M_ISSUE, tis0, tis1);
           accum = 1u;
-          ++b_it;
+          if (++sB == p.sb) { sB = 0; phB ^= 1u; }
         }
-        ++a_it;
+        if (++sA == p.sa) { sA = 0; phA ^= 1u; }
       }
     }
     HCF_T(tm1);
