@@ -1,7 +1,8 @@
 """GPU parity tests: the CUDA path (through the C ABI) against the oracle and the committed
-reference goldens.  Tolerances (fp32 mode): HR / z within 2e-4 max-abs on O(1)..O(10) values
-(the reference's own fp32-vs-fp64 floor is 3e-6; the CUDA kernels sum in a
-different order), log-det and NLL within 1e-5 relative."""
+reference goldens.  Every tolerance is <= 3x the value measured on B200 (profiles/r02_parity_report.json).  fp32 mode:
+HR / z within 1.5e-5 max-abs on O(1)..O(10) values (measured 5e-6; the reference's own fp32-vs-fp64 floor is 3e-6,
+SURVEY.md 8c-2; the CUDA kernels sum in a different order), log-det and NLL within 1e-5 relative.  Default mode
+(f16x3): 6e-5 (measured 2.1e-5), also on the stress fixtures; the package's stated tolerance is 2e-4."""
 import ctypes as C
 import math
 
@@ -18,7 +19,7 @@ from tests.helpers import is_sr, load_golden, maxabs, net_and_weights
 
 pytestmark = pytest.mark.gpu
 
-TOL_X = 2e-4
+TOL_X = 1.5e-5   # fp32 mode: <= 3x the measured 5.0e-6 (the reference's own fp32-vs-fp64 floor is 3e-6)
 TOL_REL = 1e-5
 
 
@@ -222,7 +223,7 @@ def test_full_size_inverse_then_forward_roundtrip(report):
     e_or = maxabs(raw[:1].cpu(), raw_o)
     report["full_size/sr_x4_b16"] = {"roundtrip": e_rt, "vs_oracle_img0": e_or, "nll": float(nll)}
     assert e_rt < 1e-3
-    assert e_or < TOL_X
+    assert e_or < 2 * TOL_X        # (measured 1.1e-5 at this size)
     assert torch.equal(hr, hr2)
 
 
@@ -314,7 +315,7 @@ def test_conv_tcgen05_matches_fp64(case, precision, report):
 # rounding (oracle + patched conv2d) gives 1.6e-3 / 1.3e-5 max-abs on sr_x4.
 # Tolerances are <= 3x the values measured on B200 (profiles/r02_parity_report.json).  The x3 modes (default f16x3)
 # carry the stated "fp32 tolerance" of this package: 2e-4 max-abs on the un-clamped HR, also on the stress fixtures.
-E2E_TOL = {"tf32": 4e-2, "tf32x3": 2e-4, "tf32x3_all": 2e-4, "f16": 6e-3, "f16x3": 8e-5}
+E2E_TOL = {"tf32": 4e-2, "tf32x3": 2e-4, "tf32x3_all": 2e-4, "f16": 5e-3, "f16x3": 6e-5}
 
 
 @pytest.mark.parametrize("precision", ["tf32", "tf32x3", "tf32x3_all", "f16", "f16x3"])
@@ -638,7 +639,7 @@ def test_prior_draw_consumes_the_reference_rng_stream():
     assert torch.equal(got, want) and torch.equal(got2, want2)
 
 
-@pytest.mark.parametrize("precision,tol", [("f16x3", 1e-4), ("tf32x3", 2e-4), ("f16", 6e-3)])
+@pytest.mark.parametrize("precision,tol", [("f16x3", 6e-5), ("tf32x3", 2e-4), ("f16", 6e-3)])
 def test_ragged_size_against_oracle(precision, tol, report):
     """LR 12x20 (HR 48x80): every level has partial tiles in both directions (16x8 pixel tiles), B=3 is not a
     multiple of anything -- the chained launches, the fused FlowStep epilogue and the shared-conditioning addend
@@ -744,7 +745,8 @@ def test_sr_forward_tensor_core_modes_match_reference_golden(cfg, precision, tol
 
 
 # ------------------------------------------------------------------------------ stress fixtures (O(1) couplings)
-STRESS_TOL = {"fp32": 2e-4, "f16x3": 2e-4, "tf32x3": 2e-4, "tf32x3_all": 2e-4, "f16": 5e-2, "tf32": 2e-1}
+# (<= 3x the measured values of profiles/r02_parity_report.json; the package's STATED tolerance for the x3 modes is 2e-4)
+STRESS_TOL = {"fp32": 2e-5, "f16x3": 6e-5, "tf32x3": 2e-4, "tf32x3_all": 2e-4, "f16": 6e-3, "tf32": 6e-2}
 
 
 @pytest.mark.parametrize("precision", ["fp32", "f16x3", "tf32x3", "tf32x3_all", "f16", "tf32"])
@@ -850,7 +852,7 @@ def test_config1_full_size_default_precision_vs_oracle(report):
         errs = []
         for i in (0, 15):
             _, want = orc.sr_reverse(lr[i:i + 1], sd, opt, [0.8 * e[i:i + 1] for e in unit])
-            errs.append(_img0_close(raw[i:i + 1], want, 1e-4, "configs[1] image {}".format(i)))
+            errs.append(_img0_close(raw[i:i + 1], want, 8e-5, "configs[1] image {}".format(i)))
     assert torch.isfinite(raw).all() and float(hr.min()) >= 0.0 and float(hr.max()) <= 1.0
     report["config1_full_size_f16x3"] = {"img0": errs[0], "img15": errs[1]}
 
@@ -868,12 +870,12 @@ def test_config2_x8_full_size_default_precision_vs_oracle(report):
         net(lr=lr.cuda(), eps_std=0.8, reverse=True, eps=unit)
         raw = net.last["hr_raw"].cpu()
         _, want = orc.sr_reverse(lr[:1], sd, opt, [0.8 * e[:1] for e in unit])
-        e_inv = _img0_close(raw[:1], want, 1e-4, "configs[2] inverse image 0")
+        e_inv = _img0_close(raw[:1], want, 2e-5, "configs[2] inverse image 0")
         fake_lr, nll = net(hr=hr_in.cuda(), lr=lr.cuda(), reverse=False, dequant_noise=dq)
         z = net.last["z_raw"].cpu()
         obj = net.last["objective"].cpu()
         _, _, z_w, ld_w = orc.sr_forward(hr_in[:1], lr[:1], sd, opt, dq[:1])
-    e_z = _img0_close(z[:1], z_w, 1e-4, "configs[2] forward z image 0")
+    e_z = _img0_close(z[:1], z_w, 1e-5, "configs[2] forward z image 0")
     dirac = orc.gaussian_logp(lr[:1].double(), -torch.ones_like(lr[:1]).double() * 6, fake_lr[:1].cpu().double())
     e_ld = float(((obj[:1] - dirac - ld_w.double()).abs() / ld_w.double().abs()).max())
     assert torch.isfinite(raw).all() and torch.isfinite(obj).all() and math.isfinite(float(nll))
@@ -896,9 +898,9 @@ def test_config3_rescaling_full_size_default_precision_vs_oracle(report):
         raw = net.last["hr_raw"].cpu()
         _, z1_w, z2_w, rawlr_w = orc.rescaling_forward(hr_in[:1], sd, opt)
         _, want = orc.rescaling_reverse(lr_q[:1], sd, opt, [e[:1] for e in unit])
-    e = [_img0_close(raw_lr[:1], rawlr_w, 1e-4, "configs[3] encode LR image 0"),
-         _img0_close(z1[:1].cpu(), z1_w, 2.5e-4, "configs[3] z1"), _img0_close(z2[:1].cpu(), z2_w, 2.5e-4, "configs[3] z2"),
-         _img0_close(raw[:1], want, 1e-4, "configs[3] decode image 0")]
+    e = [_img0_close(raw_lr[:1], rawlr_w, 2e-6, "configs[3] encode LR image 0"),
+         _img0_close(z1[:1].cpu(), z1_w, 2e-6, "configs[3] z1"), _img0_close(z2[:1].cpu(), z2_w, 2e-6, "configs[3] z2"),
+         _img0_close(raw[:1], want, 2e-5, "configs[3] decode image 0")]
     assert torch.isfinite(raw).all() and float(out.min()) >= 0.0 and float(out.max()) <= 1.0
     report["config3_full_size_f16x3"] = {"encode_lr": e[0], "z1": e[1], "z2": e[2], "decode": e[3]}
 
@@ -1170,7 +1172,7 @@ def test_tiled_inference_matches_the_reference_test_patchwise(report):
     assert tiling.patch_origins(h, P, OV) == [0, 16] and tiling.patch_origins(w, P, OV) == [0, 16, 32]
     err = maxabs(got, want)
     report["tiled_inference"] = {"max": err, "against": how, "windows": 6}
-    assert got.shape == (B, 3, 160, 224) and err < 8e-5, err
+    assert got.shape == (B, 3, 160, 224) and err < 2e-5, err
 
 
 def test_device_psnr_ssim_matches_the_reference_function(report):
