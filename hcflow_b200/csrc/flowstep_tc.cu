@@ -121,6 +121,13 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[3
       : "r"(taddr));
 }
 
+// two floats -> packed fp16 pair, round to nearest, finite saturation (lo half = first argument)
+__device__ __forceinline__ uint32_t cvt_f16x2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 // ------------------------------------------------------------------------------------------------ per-pixel tails
 // h[2j] = shift, h[2j+1] = scale of coupled channel n_pass + j (AffineCouplings.py:52-57, 78-84: h[:, 0::2], h[:, 1::2])
 template <int C>
@@ -255,9 +262,12 @@ __global__ void __launch_bounds__(THREADS, 1) flowstep_kernel(const __grid_const
   const uint32_t z1_full = bar0, z1_empty = bar0 + 8;
   auto w_full = [&](int k) { return bar0 + 16u + 8u * k; };
   auto w_empty = [&](int k) { return bar0 + 40u + 8u * k; };
-  const uint32_t acc1_full = bar0 + 64, a2_ready = bar0 + 72, acc2_full = bar0 + 80, a3_ready = bar0 + 88;
-  const uint32_t acc3_full = bar0 + 96, acc3_empty = bar0 + 104;
-  const uint32_t dep_seq = bar0 + 112, tmem_slot = bar0 + 116;
+  // conv1 -> epilogue 1 -> conv2 -> epilogue 2 hand-offs are per M tile (conv2 is 1x1: tile m's conv2 needs tile m's h1 only)
+  auto acc1_full = [&](int m) { return bar0 + 64u + 8u * m; };
+  auto a2_ready = [&](int m) { return bar0 + 80u + 8u * m; };
+  auto acc2_full = [&](int m) { return bar0 + 96u + 8u * m; };
+  const uint32_t a3_ready = bar0 + 112, acc3_full = bar0 + 120, acc3_empty = bar0 + 128;
+  const uint32_t dep_seq = bar0 + 136, tmem_slot = bar0 + 140;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -265,7 +275,8 @@ __global__ void __launch_bounds__(THREADS, 1) flowstep_kernel(const __grid_const
     asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.m[1]) : "memory");
     mbar_init(z1_full, 1); mbar_init(z1_empty, 1);
     for (int k = 0; k < 3; ++k) { mbar_init(w_full(k), 1); mbar_init(w_empty(k), 1); }
-    mbar_init(acc1_full, 1); mbar_init(a2_ready, 256); mbar_init(acc2_full, 1); mbar_init(a3_ready, 256);
+    for (int m = 0; m < 2; ++m) { mbar_init(acc1_full(m), 1); mbar_init(a2_ready(m), 128); mbar_init(acc2_full(m), 1); }
+    mbar_init(a3_ready, 256);
     mbar_init(acc3_full, 1); mbar_init(acc3_empty, 128);
     asm volatile("st.shared.b32 [%0], %1;" ::"r"(dep_seq), "r"(0u) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -394,49 +405,51 @@ __global__ void __launch_bounds__(THREADS, 1) flowstep_kernel(const __grid_const
         const uint64_t a0 = dense + ((sbase + OFF_Z1) >> 4);
         const uint64_t b0 = dense + ((sbase + OFF_W1) >> 4);
 #pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap) {
-          const int dy = tap / 3, dx = tap - dy * 3;
-          const uint64_t bd = b0 + (uint32_t)(tap >> 2) * W1_BLOCK16 + (uint32_t)(tap & 3) * 2u;
-#pragma unroll
-          for (int m = 0; m < 2; ++m) {
+        for (int m = 0; m < 2; ++m) {
+          const uint32_t d = tmem_base + (uint32_t)m * 128u;
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3, dx = tap - dy * 3;
+            const uint64_t bd = b0 + (uint32_t)(tap >> 2) * W1_BLOCK16 + (uint32_t)(tap & 3) * 2u;
             const uint64_t ad = a0 + (uint32_t)((m * 128 + dy * PITCH + dx) * 8);
-            const uint32_t d = tmem_base + (uint32_t)m * 128u;
             umma_f16(d, ad, bd, idesc12, tap > 0 ? 1u : 0u);
             if (split) umma_f16(d + 64u, ad + 2u, bd, idesc64, 1u);      // A_lo (bytes 32..63 of the row) x B_hi
           }
+          umma_commit(acc1_full(m));                                     // epilogue 1 of tile 0 runs under tile 1's MMAs
         }
         umma_commit(z1_empty);
-        umma_commit(acc1_full);
         if (last_of_step) umma_commit(w_empty(0));
       }
       __syncwarp();
       FS_T(ta3);
       FS_ACC(FP_M_ISSUE1, ta2, ta3);
-      // ---------------- conv2: 1x1, K = 64
-      mbar_wait(a2_ready, par);
-      FS_T(ta4);
-      FS_ACC(FP_M_A2READY, ta3, ta4);
+      // ---------------- conv2: 1x1, K = 64, tile by tile as its h1 rows arrive
       if (new_step) mbar_wait(w_full(1), wpar);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint64_t ah = dense + ((sbase + OFF_HHI) >> 4), al = dense + ((sbase + OFF_HLO) >> 4);
-        const uint64_t b0 = dense + ((sbase + OFF_W2) >> 4);
+#pragma unroll 1
+      for (int m = 0; m < 2; ++m) {
+        FS_T(tq0);
+        mbar_wait(a2_ready(m), par);
+        FS_T(tq1);
+        FS_ACC(FP_M_A2READY, tq0, tq1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t ah = dense + ((sbase + OFF_HHI) >> 4), al = dense + ((sbase + OFF_HLO) >> 4);
+          const uint64_t b0 = dense + ((sbase + OFF_W2) >> 4);
+          const uint32_t d = tmem_base + (uint32_t)m * 128u;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-#pragma unroll
-          for (int m = 0; m < 2; ++m) {
-            const uint32_t d = tmem_base + (uint32_t)m * 128u;
+          for (int k = 0; k < 4; ++k) {
             const uint32_t off = (uint32_t)(m * 128 * 8 + k * 2);
             umma_f16(d, ah + off, b0 + 2u * k, idesc12, k > 0 ? 1u : 0u);
             if (split) umma_f16(d + 64u, al + off, b0 + 2u * k, idesc64, 1u);
           }
+          umma_commit(acc2_full(m));
+          if (m == 1 && last_of_step) umma_commit(w_empty(1));
         }
-        umma_commit(acc2_full);
-        if (last_of_step) umma_commit(w_empty(1));
+        __syncwarp();
+        FS_T(tq2);
+        FS_ACC(FP_M_ISSUE2, tq1, tq2);
       }
-      __syncwarp();
       FS_T(ta5);
-      FS_ACC(FP_M_ISSUE2, ta4, ta5);
       // ---------------- conv3: 3x3 over the h2 halo tile -> cols [256, 256 + NB3)
       mbar_wait(a3_ready, par);
       FS_T(ta6);
@@ -498,7 +511,11 @@ __global__ void __launch_bounds__(THREADS, 1) flowstep_kernel(const __grid_const
         cur_step = step;
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const int et = threadIdx.x - 64;
-        s_epi[et] = __ldg(p.tabs + (size_t)step * TAB_FLOATS + et);
+        {   // bias slots hold bias * scale: the epilogue is one FMA per channel, (v + b) * s = fma(v, s, b * s)
+          const float* tb = p.tabs + (size_t)step * TAB_FLOATS;
+          const float tv = __ldg(tb + et);
+          s_epi[et] = (et & 64) ? tv : tv * __ldg(tb + et + 64);
+        }
         pre = ldg_ptr(&(p.steps + step)->pre);
         pre_ld = __ldg(&(p.steps + step)->pre_ld);
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -519,7 +536,7 @@ __global__ void __launch_bounds__(THREADS, 1) flowstep_kernel(const __grid_const
 #pragma unroll 1
       for (int stage = 0; stage < 2; ++stage) {
         FS_T(tb2);
-        mbar_wait(stage == 0 ? acc1_full : acc2_full, par);
+        mbar_wait(stage == 0 ? acc1_full(m) : acc2_full(m), par);
         FS_T(tb3);
         FS_ACC(stage == 0 ? FP_E_ACC1 : FP_E_ACC2, tb2, tb3);
         tc_fence_after();
@@ -551,34 +568,45 @@ __global__ void __launch_bounds__(THREADS, 1) flowstep_kernel(const __grid_const
                 for (int j = 0; j < 8; ++j) pa[j] = __ldg(reinterpret_cast<const float4*>(prep) + 8 + j);
               }
             }
+            if (keep) {
 #pragma unroll
-            for (int c8 = 0; c8 < 4; ++c8) {                    // one 16-byte chunk (8 channels) per plane at a time
-              uint32_t hi[4], lo4[4];
+              for (int c8 = 0; c8 < 4; ++c8) {                  // one 16-byte chunk (8 channels) per plane at a time
+                const float4* sb4 = reinterpret_cast<const float4*>(s_bias + half * 32 + c8 * 8);
+                const float4* ss4 = reinterpret_cast<const float4*>(s_scale + half * 32 + c8 * 8);
+                const float4 b0 = sb4[0], b1 = sb4[1], s0 = ss4[0], s1 = ss4[1];
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                uint32_t hi[4], lo4[4];
 #pragma unroll
-              for (int j = 0; j < 8; j += 2) {
-                const int ch = half * 32 + c8 * 8 + j;
-                float a = fmaxf((v[c8 * 8 + j] + s_bias[ch]) * s_scale[ch], 0.f);
-                float c = fmaxf((v[c8 * 8 + j + 1] + s_bias[ch + 1]) * s_scale[ch + 1], 0.f);
-                if (!keep) { a = 0.f; c = 0.f; }
-                a = fminf(a, 65504.0f); c = fminf(c, 65504.0f);
-                const __half2 hh = __floats2half2_rn(a, c);
-                const float2 hf = __half22float2(hh);
-                const __half2 ll = __floats2half2_rn((a - hf.x) * 2048.0f, (c - hf.y) * 2048.0f);
-                hi[j >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
-                lo4[j >> 1] = *reinterpret_cast<const uint32_t*>(&ll);
+                for (int j = 0; j < 8; j += 2) {
+                  const float a = fmaxf(fmaf(v[c8 * 8 + j], sc[j], bb[j]), 0.f);
+                  const float c = fmaxf(fmaf(v[c8 * 8 + j + 1], sc[j + 1], bb[j + 1]), 0.f);
+                  const uint32_t hh = cvt_f16x2_sat(a, c);     // saturates at +-65504 (fp16 range guard)
+                  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hh));
+                  const __half2 ll = __floats2half2_rn((a - hf.x) * 2048.0f, (c - hf.y) * 2048.0f);
+                  hi[j >> 1] = hh;
+                  lo4[j >> 1] = *reinterpret_cast<const uint32_t*>(&ll);
+                }
+                if (store) {
+                  // 128B swizzle: 16-byte chunk index XOR (row & 7)
+                  const int co = (((half * 4 + c8) ^ (q & 7))) * 16;
+                  *reinterpret_cast<uint4*>(rowh + co) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                  if (split) *reinterpret_cast<uint4*>(rowl + co) = make_uint4(lo4[0], lo4[1], lo4[2], lo4[3]);
+                }
               }
-              if (store) {
-                // 128B swizzle: 16-byte chunk index XOR (row & 7)
+            } else if (store) {                                 // h2 outside the image: conv3's zero padding
+#pragma unroll
+              for (int c8 = 0; c8 < 4; ++c8) {
                 const int co = (((half * 4 + c8) ^ (q & 7))) * 16;
-                *reinterpret_cast<uint4*>(rowh + co) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                if (split) *reinterpret_cast<uint4*>(rowl + co) = make_uint4(lo4[0], lo4[1], lo4[2], lo4[3]);
+                *reinterpret_cast<uint4*>(rowh + co) = make_uint4(0u, 0u, 0u, 0u);
+                if (split) *reinterpret_cast<uint4*>(rowl + co) = make_uint4(0u, 0u, 0u, 0u);
               }
             }
           }
         }
         fence_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
         tc_fence_before();
-        mbar_arrive(stage == 0 ? a2_ready : a3_ready);
+        mbar_arrive(stage == 0 ? a2_ready(m) : a3_ready);
         FS_T(tb4);
         FS_ACC(stage == 0 ? FP_E_BODY1 : FP_E_BODY2, tb3, tb4);
       }
