@@ -996,6 +996,28 @@ def test_batch_mean_nll_over_nccl_matches_the_oracle_mean(report):
     report["nccl_batch_mean_nll"] = line
 
 
+def test_gradient_allreduce_over_nccl_matches_the_oracle_on_the_whole_batch(report):
+    """SURVEY 8f-1 "DDP gradient all-reduce overlapped with backward": two ranks, each NLL forward + backward on its shard
+    through the CUDA autograd kernels, hcflow_b200.dist.GradientReducer reducing buckets while backward runs; every
+    parameter gradient against torch autograd over the oracle on the concatenated batch -- tools/nccl_grad_check.py under
+    torchrun.  Needs >= 2 GPUs."""
+    import json
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run: gpurun --gpus 2 -- python -m pytest tests -m gpu -k nccl)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29519", os.path.join(root, "tools", "nccl_grad_check.py")]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
+    out = r.stdout.decode(errors="replace")
+    assert r.returncode == 0, out[-2000:]
+    line = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+    assert line["ok"] and line["backend"] == "nccl" and line["world"] == 2 and line["buckets_reduced_during_backward"] > 0
+    report["nccl_gradient_allreduce"] = line
+
+
 # ------------------------------------------------------------------------------ fused FlowStep kernel (flowstep_tc.cu)
 FS_CASES = [
     # name, cfg, step prefixes in forward order, conditional?, (B, H, W)

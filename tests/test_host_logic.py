@@ -122,6 +122,48 @@ def test_world_size_2_gloo_nll_reduction(tmp_path):
     assert out.stdout.count("OK") == 2
 
 
+_GRAD_WORKER = r"""
+import os, sys, torch
+sys.path.insert(0, {root!r})
+from hcflow_b200 import dist as hd
+rank, local, world = hd.init_from_env(backend="gloo")
+torch.manual_seed(0)
+net = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.Tanh(), torch.nn.Linear(16, 16), torch.nn.Tanh(), torch.nn.Linear(16, 3))
+unused = torch.nn.Parameter(torch.ones(5))            # never reached by backward: reduced as zero, stays None
+x = torch.randn(8, 6, generator=torch.Generator().manual_seed(1))
+lo, hi = hd.shard_range(8, rank, world)
+red = hd.GradientReducer(list(net.parameters()) + [unused], bucket_bytes=300)
+assert len(red.buckets) > 2
+for it in range(2):                                    # buckets are reusable across steps
+    net.zero_grad()
+    net(x[lo:hi]).pow(2).mean().backward()
+    early = red.launched_early
+    red.finish()
+    got = [p.grad.clone() for p in net.parameters()]
+    net.zero_grad()
+    red.remove() if it == 1 else None
+assert early > 0
+net.zero_grad()
+net(x).pow(2).mean().backward()                        # whole batch, no reduction: the hooks are gone
+for g, p in zip(got, net.parameters()):
+    assert torch.allclose(g, p.grad, rtol=1e-5, atol=1e-7), float((g - p.grad).abs().max())
+assert unused.grad is None or float(unused.grad.abs().max()) == 0.0
+print("OK", rank)
+"""
+
+
+def test_world_size_2_gloo_gradient_reducer(tmp_path):
+    """dist.GradientReducer (bucketed all-reduce issued from inside backward): mean of the shard gradients == gradient
+    of the whole-batch mean loss; buckets left incomplete by unused parameters are flushed by finish()."""
+    script = tmp_path / "gworker.py"
+    script.write_text(_GRAD_WORKER.format(root=ROOT))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29615", str(script)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("OK") == 2
+
+
 _REF_WORKER = r"""
 import sys
 sys.path.insert(0, {root!r})
