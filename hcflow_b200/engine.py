@@ -75,6 +75,7 @@ class Engine:
         self.n_fp32_conv = 0
         self.n_chains = 0
         self.n_chains16 = 0
+        self.fallbacks = []          # fp16 chains that were refused and ran on the TF32 kernels (also warned about)
         self.shadow16 = {}       # buffer name -> (hi, lo) fp16 planes (fp16 chains)
         self.call_info = []      # per call: {"cls", "tag", "flops", "convs"}
         self.use_chains = use_chains
@@ -676,8 +677,20 @@ class Engine:
         if not pending:
             return
         lib = self.lib
-        if self.precision in ("f16", "f16x3") and self._try_chain16(pending):
-            return
+        if self.precision in ("f16", "f16x3"):
+            if self._try_chain16(pending):
+                return
+            why = self.lib.hcf_last_error()
+            why = why.decode(errors="replace") if isinstance(why, bytes) else str(why)
+            # the run as a whole does not qualify (typically a wide last conv whose weight slabs do not fit beside the
+            # rings): peel one or two convs off the end instead of dropping the whole run to the TF32 kernels
+            for cut in (len(pending) - 1, len(pending) - 2):
+                if cut >= 2 and self._try_chain16(pending[:cut]):
+                    self._flush_tc(pending[cut:])
+                    return
+            self.fallbacks.append("{}..{} x{}: fp16 chain refused ({}); TF32 operand kernels used".format(
+                pending[0][3], pending[-1][3], len(pending), why))
+            warnings.warn("hcflow_b200: " + self.fallbacks[-1], RuntimeWarning, stacklevel=2)
         for op, _, _, _ in pending:   # fp32-operand kernels read z itself
             if op.step is not None:
                 self._step_structs[id(op)].z16_hi = None
