@@ -746,7 +746,7 @@ def test_sr_forward_tensor_core_modes_match_reference_golden(cfg, precision, tol
 
 # ------------------------------------------------------------------------------ stress fixtures (O(1) couplings)
 # (<= 3x the measured values of profiles/r02_parity_report.json; the package's STATED tolerance for the x3 modes is 2e-4)
-STRESS_TOL = {"fp32": 2e-5, "f16x3": 6e-5, "tf32x3": 2e-4, "tf32x3_all": 2e-4, "f16": 6e-3, "tf32": 6e-2}
+STRESS_TOL = {"fp32": 2e-5, "f16x3": 6e-5, "tf32x3": 2e-4, "tf32x3_all": 2e-4, "f16": 1e-2, "tf32": 6e-2}
 
 
 @pytest.mark.parametrize("precision", ["fp32", "f16x3", "tf32x3", "tf32x3_all", "f16", "tf32"])
