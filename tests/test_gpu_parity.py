@@ -854,6 +854,7 @@ def test_config1_full_size_default_precision_vs_oracle(report):
             _, want = orc.sr_reverse(lr[i:i + 1], sd, opt, [0.8 * e[i:i + 1] for e in unit])
             errs.append(_img0_close(raw[i:i + 1], want, 8e-5, "configs[1] image {}".format(i)))
     assert torch.isfinite(raw).all() and float(hr.min()) >= 0.0 and float(hr.max()) <= 1.0
+    assert all(not e.fallbacks for e in net._engines.values())     # every conv run stayed on the fp16 chains
     report["config1_full_size_f16x3"] = {"img0": errs[0], "img15": errs[1]}
 
 
@@ -880,6 +881,7 @@ def test_config2_x8_full_size_default_precision_vs_oracle(report):
     e_ld = float(((obj[:1] - dirac - ld_w.double()).abs() / ld_w.double().abs()).max())
     assert torch.isfinite(raw).all() and torch.isfinite(obj).all() and math.isfinite(float(nll))
     assert e_ld < 2e-5, e_ld
+    assert all(not e.fallbacks for e in net._engines.values())     # every conv run stayed on the fp16 chains
     report["config2_full_size_f16x3"] = {"inverse_img0": e_inv, "forward_z_img0": e_z, "logdet_rel_img0": e_ld}
 
 
@@ -902,6 +904,7 @@ def test_config3_rescaling_full_size_default_precision_vs_oracle(report):
          _img0_close(z1[:1].cpu(), z1_w, 2e-6, "configs[3] z1"), _img0_close(z2[:1].cpu(), z2_w, 2e-6, "configs[3] z2"),
          _img0_close(raw[:1], want, 2e-5, "configs[3] decode image 0")]
     assert torch.isfinite(raw).all() and float(out.min()) >= 0.0 and float(out.max()) <= 1.0
+    assert all(not e.fallbacks for e in net._engines.values())     # every conv run stayed on the fp16 chains
     report["config3_full_size_f16x3"] = {"encode_lr": e[0], "z1": e[1], "z2": e[2], "decode": e[3]}
 
 
