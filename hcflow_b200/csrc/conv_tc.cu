@@ -2,6 +2,7 @@
 // of one buffer), per-layer tables of a chained launch, weight-image packing, and the C ABI entry points
 // (include/hcflow_b200.h).  The kernel and its device helpers are in conv_tc_kernel.cuh.
 #include "conv_tc_kernel.cuh"
+#include "conv_ws_kernel.cuh"
 
 namespace hcf {
 namespace tc {
@@ -74,6 +75,7 @@ struct hcf_conv_tc_plan {
   hcf::tc::Params p;
   hcf::tc::KernelFn fn;
   hcf::tc::LayerDesc* d_layers;
+  void* d_ws;                           // weight-stationary schedule: per-layer chunk tables (null: per-item schedule)
   float* d_epi;
   std::vector<const float*>* epi_src;   // per layer: bias, scale device pointers and N (for hcf_conv_tc_plan_refresh)
   std::vector<int>* epi_n;
@@ -196,6 +198,75 @@ static bool shadow_of(const hcf_shadow16* sh, int n_sh, const float* ptr, __half
     }
   }
   return false;
+}
+
+static size_t ws_smem_bytes() {
+  return 1024 + (size_t)WS_SA * a_part(1, 3) + (size_t)WS_SB * WS_SLOT + TAIL_BYTES + 3 * WS_TAB_BYTES;
+}
+
+// Chunk tables and image grouping of the weight-stationary schedule; false = the chain keeps the per-item schedule
+// (accumulators wider than a TMEM slot, raw partial-sum outputs, a single image, or not asked for).
+// OPT-IN (HCF_TC_WS=1): parity-green, but measured slower than the per-item schedule on the RRDB chains of configs[1]
+// (80x80: 6.0 vs 5.2 ms, 40x40: 2.6 vs 2.0 ms; profiles/r02_ws_*): weights are fetched once per three tiles and the MMA
+// issue time per tile drops 19 %, but a pass of three tiles that complete together needs two epilogue rounds before it
+// can be published, and that latency chain (not the tensor pipe) then sets the pace -- DESIGN.md section 8.
+static bool ws_plan(const std::vector<LayerDesc>& layers, int n, const Params& p, int sms, std::vector<WsLayer>* out,
+                    int* n_phases, int* ipp, int* grid) {
+  const char* want = getenv("HCF_TC_WS");
+  if (!want || atoi(want) == 0) return false;
+  if (p.B < 2 || p.nb_max > WS_BIG_COLS) return false;
+  const int per_img = p.tiles_x * p.tiles_y;
+  int k = WS_GMAX * sms / per_img;          // images per group such that a CTA owns at most WS_GMAX tiles of it
+  if (k > p.B / 2) k = p.B / 2;             // at least two groups: a group's next layer waits on nothing recent
+  if (k < 1) return false;
+  const int np = (p.B + k - 1) / k;
+  k = (p.B + np - 1) / np;
+  if (const char* env = getenv("HCF_WS_IPP")) {   // tuning: images per group
+    const int v = atoi(env);
+    if (v >= 1 && v <= p.B / 2) k = v;
+  }
+  *n_phases = (p.B + k - 1) / k;
+  *ipp = k;
+  *grid = k * per_img < sms ? k * per_img : sms;
+  if ((k * per_img + *grid - 1) / *grid > WS_GMAX) return false;
+  out->resize(n);
+  for (int i = 0; i < n; ++i) {
+    const LayerDesc& L = layers[i];
+    WsLayer& W = (*out)[i];
+    memset(&W, 0, sizeof(W));
+    if (L.raw2 || L.step_z) return false;
+    const int split = L.parts == 2 ? L.split_kc : 0;
+    if (L.parts == 2 && split < 1) return false;
+    const int kcs = L.kchunks, total = kcs + (split < kcs ? split : kcs);
+    if (total > WS_MAX_CHUNKS || L.N * L.parts > WS_BIG_COLS) return false;
+    W.n_chunks = total; W.taps = L.taps; W.tap0 = L.tap0; W.nb = L.N * L.parts;
+    W.wimg = (unsigned long long)reinterpret_cast<uintptr_t>(L.wimg);
+    const uint32_t tap_n = (uint32_t)L.N * ROW_BYTES;
+    int c = 0;
+    auto add = [&](int kc, int kind) {   // kind 0: one pass, 1: hi plane x [B_hi ; B_lo], 2: lo plane x B_hi
+      const int seg = kc < L.seg_end[0] ? 0 : (kc < L.seg_end[1] ? 1 : 2);
+      const int kl = kc - (seg == 0 ? 0 : L.seg_end[seg - 1]);
+      WsChunk& ch = W.ch[c++];
+      ch.map = kind == 2 ? L.map_lo[seg] : L.map_idx[seg];
+      ch.cch = kl * KCH16 + L.seg_coff[seg];
+      const int kmax = (kc == kcs - 1) ? L.seg_last_k[2]
+                                      : ((kc == L.seg_end[0] - 1) ? L.seg_last_k[0] : ((kc == L.seg_end[1] - 1) ? L.seg_last_k[1] : 4));
+      ch.rows = kind == 1 ? 2 * L.N : L.N;
+      ch.dcol = kind == 2 ? L.N : 0;
+      ch.idesc = (1u << 4) | (((uint32_t)ch.rows >> 3) << 17) | ((128u >> 4) << 24);   // fp16 operands, fp32 accumulate
+      const int sk = kc < split ? kc : split;
+      ch.b_off = (uint32_t)(((size_t)sk * 2u + (size_t)(kc - sk)) * (uint32_t)L.taps * tap_n);
+      ch.b_tap_src = kc < split ? 2u * tap_n : tap_n;
+      const int per = WS_SLOT / (ch.rows * ROW_BYTES);
+      int slabs = 1, tps = L.taps;
+      if (per < L.taps) { slabs = (L.taps + per - 1) / per; tps = (L.taps + slabs - 1) / slabs; }
+      ch.kst = kmax | (tps << 8) | (slabs << 16);
+    };
+    for (int kc = 0; kc < split && kc < kcs; ++kc) add(kc, 1);
+    for (int kc = 0; kc < split && kc < kcs; ++kc) add(kc, 2);
+    for (int kc = split; kc < kcs; ++kc) add(kc, 0);
+  }
+  return true;
 }
 
 static int chain_create(const hcf_conv_args* args, const void* const* wtc, const int32_t* layer_passes,
@@ -542,7 +613,24 @@ static int chain_create(const hcf_conv_args* args, const void* const* wtc, const
   p.layers = pl->d_layers;
   pl->grid = dim3((unsigned)(p.n_tiles < sms ? p.n_tiles : sms));
   p.tpc = 0;
-  if (n > 1 && p.n_tiles > sms && p.n_tiles <= 3 * sms) {
+  // ---- weight-stationary schedule (conv_ws_kernel.cuh) for fp16 3x3 chains whose accumulators fit its TMEM slots
+  std::vector<WsLayer> ws;
+  int ws_grid = 0;
+  const bool use_ws = f16 && n > 1 && ks == 3 && mt == 1 && !tail_extra &&
+                      ws_plan(layers, n, p, sms, &ws, &p.n_phases, &p.ipp, &ws_grid);
+  if (use_ws) {
+    e = cudaMalloc(&pl->d_ws, sizeof(WsLayer) * n);
+    if (e == cudaSuccess) e = cudaMemcpy(pl->d_ws, ws.data(), sizeof(WsLayer) * n, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      set_error("tc_chain: chunk table upload: %s", cudaGetErrorString(e));
+      hcf_conv_tc_plan_destroy(pl);
+      return (int)e;
+    }
+    p.ws_layers = pl->d_ws;
+    pl->grid = dim3((unsigned)ws_grid);
+    pl->smem_bytes = ws_smem_bytes();
+  }
+  if (!use_ws && n > 1 && p.n_tiles > sms && p.n_tiles <= 3 * sms) {
     // few tiles per CTA and layer (40x40 level: 240 tiles on 148 SMs): instead of rotating the items over the CTAs,
     // each CTA can own tpc tiles for all layers when the tile count divides into a grid that still covers >= 3/4 of
     // the SMs.  Opt-in (HCF_TC_STATIC=1): measured on the same box, 120 owning CTAs are not faster than 148 rotating
@@ -561,7 +649,7 @@ static int chain_create(const hcf_conv_args* args, const void* const* wtc, const
     set_error("tc_chain: fused FlowStep layers need a 3x3 chain");
     return HCF_ENOTSUP;
   }
-  pl->fn = pick_kernel(mt, passes, ks, f16, tail_extra != 0);
+  pl->fn = use_ws ? conv_ws_kernel : pick_kernel(mt, passes, ks, f16, tail_extra != 0);
   e = cudaFuncSetAttribute(reinterpret_cast<const void*>(pl->fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
                            SMEM_LIMIT);
   if (e != cudaSuccess) {
@@ -693,6 +781,7 @@ extern "C" void hcf_conv_tc_plan_destroy(hcf_conv_tc_plan* p) {
     cudaFree(p->d_prof);
   }
   if (p->d_layers) cudaFree(p->d_layers);
+  if (p->d_ws) cudaFree(p->d_ws);
   if (p->d_epi) cudaFree(p->d_epi);
   delete p->epi_src;
   delete p->epi_n;

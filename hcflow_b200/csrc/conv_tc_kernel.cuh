@@ -128,6 +128,9 @@ struct Params {
   const float* epi;   // [n_layers][256]: bias (0) | scale (1) of every layer, padded: one coalesced load per layer change
   int step_tab;       // 1: the chain has fused FlowStep layers (shared memory carries their W^-1 / ActNorm tables)
   long long* prof;    // HCF_TC_PROF=1: cycles per role / wait class summed over CTAs (see PROF_* below)
+  // weight-stationary schedule (conv_ws_kernel.cuh): image groups ("phases") of ipp images each, per-layer chunk tables
+  int n_phases, ipp;
+  const void* ws_layers;
   int* status;        // sticky device word (may be null): bit 0 = an fp16 operand plane saturated (|x| > 65504),
                       // bit 1 = a dependency wait timed out (the chain's CTAs were not co-resident)
 };

@@ -480,6 +480,44 @@ def test_chain16_full_size_is_deterministic_and_close_to_fp32_path(precision, re
     assert err < E2E_TOL[precision] + E2E_TOL["tf32x3"], err
 
 
+def test_weight_stationary_schedule_matches_the_per_item_schedule(report, monkeypatch):
+    """The opt-in weight-stationary schedule of the chained conv launch (HCF_TC_WS=1, csrc/conv_ws_kernel.cuh: a CTA owns
+    up to three tiles per image group, every weight slab is fetched once per group pass) against the default per-item
+    schedule: the RDB chain against fp64 at the same tolerance, and configs[1] at full size against the default
+    schedule's output (the main accumulator columns see the same sequence of MMAs; the correction columns of a split
+    chunk are summed in a different order, so the outputs agree to fp32 rounding, not bit for bit) -- three runs give
+    the same bits (dependency counters across 148 CTAs)."""
+    monkeypatch.setenv("HCF_TC_WS", "1")
+    got, ref, mid, mid_ref, y16 = _rdb_chain16(2, 40, 40, [1, 1, 1, 1, 3], conv5_split=64)
+    err = maxabs(got, ref)
+    assert err < 3e-3 and maxabs(mid, mid_ref) < 6e-3 and maxabs(y16, got) < 4e-6, err
+    got2, ref2, _, _, _ = _rdb_chain16(2, 40, 40, [3, 3, 3, 3, 3])
+    err2 = maxabs(got2, ref2)
+    assert err2 < 2e-5, err2
+    monkeypatch.delenv("HCF_TC_WS")
+    opt, net, sd = _net_cuda("sr_x4", "f16x3")
+    B = 16
+    lr = synth.synthetic_lr(B, 40, 40, seed=5).cuda()
+    unit = synth.synthetic_noise(orc.noise_shapes(opt, B, 40, 40, True), seed=9)
+    with torch.no_grad():
+        net(lr=lr, eps_std=0.8, reverse=True, eps=unit)
+        want = net.last["hr_raw"].clone()
+        monkeypatch.setenv("HCF_TC_WS", "1")
+        net.clear_engines()
+        outs = []
+        for rep in range(3):
+            net(lr=lr, eps_std=0.8, reverse=True, eps=unit)
+            outs.append(net.last["hr_raw"].clone())
+        assert all(not e.fallbacks for e in net._engines.values())
+    monkeypatch.delenv("HCF_TC_WS")
+    net.clear_engines()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    diff = float((outs[0] - want).abs().max())
+    report["weight_stationary_schedule"] = {"rdb_conv5_split_vs_fp64": err, "rdb_all_split_vs_fp64": err2,
+                                            "config1_vs_per_item_schedule": diff}
+    assert diff < 2e-5, diff
+
+
 # ------------------------------------------------------------------------------ coupling sub-net as one chain
 def _fcn_chain(kind, B, H, W, zc=6, cond=128, hidden=64, cout=12, seed=0):
     """FCN(cat(z1, u)) (Basic.py:426-447) the way the engine lowers it in the tensor-core modes: the W_u * u part of
