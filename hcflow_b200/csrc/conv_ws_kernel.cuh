@@ -8,8 +8,12 @@
 //     activation tiles before it leaves (weight-stationary), each tile accumulating in its own TMEM slot;
 //   * one dependency poll + gpu-scope acquire fence per item: one per group;
 //   * activation stages that carried [hi | lo] although only an RDB's conv5 reads a lo plane: the ring holds single
-//     planes (six stages instead of two), the lo plane of a split chunk is its own K chunk (A_lo x B_hi into the
-//     correction columns), and weights have their own producer warp, so neither ring waits for the other.
+//     planes (five stages instead of two pairs), the lo plane of a split chunk is its own K chunk (A_lo x B_hi into
+//     the correction columns), and weights have their own producer warp, so neither ring waits for the other.
+// STATUS: opt-in (HCF_TC_WS=1).  Parity-green and it does what it was built for (weight fills -2/3, MMA issue time per
+// tile -19 %, L2 -> SM traffic 31.5 -> 20.0 GB on the 80x80 encoder chain), but the launch is slower than the per-item
+// schedule (6.0 vs 5.2 ms): three tiles of a pass complete together and need two epilogue rounds before the pass can be
+// published, static ownership pays six tile slots per layer for 5.4 tiles of work -- DESIGN.md section 4.2.
 // Image groups ("phases") alternate: images are independent, so the tiles of group p at layer l + 1 depend only on
 // group p at layer l, which finished one whole group pass earlier -- the dependency wait is off the critical path
 // instead of being hidden by luck.
@@ -84,75 +88,6 @@ __device__ __noinline__ void ws_wait_failed(int code, int a, int b, int c, volat
       }                                                                                      \
     }                                                                                        \
   } while (0)
-
-// 16 accumulator columns WITHOUT the wait (the main and correction columns of a column group share one tcgen05.wait::ld)
-__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-
-// Coalesced-domain store of one 32-column group, straight-line: the eight staging reads are issued together, the
-// arithmetic of the eight pixels is independent, stores are predicated on the pixel being inside the image, and the
-// fp16 range guard is a clamp + one flag per call instead of a branch per pixel (coal_store_fast of the per-item
-// kernel puts every pixel in its own reconvergence region: ~500 cycles per pixel quad, latency-bound).
-template <bool W32, bool WHI, bool WLO>
-__device__ __forceinline__ void ws_coal_store(const float4* __restrict__ stage, const uint32_t (&pixv)[8], int lane, int ch,
-                                              int ld, float* __restrict__ out, __half* __restrict__ hi_p,
-                                              __half* __restrict__ lo_p, const Chan4& cc, bool has_pre, bool has_r1,
-                                              bool has_r2, const float4 (&r1v)[8], const float4 (&r2v)[8], float alpha1,
-                                              float alpha2, int* __restrict__ status, int dbg) {
-  const int cidx = lane & 7;
-  float amax = 0.f;
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
-  float4 o[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int pl = (half * 4 + i) * 4 + (lane >> 3);
-    o[i] = stage[pl * 8 + (cidx ^ (pl & 7))];
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int it = half * 4 + i;
-    const bool in = pixv[it] != 0xffffffffu && !(dbg & 256);
-    float4 v = o[i];
-    if (has_pre) {
-      const float4 rr = r1v[it];
-      v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
-    }
-    v = chan_apply(v, cc);
-    if (has_r1) {
-      const float4 rr = r1v[it];
-      v.x = fmaf(v.x, alpha1, rr.x); v.y = fmaf(v.y, alpha1, rr.y); v.z = fmaf(v.z, alpha1, rr.z); v.w = fmaf(v.w, alpha1, rr.w);
-    }
-    if (has_r2) {
-      const float4 rr = r2v[it];
-      v.x = fmaf(v.x, alpha2, rr.x); v.y = fmaf(v.y, alpha2, rr.y); v.z = fmaf(v.z, alpha2, rr.z); v.w = fmaf(v.w, alpha2, rr.w);
-    }
-    const uint32_t e1 = (in ? pixv[it] : 0u) * (uint32_t)ld + ch;
-    if (W32 && in) { if (dbg & 1024) *reinterpret_cast<float4*>(out + e1) = v; else __stcg(reinterpret_cast<float4*>(out + e1), v); }
-    if (WHI) {
-      // range guard: saturate (NaN -> finite as well) and remember that it happened
-      const float m = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
-      if (in) amax = (m <= 65504.0f) ? fmaxf(amax, m) : __int_as_float(0x7f800000);
-      v.x = fminf(fmaxf(v.x, -65504.0f), 65504.0f); v.y = fminf(fmaxf(v.y, -65504.0f), 65504.0f);
-      v.z = fminf(fmaxf(v.z, -65504.0f), 65504.0f); v.w = fminf(fmaxf(v.w, -65504.0f), 65504.0f);
-      const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
-      const uint2 hi = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
-      if (in) { if (dbg & 1024) *reinterpret_cast<uint2*>(hi_p + e1) = hi; else __stcg(reinterpret_cast<uint2*>(hi_p + e1), hi); }
-      if (WLO) {
-        const uint2 lo = split_lo(v, hi);
-        if (in) { if (dbg & 1024) *reinterpret_cast<uint2*>(lo_p + e1) = lo; else __stcg(reinterpret_cast<uint2*>(lo_p + e1), lo); }
-      }
-    }
-  }
-  }
-  if (WHI && amax > 65504.0f && status) atomicOr(status, STATUS_F16_OVERFLOW);
-}
 
 __device__ __forceinline__ void ws_load_tab(const WsLayer* __restrict__ src, uint32_t* dst, int lane) {
   const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
