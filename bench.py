@@ -266,7 +266,7 @@ def per_class_times(eng):
     return out
 
 
-def run_configs4(net, opt, dev, rank, world, hd, orc, flush, steps):
+def run_configs4(net, opt, dev, rank, world, hd, flush, steps):
     """configs[4] as BASELINE.json states it: 4x SR, global batch 64 x N sharded over the N ranks (64 per GPU; the
     reference's batch_size // world_size, codes/data/__init__.py:13-14), inverse pass, plus one forward NLL step whose
     batch mean (HCFlowNet_SR_arch.py:65 nll.mean()) is the path's only collective: ONE all-reduce of (sum nll_i, count)
@@ -275,7 +275,7 @@ def run_configs4(net, opt, dev, rank, world, hd, orc, flush, steps):
     B4, HR = 64, LR_HW * SCALE
     lr = synth.synthetic_lr(B4, LR_HW, LR_HW, seed=100 + rank)
     hr = synth.synthetic_hr(B4, HR, HR, seed=100 + rank)
-    unit = synth.synthetic_noise(orc.noise_shapes(opt, B4, LR_HW, LR_HW, True), seed=200 + rank)
+    unit = synth.synthetic_noise(net.noise_shapes(B4, LR_HW, LR_HW), seed=200 + rank)
     er = net.engine("reverse", B4, LR_HW, LR_HW, dev)
     er.ext["lr"].copy_(lr)
     for i, e in enumerate(unit):
@@ -336,7 +336,6 @@ def run_configs4(net, opt, dev, rank, world, hd, orc, flush, steps):
 def run_ours(args):
     from hcflow_b200 import dist as hd, options as popt, synth
     from hcflow_b200.arch import build_net
-    from oracle import hcflow_oracle as orc  # noise shapes helper + cpu_baseline leg only
     rank, local, world = hd.init_from_env()
     assert world == args.gpus or world == 1, (world, args.gpus)
     torch.cuda.set_device(local)
@@ -350,7 +349,7 @@ def run_ours(args):
     B = B_PER_GPU
     HR = LR_HW * SCALE
     lr = synth.synthetic_lr(B, LR_HW, LR_HW, seed=rank)
-    unit = synth.synthetic_noise(orc.noise_shapes(opt, B, LR_HW, LR_HW, True), seed=123 + rank)
+    unit = synth.synthetic_noise(net.noise_shapes(B, LR_HW, LR_HW), seed=123 + rank)
     eng = net.engine("reverse", B, LR_HW, LR_HW, dev)
     eng.ext["lr"].copy_(lr)
     for i, e in enumerate(unit):
@@ -429,7 +428,7 @@ def run_ours(args):
 
     cfg4 = None
     if world > 1 or args.configs4:
-        cfg4 = run_configs4(net, opt, dev, rank, world, hd, orc, flush, steps=max(3, min(args.steps, 10)))
+        cfg4 = run_configs4(net, opt, dev, rank, world, hd, flush, steps=max(3, min(args.steps, 10)))
 
     if rank != 0:
         return

@@ -78,6 +78,12 @@ class _HCFlowBase(nn.Module):
             self.precision = precision
             self.clear_engines()
 
+    def noise_shapes(self, B, h, w):
+        """[(B, C, H, W)] of the prior draws of an inverse pass on an h x w LR input, in draw order (deepest level first:
+        the order in which the reference calls torch.normal, ConditionalFlow.py:44-110) -- what `eps=` expects."""
+        from .plan import build_plan
+        return [(B, c, H, W) for c, H, W in build_plan(self, "reverse", B, h, w).noise_shapes]
+
     def clear_engines(self):
         for eng in self._engines.values():
             eng.close()

@@ -30,6 +30,7 @@ def test_reverse_plan_matches_golden(cfg):
     lr, hr, eps = _inputs(g, opt)
     plan = P.build_plan(net, "reverse", g["B"], g["h"], g["w"])
     assert [tuple(s) for s in plan.noise_shapes] == [tuple(e.shape[1:]) for e in eps]
+    assert net.noise_shapes(g["B"], g["h"], g["w"]) == [tuple(e.shape) for e in eps]   # the public helper bench.py uses
     em = Emulator(net, plan)
     out = em.run(lr=lr, **{"eps{}".format(i): e for i, e in enumerate(eps)})
     assert maxabs(out["hr_raw"], g["inv_raw"]) < 2e-4

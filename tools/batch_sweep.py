@@ -9,7 +9,6 @@ import torch  # noqa: E402
 
 from hcflow_b200 import options as popt, synth  # noqa: E402
 from hcflow_b200.arch import build_net  # noqa: E402
-from oracle import hcflow_oracle as orc  # noqa: E402
 
 
 def main():
@@ -25,7 +24,7 @@ def main():
     for B in (1, 4, 16, 64):
         eng = net.engine("reverse", B, 40, 40, torch.device("cuda", 0))
         eng.ext["lr"].copy_(synth.synthetic_lr(B, 40, 40, seed=0))
-        unit = synth.synthetic_noise(orc.noise_shapes(opt, B, 40, 40, True), seed=123)
+        unit = synth.synthetic_noise(net.noise_shapes(B, 40, 40), seed=123)
         for i, e in enumerate(unit):
             eng.ext["eps{}".format(i)].copy_(0.8 * e)
         for _ in range(3):

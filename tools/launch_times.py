@@ -11,7 +11,6 @@ import torch  # noqa: E402
 
 from hcflow_b200 import options as popt, synth  # noqa: E402
 from hcflow_b200.arch import build_net  # noqa: E402
-from oracle import hcflow_oracle as orc  # noqa: E402
 
 
 def main():
@@ -33,7 +32,7 @@ def main():
     if "hr" in eng.ext:
         eng.ext["hr"].copy_(synth.synthetic_hr(B, hw * s_, hw * s_, seed=0))
     if cfg != "rescaling_x4" and direction == "reverse":
-        for i, e in enumerate(synth.synthetic_noise(orc.noise_shapes(opt, B, hw, hw, True), seed=123)):
+        for i, e in enumerate(synth.synthetic_noise(net.noise_shapes(B, hw, hw), seed=123)):
             eng.ext["eps{}".format(i)].copy_(0.8 * e)
     st = torch.cuda.current_stream()
     acc, count = {}, {}

@@ -14,7 +14,6 @@ import torch  # noqa: E402
 
 from hcflow_b200 import options as popt, synth  # noqa: E402
 from hcflow_b200.arch import build_net  # noqa: E402
-from oracle import hcflow_oracle as orc  # noqa: E402
 
 
 def main():
@@ -28,7 +27,7 @@ def main():
     B, hw = 16, 40
     eng = net.engine("reverse", B, hw, hw, torch.device("cuda", 0))
     eng.ext["lr"].copy_(synth.synthetic_lr(B, hw, hw, seed=0))
-    for i, e in enumerate(synth.synthetic_noise(orc.noise_shapes(opt, B, hw, hw, True), seed=123)):
+    for i, e in enumerate(synth.synthetic_noise(net.noise_shapes(B, hw, hw), seed=123)):
         eng.ext["eps{}".format(i)].copy_(0.8 * e)
     for _ in range(4):
         eng.run()
