@@ -14,13 +14,21 @@ Extensions (keyword-only, all optional, ignored by the reference's callers):
 After a call ``net.last`` holds the un-clamped tensors (hr_raw / z_raw / logdet / ...).
 """
 import collections
+import contextlib
 import math
+import threading
 
 import torch
 from torch import nn
 
 from . import modules as M
 from .options import opt_get
+
+
+# nn.DataParallel runs its replicas in threads of one process: the engine cache of the master module is shared by all of
+# them (one engine per device), so cache look-ups, engine construction and the host side of a launch (incl. CUDA-graph
+# capture, which is process-global) are serialised; the device work itself is asynchronous and overlaps across the GPUs.
+_DP_LOCK = threading.RLock()
 
 
 class _HCFlowBase(nn.Module):
@@ -61,10 +69,30 @@ class _HCFlowBase(nn.Module):
         self._weights_epoch += 1
 
     def _replicate_for_data_parallel(self):
-        raise RuntimeError(
-            "hcflow_b200 nets cannot be replicated by nn.DataParallel over several GPUs (replicas carry no parameters "
-            "and would share one engine cache across threads).  Use one process per GPU (torchrun / "
-            "DistributedDataParallel, hcflow_b200.dist), or DataParallel with a single device id.")
+        """nn.DataParallel over several GPUs (the reference's default wrapper when no launcher is used,
+        HCFlow_SR_model.py:33-36): a replica carries no Parameters of its own (torch attaches broadcast copies as plain
+        attributes), so it remembers the module it was copied from and runs INFERENCE through that module's engine cache
+        -- one engine, one packed-weight store per device, weights read from the master's state_dict.  Training under
+        multi-device DataParallel is refused (use one process per GPU: torchrun / DistributedDataParallel,
+        hcflow_b200.dist)."""
+        replica = super()._replicate_for_data_parallel()
+        replica.__dict__["_dp_master"] = self.__dict__.get("_dp_master") or self
+        return replica
+
+    def _master(self):
+        return self.__dict__.get("_dp_master") or self
+
+    def _guard(self):
+        """Replicas (threads of one process) serialise the host side of their calls; a plain module pays nothing."""
+        return _DP_LOCK if self.__dict__.get("_dp_master") is not None else contextlib.nullcontext()
+
+    def _refuse_replica_training(self):
+        m = self.__dict__.get("_dp_master")
+        if m is not None and torch.is_grad_enabled() and any(p.requires_grad for p in m.parameters()):
+            raise RuntimeError(
+                "hcflow_b200: training through nn.DataParallel replicas on several GPUs is not supported (replicas carry "
+                "no Parameters).  Use one process per GPU (torchrun / DistributedDataParallel, hcflow_b200.dist), or call "
+                "the wrapped module under torch.no_grad() for inference.")
 
     # ---- engine management -------------------------------------------------------------
     def set_precision(self, precision):
@@ -95,21 +123,25 @@ class _HCFlowBase(nn.Module):
         device = torch.device(device)
         if device.type == "cuda" and device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
+        m = self._master()          # replicas share the master's cache (keyed by device) and read its weights
         key = (direction, B, h, w, str(device), self.precision, self.use_graph, self.use_chains, self.share_cond,
                self.fuse_steps, io, self.pair_convs, self.flowchain)
-        eng = self._engines.get(key)
-        if eng is not None:
-            self._engines.move_to_end(key)
+        with self._guard():
+            eng = m._engines.get(key)
+            if eng is not None:
+                m._engines.move_to_end(key)
+                return eng
+            # the bound is per device: a replica must not evict the engine another GPU is running
+            mine = [k for k in m._engines if k[4] == str(device)]
+            while len(mine) >= max(1, m.max_engines):
+                m._engines.pop(mine.pop(0)).close()          # least recently used of this device
+            store = m._stores.setdefault(str(device), WeightStore())
+            with torch.cuda.device(device):    # the plans allocate and set function attributes on the CURRENT device
+                eng = Engine(m, direction, B, h, w, device, precision=self.precision, use_graph=self.use_graph,
+                             use_chains=self.use_chains, share_cond=self.share_cond, fuse_steps=self.fuse_steps, io=io,
+                             pair_convs=self.pair_convs, store=store, flowchain=self.flowchain)
+            m._engines[key] = eng
             return eng
-        while len(self._engines) >= max(1, self.max_engines):
-            _, old = self._engines.popitem(last=False)     # least recently used
-            old.close()
-        store = self._stores.setdefault(str(device), WeightStore())
-        eng = Engine(self, direction, B, h, w, device, precision=self.precision, use_graph=self.use_graph,
-                     use_chains=self.use_chains, share_cond=self.share_cond, fuse_steps=self.fuse_steps, io=io,
-                     pair_convs=self.pair_convs, store=store, flowchain=self.flowchain)
-        self._engines[key] = eng
-        return eng
 
     def check_status(self):
         """Synchronous check of the engines' device status words (fp16 range guard): raises FP16RangeError /
@@ -144,11 +176,13 @@ class _HCFlowBase(nn.Module):
                 dst.normal_(0.0, 1.0).mul_(std)
 
     def _reverse(self, lr, eps_std, eps):
+        self._refuse_replica_training()
         if self.SR and torch.is_grad_enabled() and lr is not None and lr.is_cuda and (
                 any(p.requires_grad for p in self.parameters()) or lr.requires_grad):
             # inverse-path loss of the reference's training loop (HCFlow_SR_model.py:207-218): differentiable graph
             from . import autograd as ag
-            return ag.sr_reverse(self, lr, eps_std, eps)
+            with torch.cuda.device(lr.device):
+                return ag.sr_reverse(self, lr, eps_std, eps)
         lr_arg = lr
         lr = self._check(lr, "lr")
         B, _, h, w = lr.shape
@@ -159,7 +193,7 @@ class _HCFlowBase(nn.Module):
         same = self.reuse_lr_features and key == self._last_lr_key and self._last_lr_ref is lr_arg
         self._last_lr_key = key
         self._last_lr_ref = lr_arg if self.reuse_lr_features else None
-        with torch.cuda.device(lr.device):
+        with self._guard(), torch.cuda.device(lr.device):
             eng.ext["lr"].copy_(lr)
             self._draw_eps(eng, eps_std, eps, lr.device)
             eng.run(reuse_lr_features=same)
@@ -178,7 +212,7 @@ class _HCFlowBase(nn.Module):
             raise RuntimeError("hcflow_b200 runs on CUDA tensors only (no CPU fallback)")
         B, h, w, _ = lr_u8.shape
         eng = self.engine("reverse", B, h, w, lr_u8.device, io="u8" if bgr else "u8rgb")
-        with torch.cuda.device(lr_u8.device):
+        with self._guard(), torch.cuda.device(lr_u8.device):
             eng.ext["lr_u8"].copy_(lr_u8)
             self._draw_eps(eng, eps_std, eps, lr_u8.device)
             eng.run()
@@ -205,6 +239,7 @@ class HCFlowNet_SR(_HCFlowBase):
         return self._forward_nll(hr, lr, dequant_noise)
 
     def _forward_nll(self, hr, lr, dequant_noise):
+        self._refuse_replica_training()
         if torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or (hr is not None and hr.requires_grad)):
             # training (HCFlow_SR_model.py:184-203 optimize_parameters): the same ops as torch.autograd.Function
             # extensions with CUDA forward + backward kernels (hcflow_b200/autograd.py); the fused engine is inference-only
@@ -213,7 +248,8 @@ class HCFlowNet_SR(_HCFlowBase):
                 raise ValueError("hr and lr are required")
             if not hr.is_cuda:
                 raise RuntimeError("hcflow_b200 runs on CUDA tensors only (no CPU fallback)")
-            return ag.sr_forward_nll(self, hr.to(torch.float32), lr.to(torch.float32), dequant_noise)
+            with torch.cuda.device(hr.device):
+                return ag.sr_forward_nll(self, hr.to(torch.float32), lr.to(torch.float32), dequant_noise)
         hr = self._check(hr, "hr")
         lr = self._check(lr, "lr")
         B, _, H, W = hr.shape
@@ -223,7 +259,7 @@ class HCFlowNet_SR(_HCFlowBase):
         h, w = H // s, W // s
         assert tuple(lr.shape) == (B, 3, h, w), (tuple(lr.shape), (B, 3, h, w))
         eng = self.engine("forward", B, h, w, hr.device)
-        with torch.cuda.device(hr.device):
+        with self._guard(), torch.cuda.device(hr.device):
             eng.ext["hr"].copy_(hr)
             eng.ext["lr"].copy_(lr)
             if dequant_noise is None:
@@ -255,7 +291,7 @@ class HCFlowNet_Rescaling(_HCFlowBase):
         if H % s or W % s:
             raise ValueError("HR size {}x{} not divisible by {}".format(H, W, s))
         eng = self.engine("forward", B, H // s, W // s, hr.device)
-        with torch.cuda.device(hr.device):
+        with self._guard(), torch.cuda.device(hr.device):
             eng.ext["hr"].copy_(hr)
             eng.run()
             self.last = {"z_raw": eng.ext["z_raw"].clone()}

@@ -53,6 +53,7 @@ class Engine:
         self.use_graph = use_graph
         self.graph = None
         self._graphs = {}
+        self._capture_stream = None
         self._lr_features_valid = False
         self._keep = []          # ctypes structs must outlive the launches
         self._params = None
@@ -783,8 +784,14 @@ class Engine:
                                  "operand planes saturated; use tf32x3 / fp32 for these weights".format(self.precision))
 
     def run(self, reuse_lr_features=False):
-        """Run the plan on the current stream (inputs already in self.ext).  reuse_lr_features: skip the launches
-        that depend on the LR image alone (valid when ext["lr"] is the same image as in the previous run)."""
+        """Run the plan on the current stream of the engine's device (inputs already in self.ext).  reuse_lr_features:
+        skip the launches that depend on the LR image alone (valid when ext["lr"] is the same image as in the previous
+        run).  The engine's device is made current for the duration: a process that drives several GPUs (nn.DataParallel
+        threads, a net on cuda:1 while cuda:0 is current) must not launch, capture or allocate on the wrong one."""
+        with torch.cuda.device(self.device):
+            self._run(reuse_lr_features)
+
+    def _run(self, reuse_lr_features):
         assert not self.closed, "engine was evicted from the cache"
         self.check_status()
         if self.weight_signature() != self._sig:
@@ -800,7 +807,10 @@ class Engine:
                 self._launch_all(skip)
                 torch.cuda.current_stream(self.device).synchronize()
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                if self._capture_stream is None:
+                    # torch's default capture stream is created once per process, on whatever device was current then
+                    self._capture_stream = torch.cuda.Stream(device=self.device)
+                with torch.cuda.graph(g, stream=self._capture_stream):
                     self._launch_all(skip)
                 self._graphs[key] = g
             self._graphs[key].replay()

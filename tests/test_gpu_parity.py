@@ -1004,8 +1004,7 @@ def test_fp16_range_guard_raises_instead_of_returning_nans():
 
 def test_single_device_dataparallel_and_reference_model_wrapper_call():
     """The reference always wraps the net (HCFlow_SR_model.py:33-36): nn.DataParallel over ONE device runs the module
-    itself and must work; replication over several devices is refused with a clear error (one process per GPU is the
-    supported multi-GPU mode)."""
+    itself and must work (several devices: test_multi_gpu_dataparallel_inference_matches_one_gpu)."""
     opt, net, sd = _net_cuda("sr_x4", "f16x3")
     lr = synth.synthetic_lr(2, 8, 8, seed=2).cuda()
     dp = torch.nn.DataParallel(net, device_ids=[0])
@@ -1013,8 +1012,48 @@ def test_single_device_dataparallel_and_reference_model_wrapper_call():
         a = dp(lr=lr, z=None, u=None, eps_std=0.0, reverse=True, training=False)
         b = net(lr=lr, z=None, u=None, eps_std=0.0, reverse=True, training=False)
     assert torch.equal(a, b)
+
+
+def test_multi_gpu_dataparallel_inference_matches_one_gpu(report):
+    """The reference's default wrapper when several GPUs are visible and no launcher is used is nn.DataParallel over ALL
+    of them (HCFlow_SR_model.py:33-36), called under no_grad by test() (:296-316).  Replicas run through the master's
+    engine cache (one engine per device): the scattered batch gives the one-GPU result, for the inverse and for the
+    forward NLL (per-replica NLLs, which the reference averages), twice in a row (engine reuse).  Needs >= 2 GPUs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    opt, net, sd = _net_cuda("sr_x4", "f16x3")
+    B = 4
+    lr = synth.synthetic_lr(B, 16, 16, seed=2).cuda()
+    hr = synth.synthetic_hr(B, 64, 64, seed=3).cuda()
+    dq = torch.rand(hr.shape, generator=torch.Generator().manual_seed(5)).cuda()
+    unit = [e.cuda() for e in synth.synthetic_noise(net.noise_shapes(B, 16, 16), seed=9)]
+    dp = torch.nn.DataParallel(net, device_ids=[0, 1])
+    with torch.no_grad():
+        want = net(lr=lr, z=None, u=None, eps_std=0.8, reverse=True, training=False, eps=unit)
+        want_lr, want_nll = net(hr=hr, lr=lr, u=None, reverse=False, training=False, dequant_noise=dq)
+        for rep in range(2):
+            got = dp(lr=lr, z=None, u=None, eps_std=0.8, reverse=True, training=False, eps=unit)
+            got_lr, got_nll = dp(hr=hr, lr=lr, u=None, reverse=False, training=False, dequant_noise=dq)
+            assert got.device == lr.device and tuple(got.shape) == tuple(want.shape)
+            e1, e2 = float((got - want).abs().max()), float((got_lr - want_lr).abs().max())
+            e3 = abs(float(got_nll.mean()) - float(want_nll))
+            assert e1 < 1e-6 and e2 < 1e-6 and e3 < 1e-5 * abs(float(want_nll)), (e1, e2, e3)
+    assert len({k[4] for k in net._engines}) == 2          # one set of engines per device, all in the master's cache
+    # a net that lives on cuda:1 while cuda:0 is the current device (no DataParallel): same numbers, twice (graph replay)
+    net1 = build_net(opt)
+    net1.load_state_dict(net.state_dict(), strict=True)
+    net1 = net1.to("cuda:1").eval()
+    net1.set_precision("f16x3")
+    with torch.no_grad():
+        for rep in range(2):
+            o1 = net1(lr=lr.to("cuda:1"), eps_std=0.8, reverse=True, eps=[e.to("cuda:1") for e in unit])
+            l1, n1 = net1(hr=hr.to("cuda:1"), lr=lr.to("cuda:1"), reverse=False, dequant_noise=dq.to("cuda:1"))
+            assert o1.device.index == 1 and float((o1.cpu() - want.cpu()).abs().max()) < 1e-6
+            assert float((l1.cpu() - want_lr.cpu()).abs().max()) < 1e-6
+            assert abs(float(n1) - float(want_nll)) < 1e-5 * abs(float(want_nll)), (float(n1), float(want_nll))
     with pytest.raises(RuntimeError, match="one process per GPU"):
-        net._replicate_for_data_parallel()
+        dp(hr=hr, lr=lr, u=None, reverse=False)            # training through replicas is refused, loudly
+    report["dataparallel_2gpu"] = {"hr": e1, "fake_lr": e2, "nll_rel": e3 / abs(float(want_nll))}
 
 
 def test_batch_mean_nll_over_nccl_matches_the_oracle_mean(report):

@@ -256,12 +256,21 @@ def test_tf32_weight_image_layout(cout, kin, ks, passes):
     assert lib.hcf_conv_tc_weight_bytes(kin + 8, cout, ks, passes) == 0
 
 
-def test_replication_is_refused_and_load_state_dict_invalidates():
-    """CPU side of two ADVICE items: DataParallel replication raises a clear error (replicas carry no parameters),
-    load_state_dict bumps the weight epoch the engines' signature includes."""
+def test_dataparallel_replicas_share_the_master_and_load_state_dict_invalidates():
+    """CPU side of two ADVICE items.  nn.DataParallel replicas carry no Parameters: a replica remembers the module it
+    was copied from (its engine cache and weights), a replica of a replica still points at the root, training through a
+    replica is refused with a clear error; load_state_dict bumps the weight epoch the engines' signature includes."""
+    import torch
     opt, net, sd = net_and_weights("sr_x4")
+    rep = net._replicate_for_data_parallel()
+    assert rep._master() is net and net._master() is net
+    assert rep._replicate_for_data_parallel()._master() is net
+    assert rep._engines is net._engines and rep._stores is net._stores     # one cache, keyed by device
     with pytest.raises(RuntimeError, match="one process per GPU"):
-        net._replicate_for_data_parallel()
+        rep._refuse_replica_training()
+    with torch.no_grad():
+        rep._refuse_replica_training()          # inference through replicas is the supported case
+    net._refuse_replica_training()              # a plain module is never refused
     e0 = net._weights_epoch
     net.load_state_dict(sd, strict=True)
     assert net._weights_epoch == e0 + 1
