@@ -1014,6 +1014,24 @@ def test_single_device_dataparallel_and_reference_model_wrapper_call():
     assert torch.equal(a, b)
 
 
+def test_reference_model_wrapper_runs_its_own_test_loop_on_the_dropin():
+    """Drop-in, end to end: the UNMODIFIED reference's create_model(opt) -> HCFlowSRModel -> feed_data -> test()
+    (HCFlow_SR_model.py:296-316) -> get_current_visuals with hcflow_b200.install() as the only change (tests/
+    ref_model_worker.py, a subprocess because it puts the reference's packages on sys.path): the wrapper's NLL and every
+    (heat, sample) output equal the same calls made directly on the module with the same seed.  With several GPUs
+    visible the wrapper's DataParallel replicates over all of them (heat-0 outputs compared)."""
+    import os
+    import subprocess
+    import sys
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("unmodified reference not staged (oracle/build_ref.py)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "ref_model_worker.py"), root], capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout[-2000:] + out.stderr[-3000:]
+
+
 def test_multi_gpu_dataparallel_inference_matches_one_gpu(report):
     """The reference's default wrapper when several GPUs are visible and no launcher is used is nn.DataParallel over ALL
     of them (HCFlow_SR_model.py:33-36), called under no_grad by test() (:296-316).  Replicas run through the master's

@@ -189,6 +189,17 @@ def test_reference_factory_builds_the_dropin_after_install(tmp_path):
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference/codes"), reason="reference checkout not present")
+def test_reference_create_model_wraps_the_dropin():
+    """The reference's own model factory and wrapper (create_model -> HCFlowSRModel, which wraps the net in
+    nn.DataParallel and calls print_network / load) construct on top of the drop-in; the GPU half of this worker
+    (feed_data -> test() -> get_current_visuals) runs in tests/test_gpu_parity.py."""
+    worker = os.path.join(ROOT, "tests", "ref_model_worker.py")
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, worker, ROOT], capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0 and "OK" in out.stdout and "HCFlowSRModel" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
 @pytest.mark.parametrize("cout,kin,ks,split_kin", [(32, 64, 3, 0), (64, 192, 3, 64), (64, 192, 3, 192), (22, 64, 3, 0),
                                                    (64, 64, 1, 0)])
 def test_fp16_weight_image_layout(cout, kin, ks, split_kin):
