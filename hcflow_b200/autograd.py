@@ -364,10 +364,38 @@ def _cat(ts):
     return torch.cat(ts, dim=-1)        # channel concat on NHWC: data movement only
 
 
+def _actnorm_data_init(an, x):
+    """ActNorms.py:29-43 + :79-80, on an NHWC input: a not-yet-initialised ActNorm in TRAINING mode whose bias is still
+    all zero takes bias = -mean and logs = log(scale / (std + 1e-6)) of its input over (batch, pixels); a non-zero bias
+    counts as initialised (loaded weights); eval mode never initialises.  The reference's training loop clears `inited`
+    on every step below act_norm_start_step (HCFlow_SR_model.py:184-187), so on a net trained from scratch exactly the
+    first step initialises.  Parameter-side work on a few hundred channels: torch ops, like the reference."""
+    if an.inited or not an.training:
+        return
+    if bool((an.bias != 0).any()):
+        an.inited = True
+        return
+    with torch.no_grad():
+        xf = x.detach().to(torch.float32)
+        bias = -xf.mean(dim=(0, 1, 2))
+        var = ((xf + bias) ** 2).mean(dim=(0, 1, 2))
+        logs = torch.log(an.scale / (torch.sqrt(var) + 1e-6))
+        an.bias.data.copy_(bias.view_as(an.bias))
+        an.logs.data.copy_(logs.view_as(an.logs))
+        an.inited = True
+
+
+def _actnorm_conv(x, conv, act):
+    """Basic.py:49-53: bias-free conv, then its ActNorm (data-initialised on the conv's output when due), then act."""
+    y = Conv2dFn.apply(x, conv.weight)
+    _actnorm_data_init(conv.actnorm, y)
+    return AffineActFn.apply(y, conv.actnorm.bias, torch.exp(conv.actnorm.logs), act)
+
+
 def _fcn(x, f):
     """Basic.py:442-447 (ActNorm inside Conv2d: Basic.py:49-53)."""
-    h = _conv(x, f.conv1.weight, f.conv1.actnorm.bias, torch.exp(f.conv1.actnorm.logs), ACT_RELU)
-    h = _conv(h, f.conv2.weight, f.conv2.actnorm.bias, torch.exp(f.conv2.actnorm.logs), ACT_RELU)
+    h = _actnorm_conv(x, f.conv1, ACT_RELU)
+    h = _actnorm_conv(h, f.conv2, ACT_RELU)
     return _conv(h, f.conv3.weight, f.conv3.bias, torch.exp(f.conv3.logs * 3.0), ACT_NONE)
 
 
@@ -404,6 +432,7 @@ def _flow_step_forward(z, u, step, logdet):
     """FlowStep.normal_flow (FlowStep.py:40-51): ActNorm -> invconv -> affine coupling; logdet fp64 [B]."""
     B, H, W, Cc = z.shape
     pixels = H * W
+    _actnorm_data_init(step.actnorm, z)
     z = AffineActFn.apply(z, step.actnorm.bias, torch.exp(step.actnorm.logs), ACT_NONE)
     logdet = logdet + step.actnorm.logs.sum().double() * pixels
     if step.permute is not None:
@@ -478,6 +507,7 @@ def _flow_step_reverse(z, u, step):
         winv = torch.inverse(step.permute.weight.double()).float()
         z = Conv2dFn.apply(z, winv.view(Cc, Cc, 1, 1))
     # x * exp(-logs) - bias  ==  (x + (-bias * exp(logs))) * exp(-logs)      (ActNorms.py:90-93)
+    _actnorm_data_init(step.actnorm, z)     # (ActNorms.py:79-80 runs in either direction)
     logs, bias = step.actnorm.logs, step.actnorm.bias
     return AffineActFn.apply(z, -bias * torch.exp(logs), torch.exp(-logs), ACT_NONE)
 

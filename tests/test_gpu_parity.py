@@ -1032,6 +1032,26 @@ def test_reference_model_wrapper_runs_its_own_test_loop_on_the_dropin():
     assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout[-2000:] + out.stderr[-3000:]
 
 
+def test_reference_training_loop_and_actnorm_data_init_on_the_dropin():
+    """Training drop-in (tests/ref_train_worker.py, a subprocess): (1) ActNorm data initialisation (ActNorms.py:29-43) --
+    from zeroed ActNorm parameters, one train-mode forward of the UNMODIFIED reference net (stock PyTorch, fp32 convs)
+    and of this package's net leave the same ActNorm parameters, NLL and gradients; (2) the reference's own training
+    loop -- options.parse(train YAML) -> create_model -> HCFlowSRModel.optimize_parameters (HCFlow_SR_model.py:184-218:
+    NLL, backward, gradient clipping, Adam step) -- runs on hcflow_b200.install(), logs the NLL a direct evaluation
+    gives, and the loss goes down."""
+    import os
+    import subprocess
+    import sys
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("unmodified reference not staged (oracle/build_ref.py)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0] or "0")
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "ref_train_worker.py"), root], capture_output=True,
+                         text=True, timeout=900, env=env)
+    assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout[-3000:] + out.stderr[-3000:]
+
+
 def test_multi_gpu_dataparallel_inference_matches_one_gpu(report):
     """The reference's default wrapper when several GPUs are visible and no launcher is used is nn.DataParallel over ALL
     of them (HCFlow_SR_model.py:33-36), called under no_grad by test() (:296-316).  Replicas run through the master's
