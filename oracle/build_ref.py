@@ -18,6 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.environ.get("HCFLOW_REFERENCE", "/root/reference")
 DST = os.path.join(HERE, "_ref")
 SUBDIRS = ["codes/models", "codes/utils", "codes/options", "codes/data"]
+FILES = ["codes/test_HCFlow.py", "codes/train_HCFlow.py"]     # the reference's entry scripts (tests/ref_script_worker.py)
 
 
 def build(verbose=False):
@@ -33,8 +34,13 @@ def build(verbose=False):
         shutil.copytree(s, d, ignore=shutil.ignore_patterns("__pycache__", "*.pyc"))
         cmp = filecmp.dircmp(s, d, ignore=["__pycache__"])
         assert not cmp.diff_files and not cmp.left_only, (sub, cmp.diff_files, cmp.left_only)
+    for rel in FILES:
+        s = os.path.join(SRC, rel)
+        if os.path.isfile(s):
+            shutil.copyfile(s, os.path.join(DST, rel))
+            assert filecmp.cmp(s, os.path.join(DST, rel), shallow=False), rel
     with open(os.path.join(DST, "README"), "w") as f:
-        f.write("Unmodified copy of {}/codes/{{models,utils,options,data}} staged by oracle/build_ref.py.\n"
+        f.write("Unmodified copy of {}/codes/{{models,utils,options,data,test_HCFlow.py,train_HCFlow.py}} staged by oracle/build_ref.py.\n"
                 "Not tracked by git, not imported by the product.\n".format(SRC))
     if verbose:
         print("staged", DST)

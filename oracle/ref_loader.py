@@ -4,7 +4,8 @@ TEST / BENCH INFRASTRUCTURE.  /root/reference does not exist on the GPU box: the
 committed fixtures under tests/golden/; the bench's reference arm and the factory test use the unmodified copy that
 oracle/build_ref.py stages under oracle/_ref (git-ignored).  The reference's
 ``utils/util.py`` needs ``natsort`` and ``matplotlib`` at import time (SURVEY.md 8c);
-two three-line stubs under oracle/_stubs/ satisfy that.
+two three-line stubs under oracle/_stubs/ satisfy that (plus ``lpips`` / ``lmdb`` stand-ins for the
+reference's test script and dataset modules, which this image lacks).
 """
 import os
 import sys

@@ -1052,6 +1052,23 @@ def test_reference_training_loop_and_actnorm_data_init_on_the_dropin():
     assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout[-3000:] + out.stderr[-3000:]
 
 
+def test_reference_test_script_runs_unmodified_on_the_dropin(tmp_path):
+    """The UNMODIFIED reference script codes/test_HCFlow.py -- option parser, image-folder dataset + dataloader,
+    create_model, HCFlowSRModel.test(), tensor2img, PSNR / SSIM, PNG writer -- on a generated two-image dataset and a
+    synthetic checkpoint, with hcflow_b200.install() as the only addition (tests/ref_script_worker.py, a subprocess; lpips
+    and lmdb, which this image lacks, are import-time stubs): the PNGs it writes are the images the module computes."""
+    import os
+    import subprocess
+    import sys
+    from oracle import ref_loader
+    if not ref_loader.available() or not os.path.isfile(os.path.join(ref_loader.REF_CODES, "test_HCFlow.py")):
+        pytest.skip("unmodified reference script not staged (oracle/build_ref.py)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "ref_script_worker.py"), root, str(tmp_path)],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout[-3000:] + out.stderr[-3000:]
+
+
 def test_multi_gpu_dataparallel_inference_matches_one_gpu(report):
     """The reference's default wrapper when several GPUs are visible and no launcher is used is nn.DataParallel over ALL
     of them (HCFlow_SR_model.py:33-36), called under no_grad by test() (:296-316).  Replicas run through the master's
