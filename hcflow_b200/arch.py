@@ -16,6 +16,7 @@ After a call ``net.last`` holds the un-clamped tensors (hr_raw / z_raw / logdet 
 import collections
 import contextlib
 import math
+import os
 import threading
 
 import torch
@@ -40,7 +41,11 @@ class _HCFlowBase(nn.Module):
         hr_size = opt_get(opt, ["datasets", "train", "GT_size"], 160)
         hr_channel = opt_get(opt, ["network_G", "in_nc"], 3)
         self.flow = M.FlowNet((hr_size, hr_size, hr_channel), opt, SR=self.SR)
-        self.precision = "fp32"
+        # arithmetic of the inference engine: the validated default is "f16x3" (fp16 hi / lo operand planes, 2e-4
+        # max-abs parity tolerance on the un-clamped HR); HCFLOW_PRECISION picks another mode for
+        # callers that never see the module (the reference's scripts after install()); set_precision() at run time
+        self.precision = os.environ.get("HCFLOW_PRECISION", "f16x3")
+        assert self.precision in ("fp32", "tf32", "tf32x3", "tf32x3_all", "f16", "f16x3"), self.precision
         self.use_graph = True
         self.use_chains = True   # fuse runs of tensor-core convs into one persistent chained launch
         self.share_cond = True   # tensor-core modes: the sub-nets' shared conditioning conv once per level (engine.py)
