@@ -206,6 +206,27 @@ class _HCFlowBase(nn.Module):
             return eng.ext["hr"].clone()
 
 
+    def sample_many(self, lr, heats, n_sample=1):
+        """All samples of one LR batch in ONE pass: what the reference's test loop computes with
+        len(heats) * n_sample separate calls (HCFlow_SR_model.py:308-312: for heat: for sample: netG(lr, eps_std=heat,
+        reverse=True)).  The LR batch is replicated along the batch axis, every replica gets its own heat, and the noise is
+        drawn slice by slice in the loop's order (heat-major, then sample, deepest level first), so a seeded call returns
+        exactly the tensors the loop returns.  Returns {(heat, sample): clamp(fake_hr) [B,3,H,W]}."""
+        lr = self._check(lr, "lr")
+        heats = [float(h) for h in heats]
+        B, _, h, w = lr.shape
+        combos = [(ht, i) for ht in heats for i in range(int(n_sample))]
+        eng = self.engine("reverse", B * len(combos), h, w, lr.device)
+        with self._guard(), torch.cuda.device(lr.device):
+            eng.ext["lr"].copy_(lr.repeat(len(combos), 1, 1, 1))
+            for k, (ht, _) in enumerate(combos):                  # the reference's draw order
+                for i in range(len(eng.plan.noise_shapes)):
+                    eng.ext["eps{}".format(i)][k * B:(k + 1) * B].normal_(0.0, 1.0).mul_(ht)
+            eng.run()
+            hr = eng.ext["hr"]
+            self.last = {"hr_raw": eng.ext["hr_raw"].clone()}
+            return {c: hr[k * B:(k + 1) * B].clone() for k, c in enumerate(combos)}
+
     def sample_uint8(self, lr_u8, eps_std=None, eps=None, bgr=True):
         """Inverse pass on 8-bit images: lr_u8 uint8 [B,h,w,3] as cv2 / the LMDB reader deliver it (HWC, BGR
         unless bgr=False) -> uint8 [B,H,W,3] in the same convention.  Replaces, on the device, the reference's

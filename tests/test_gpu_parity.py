@@ -717,6 +717,39 @@ def test_uint8_image_edges_match_the_reference_conversions():
     assert np.array_equal(got, want), int(np.abs(got.astype(int) - want.astype(int)).max())
 
 
+def test_sample_many_equals_the_reference_test_loop(report):
+    """SURVEY 8f-2, third bullet: all heats x n_sample samples of one LR batch as ONE pass.  With the same seed it returns
+    exactly the tensors of the reference's loop (HCFlow_SR_model.py:308-312: one call per heat and sample, noise drawn in
+    that order), and it is faster than the loop."""
+    opt, net, sd = _net_cuda("sr_x4", "f16x3")
+    lr = synth.synthetic_lr(1, 40, 40, seed=8).cuda()
+    heats, n_sample = [0.0, 0.8, 0.9], 2
+    with torch.no_grad():
+        torch.manual_seed(3)
+        loop = {(ht, i): net(lr=lr, z=None, u=None, eps_std=ht, reverse=True, training=False) for ht in heats for i in range(n_sample)}
+        torch.manual_seed(3)
+        many = net.sample_many(lr, heats, n_sample)
+        assert sorted(many) == sorted(loop)
+        for k in loop:
+            assert torch.equal(many[k], loop[k]), (k, float((many[k] - loop[k]).abs().max()))
+        assert not torch.equal(many[(0.8, 0)], many[(0.8, 1)])
+
+        def timed(fn, n=5):
+            fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / n
+        t_loop = timed(lambda: [net(lr=lr, eps_std=ht, reverse=True) for ht in heats for _ in range(n_sample)])
+        t_many = timed(lambda: net.sample_many(lr, heats, n_sample))
+    report["sample_many"] = {"loop_ms": t_loop, "one_pass_ms": t_many, "samples": len(loop)}
+    assert t_many < t_loop, (t_many, t_loop)
+
+
 def test_lr_feature_reuse_is_bit_identical(report):
     """net.reuse_lr_features: sampling the same LR tensor again skips the deepest level's encoder chain
     and must give exactly the bits of a full run with the same noise; a new LR tensor triggers a full run."""
