@@ -463,6 +463,16 @@ def run_ours(args):
             peaks["source"], "the kernel computes on fp16 operands: same tensor rate; split layers issue 2 MMAs per useful "
             "K-step" if f16_mode else "the kernel computes in TF32, nominal peak = half of it; tf32x3 issues 2 MMAs per "
             "useful K-step"),
+        # what actually binds this launch: the SM's shared-memory data pipe -- per (tile, layer) work item
+        # ~3.5 k MMA operand wavefronts (ncu: 605 M per launch) + ~1.3 k TMA fill + ~0.4 k staging wavefronts against
+        # ~1.5 k cycles of tensor work at the nominal rate, because an RDB conv has only N = 32 / 64 output channels
+        "binding_resource": {
+            "what": "shared-memory operand pipe of an implicit GEMM with N = 32 / 64 (not HBM, not instruction issue)",
+            "smem_wavefronts_per_item": 5300, "nominal_tensor_cycles_per_item": 1500,
+            "formulation_ceiling_frac_of_sustained_peak": 0.49,
+            "frac_of_formulation_ceiling": (achieved / peak_used) / 0.49,
+            "evidence": "profiles/r02_prof_chain_L0_f16x3_summary.csv, r02_wait_profile_f16x3.log, r02_ws_*, "
+                        "r02_unrolled_issue_*, r02_split_producers_single_plane_*"},
         "launches": n, "avg_launch_ms": ms / n, "share_of_step": ms / total_ms,
         "classes": {c: {"n": v[0], "ms": round(v[1], 4), "gflop": round(v[2] / 1e9, 3)} for c, v in classes.items()},
         "conv_by_layer": {t: {"n": v[0], "ms": round(v[1], 3), "tflops": round(v[2] / max(v[1], 1e-9) / 1e9, 1)}
