@@ -677,6 +677,31 @@ def test_prior_draw_consumes_the_reference_rng_stream():
     assert torch.equal(got, want) and torch.equal(got2, want2)
 
 
+def test_large_ragged_image_default_mode_against_the_fp32_path(report):
+    """A realistic single image (LR 250x182 -> HR 1000x728, B=1: 16 x 46 and 32 x 91 partly filled tiles per layer at
+    the two levels, ~5 GB of activations, the forward pass on top): the default tensor-core mode against the exact-fp32
+    CUDA-core kernels of this package (an independent code path: no TMA, no chains, no fp16 planes), which the small
+    cases pin to the oracle.  Inverse, then forward NLL of the sampled HR (consistency: fake_lr reproduces lr)."""
+    opt, net, sd = _net_cuda("sr_x4", "f16x3")
+    B, h, w = 1, 182, 250
+    lr = synth.synthetic_lr(B, h, w, seed=31).cuda()
+    unit = synth.synthetic_noise(net.noise_shapes(B, h, w), seed=32)
+    with torch.no_grad():
+        hr = net(lr=lr, eps_std=0.8, reverse=True, eps=unit)
+        raw = net.last["hr_raw"].clone()
+        fake_lr, nll = net(hr=raw, lr=lr, reverse=False, dequant_noise=torch.zeros_like(raw))
+        net.set_precision("fp32")
+        net(lr=lr, eps_std=0.8, reverse=True, eps=unit)
+        want = net.last["hr_raw"].clone()
+    err = float((raw - want).abs().max())
+    back = float((fake_lr - lr.clamp(0, 1)).abs().max())
+    report["large_ragged_250x182"] = {"hr_raw_vs_fp32_path": err, "forward_of_sample_reproduces_lr": back,
+                                      "range": [float(want.min()), float(want.max())]}
+    assert tuple(hr.shape) == (1, 3, 4 * h, 4 * w) and torch.isfinite(raw).all() and math.isfinite(float(nll))
+    assert err < 8e-5, err
+    assert back < 1.0 / 255 + 1e-4, back        # the forward pass quantises fake_lr to 8 bits (Basic.py:186-198)
+
+
 @pytest.mark.parametrize("precision,tol", [("f16x3", 6e-5), ("tf32x3", 2e-4), ("f16", 6e-3)])
 def test_ragged_size_against_oracle(precision, tol, report):
     """LR 12x20 (HR 48x80): every level has partial tiles in both directions (16x8 pixel tiles), B=3 is not a
