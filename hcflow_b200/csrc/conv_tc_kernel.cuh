@@ -810,6 +810,8 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
     int out_ld = 0, out2_ld = 0, res1_ld = 0, res2_ld = 0;
     bool has_bias = false, has_scale = false;
     int fast = 0;   // straight-line store path: bit0 fp32, bit1 hi plane, bit2 lo plane (0 = generic path)
+    bool direct_hi = false;
+    const bool getenv_direct = !(p.debug & 512);   // (HCF_TC_DEBUG=512 switches the direct path off: A/B timing)
     float* out = nullptr; float* out2 = nullptr;
     const float* res1 = nullptr; const float* res2 = nullptr;
     float alpha1 = 0.f, alpha2 = 0.f;
@@ -858,6 +860,9 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
         if (out_vec && cout % 32 == 0 && out2 == nullptr && o16.hi2 == nullptr && o16.lo2 == nullptr &&
             (o16.lo == nullptr || o16.hi != nullptr))
           fast = (out ? 1 : 0) | (o16.hi ? 2 : 0) | (o16.lo ? 4 : 0);
+        // hi plane only, no residual / addend / raw partial sums, one pass, 16-byte aligned rows: direct stores
+        direct_hi = F16 && fast == 2 && res1 == nullptr && res2 == nullptr && raw2 == nullptr && parts == 1 &&
+                    !(STEP && step_z) && out_ld % 8 == 0 && getenv_direct;
         asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");   // everyone is done with the previous layer's bias / scale
         s_bias[et] = __ldg(p.epi + (size_t)layer * 256 + et);          // inline table: no pointer chase
         s_scale[et] = __ldg(p.epi + (size_t)layer * 256 + 128 + et);
@@ -987,6 +992,47 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
               }
             }
             __syncwarp();
+            continue;
+          }
+          if (F16 && direct_hi && !(p.debug & 8)) {
+            // ---- hi-plane-only layers without residuals (an RDB's growth convs: four of five items): no staging
+            // transpose -- the thread keeps its pixel, applies bias / scale / activation to its 32 accumulator columns and
+            // writes the pixel's 64 contiguous bytes of the hi plane with four 16-byte stores (both 32-byte sectors are
+            // completed by the same thread).  ~170 instead of ~860 warp-instructions per item and no shared-memory
+            // traffic for the transpose.
+            const int mm = q * 32 + lane;
+            const int gy = y0 + mt * TH + mm / TW, gx = x0 + mm % TW;
+            const bool in = gy < p.H && gx < p.W;
+            __half* dst = o16.hi + ((size_t)((b * p.H + (in ? gy : 0)) * p.W + (in ? gx : 0)) * (size_t)out_ld + c0);
+            const float slope = act == HCF_ACT_RELU ? 0.f : (act == HCF_ACT_LRELU ? 0.2f : 1.f);
+            float amax = 0.f;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              float v[16];
+              const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (acc * MT + mt) * p.nb_max + (uint32_t)(c0 + h * 16);
+              tmem_ld16(tcol, v);
+              if (h == 1 && mt == MT - 1 && c0 + 32 >= N) {   // last TMEM read of the item
+                tc_fence_before();
+                mbar_arrive(tmem_empty(acc));
+              }
+              uint32_t pk[8];
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                float a0 = (v[j] + s_bias[c0 + h * 16 + j]) * s_scale[c0 + h * 16 + j];
+                float a1 = (v[j + 1] + s_bias[c0 + h * 16 + j + 1]) * s_scale[c0 + h * 16 + j + 1];
+                a0 = fmaxf(a0, slope * a0); a1 = fmaxf(a1, slope * a1);
+                amax = fmaxf(amax, fmaxf(fabsf(a0), fabsf(a1)));
+                if (!(fabsf(a0) <= 65504.0f)) a0 = fminf(fmaxf(a0, -65504.0f), 65504.0f);
+                if (!(fabsf(a1) <= 65504.0f)) a1 = fminf(fmaxf(a1, -65504.0f), 65504.0f);
+                const __half2 hh = __floats2half2_rn(a0, a1);
+                pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+              }
+              if (in) {
+                __stcg(reinterpret_cast<uint4*>(dst + h * 16), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+                __stcg(reinterpret_cast<uint4*>(dst + h * 16 + 8), make_uint4(pk[4], pk[5], pk[6], pk[7]));
+              }
+            }
+            if (in && !(amax <= 65504.0f) && p.status) atomicOr(p.status, STATUS_F16_OVERFLOW);
             continue;
           }
           // ---- row domain (thread = pixel): TMEM accumulator -> staging (transpose through shared memory)
