@@ -1,7 +1,6 @@
 #!/bin/bash
-# A/B of a per-item-kernel change: per-launch times (HCF_TC_DEBUG=512 switches the direct hi-plane stores off), parity tests
+# A/B of a per-item-kernel change: per-launch times (HCF_TC_DEBUG=512 switches the direct hi-plane stores off), parity
 mkdir -p gpurun_out
-for d in 0 512; do HCF_TC_DEBUG=$d timeout -k 5 120 python tools/launch_times.py f16x3 2>&1 | grep -v CUDAEvent | tail -1 | python -c "
+for d in 0 512 0; do HCF_TC_DEBUG=$d timeout -k 5 120 python tools/launch_times.py f16x3 2>&1 | grep -v CUDAEvent | tail -1 | python -c "
 import sys,json
 d=json.loads(sys.stdin.read()); print(d['debug'], {k[:34]:v for k,v in d['ms'].items() if 'chain16' in k or k=='total'})"; done | tee gpurun_out/v1_times.log
-timeout -k 5 400 python -m pytest tests/test_gpu_parity.py -m gpu -q -x --timeout 90 -k "chain16 or config1 or tcgen05 or chained_launch or tensor_core_modes or fcn_as_one or stress_fixture_reverse or ragged" 2>&1 | grep -v CUDAEvent | tail -3 | cut -c1-400 | tee gpurun_out/pytest_v1.log
