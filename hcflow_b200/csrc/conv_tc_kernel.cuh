@@ -122,7 +122,7 @@ struct Params {
   int slot_bytes;     // bytes of one B ring slot
   int debug;          // timing experiments only (HCF_TC_DEBUG, wrong results): 1 aligned A descriptors,
                       // 2 no MMAs, 4 no loads, 8 no epilogue stores, 16 launch only, 32 prologue only,
-                      // 64 no dependency waits
+                      // 64 no dependency waits, 128 no FlowStep arithmetic, 512 direct hi-plane stores off
   const LayerDesc* layers;
   int* done;          // chain mode: per-tile count of completed layers (zeroed before the launch)
   const float* epi;   // [n_layers][256]: bias (0) | scale (1) of every layer, padded: one coalesced load per layer change
