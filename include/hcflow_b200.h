@@ -161,7 +161,11 @@ int hcf_conv_chain_create(const hcf_conv_args* args, const float* const* wtc, co
  * the fp32 view (residual sources and anything read outside the chain), the hi plane, the lo plane.
  * Inputs that no chain conv produced must be converted first (hcf_split16).  w16[i] comes from
  * hcf_conv_tc16_pack_weights with the same `passes`; the input-channel axis is padded per segment to
- * multiples of 64.  Returns HCF_ENOTSUP when a conv of the chain does not qualify (ld % 8, alignment). */
+ * multiples of 64.  Returns HCF_ENOTSUP when a conv of the chain does not qualify (ld % 8, alignment).
+ * Scheduling: work items (tile, layer) rotate over the persistent CTAs.  HCF_TC_WS=1 in the environment at plan creation
+ * selects the weight-stationary schedule instead (csrc/conv_ws_kernel.cuh: a CTA owns up to three tiles per image group
+ * and fetches every weight slab once per group pass) for 3x3 chains with B >= 2 whose accumulators fit its TMEM slots;
+ * same results to fp32 rounding, measured slower on the encoder chains of configs[1], opt-in. */
 typedef struct {
   const float* f32;  /* base of the fp32 buffer */
   int64_t bytes;     /* its size */
