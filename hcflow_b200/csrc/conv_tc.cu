@@ -50,7 +50,9 @@ static bool pick_rings(int mt, int passes, int ks, int NB, int extra, int* sa, i
 
 typedef void (*KernelFn)(const Maps, const Params);
 
-static KernelFn pick_kernel(int mt, int passes, int ks, bool f16, bool step) {
+static KernelFn pick_kernel(int mt, int passes, int ks, bool f16, bool step, bool direct) {
+  if (f16 && !step && ks == 3 && direct)   // a layer of the chain qualifies for the direct hi-plane stores
+    return passes == 3 ? conv_tc_kernel<1, 3, 3, true, false, true> : conv_tc_kernel<1, 1, 3, true, false, true>;
   if (step) {   // fused FlowStep layers: 3x3 chains, MT = 1 (chain_create enforces both)
     if (f16) return passes == 3 ? conv_tc_kernel<1, 3, 3, true, true> : conv_tc_kernel<1, 1, 3, true, true>;
     return passes == 3 ? conv_tc_kernel<1, 3, 3, false, true> : conv_tc_kernel<1, 1, 3, false, true>;
@@ -649,7 +651,14 @@ static int chain_create(const hcf_conv_args* args, const void* const* wtc, const
     set_error("tc_chain: fused FlowStep layers need a 3x3 chain");
     return HCF_ENOTSUP;
   }
-  pl->fn = use_ws ? conv_ws_kernel : pick_kernel(mt, passes, ks, f16, tail_extra != 0);
+  bool any_direct = false;   // (mirrors the kernel's per-layer test: hi plane only, no residual / addend, one pass)
+  for (int i = 0; i < n && f16; ++i) {
+    const LayerDesc& L = layers[i];
+    if (L.out_hi && !L.out_lo && !L.out && !L.out2 && !L.out2_hi && !L.out2_lo && !L.res1 && !L.res2 && !L.pre && !L.raw2 &&
+        !L.step_z && L.parts == 1 && L.out_vec && L.cout % 32 == 0 && L.out_ld % 8 == 0)
+      any_direct = true;
+  }
+  pl->fn = use_ws ? conv_ws_kernel : pick_kernel(mt, passes, ks, f16, tail_extra != 0, any_direct);
   e = cudaFuncSetAttribute(reinterpret_cast<const void*>(pl->fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
                            SMEM_LIMIT);
   if (e != cudaSuccess) {

@@ -467,7 +467,9 @@ __device__ __forceinline__ bool deps_ready(const Deps& d, int layer) {
 // F16: operands are fp16 (hi / lo planes, 64 channels per 128-byte row, kind::f16); otherwise fp32 words read as TF32.
 // STEP: the chain contains fused FlowStep layers (only those variants carry the per-pixel FlowStep code: its
 // registers cost the encoder kernels 4 % when it was compiled into all of them).
-template <int MT, int PASSES, int KS, bool F16, bool STEP = false>
+// DIRECT: the variant carries the direct fp16-plane store path of the epilogue (chains with hi-plane-only layers, i.e.
+// the RRDB encoder chains); the other chains keep the smaller binary -- code growth in one role costs every role.
+template <int MT, int PASSES, int KS, bool F16, bool STEP = false, bool DIRECT = false>
 __global__ void __launch_bounds__(F16 ? 384 : (PASSES == 3 ? 320 : 192), 1)
 conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
   constexpr int HALO = KS / 2;
@@ -861,7 +863,7 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
             (o16.lo == nullptr || o16.hi != nullptr))
           fast = (out ? 1 : 0) | (o16.hi ? 2 : 0) | (o16.lo ? 4 : 0);
         // hi plane only, no residual / addend / raw partial sums, one pass, 16-byte aligned rows: direct stores
-        direct_hi = F16 && fast == 2 && res1 == nullptr && res2 == nullptr && raw2 == nullptr && parts == 1 &&
+        direct_hi = DIRECT && F16 && fast == 2 && res1 == nullptr && res2 == nullptr && raw2 == nullptr && parts == 1 &&
                     !(STEP && step_z) && out_ld % 8 == 0 && getenv_direct;
         asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");   // everyone is done with the previous layer's bias / scale
         s_bias[et] = __ldg(p.epi + (size_t)layer * 256 + et);          // inline table: no pointer chase
@@ -994,7 +996,7 @@ conv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
             __syncwarp();
             continue;
           }
-          if (F16 && direct_hi && !(p.debug & 8)) {
+          if (DIRECT && F16 && direct_hi && !(p.debug & 8)) {
             // ---- hi-plane-only layers without residuals (an RDB's growth convs: four of five items): no staging
             // transpose -- the thread keeps its pixel, applies bias / scale / activation to its 32 accumulator columns and
             // writes the pixel's 64 contiguous bytes of the hi plane with four 16-byte stores (both 32-byte sectors are
