@@ -287,3 +287,18 @@ def test_dataparallel_replicas_share_the_master_and_load_state_dict_invalidates(
     assert net._weights_epoch == e0 + 1
     net.invalidate_weights()
     assert net._weights_epoch == e0 + 2
+
+
+def test_default_precision_is_the_validated_mode_and_env_overrides_it(monkeypatch):
+    """A drop-in user never calls set_precision: the module default is the validated tensor-core mode (f16x3), and
+    HCFLOW_PRECISION picks another one for callers that only see the reference's scripts."""
+    from hcflow_b200 import options
+    from hcflow_b200.arch import build_net
+    opt = options.shrink_config(options.load_config("sr_x4"), K=4, after=[2, 2], rrdb_nb=[1, 1])
+    monkeypatch.delenv("HCFLOW_PRECISION", raising=False)
+    assert build_net(opt).precision == "f16x3"
+    monkeypatch.setenv("HCFLOW_PRECISION", "fp32")
+    assert build_net(opt).precision == "fp32"
+    monkeypatch.setenv("HCFLOW_PRECISION", "bogus")
+    with pytest.raises(AssertionError):
+        build_net(opt)
